@@ -1,0 +1,22 @@
+"""ORACLE support (test infrastructure): the small synthetic cases shared by make_golden.py and tests/."""
+from oracle import rsa_oracle as O
+
+CASES = {
+    # name: (family, grid(t,h,w), text_len, num_true_delta, heads, top_k, p, regime, seed)
+    "wan_c1": ("wan", (4, 16, 16), 0, 0, 2, 2, 0.3, "walk", 1),
+    "wan_ragged": ("wan", (3, 10, 13), 0, 0, 2, 1, 0.3, "walk", 2),
+    "wan_iid": ("wan", (4, 16, 16), 0, 0, 2, 3, 0.5, "iid", 3),
+    "hunyuan_small": ("hunyuan", (4, 16, 16), 256, 200, 2, 2, 0.3, "walk", 4),
+    "hunyuan_fulltext": ("hunyuan", (2, 16, 16), 256, 256, 2, 1, 0.3, "cluster", 5),
+    "flux_small": ("flux", (1, 32, 32), 512, 512, 2, 1, 0.3, "walk", 6),
+    "cog_small": ("cogvideo", (4, 16, 16), 226, 226, 2, 2, 0.3, "walk", 7),
+    "hunyuan_mid": ("hunyuan", (8, 16, 32), 256, 77, 2, 6, 0.3, "walk", 8),
+}
+
+
+def case_inputs(name):
+    fam, (t, h, w), text_len, ntrue_d, heads, top_k, p, regime, seed = CASES[name]
+    nv = t * h * w
+    s = nv + text_len
+    q, k, v = O.synth_qkv(heads, s, 128, regime, seed)
+    return fam, (t, h, w), nv, s, text_len, ntrue_d, heads, top_k, p, q, k, v

@@ -1,0 +1,224 @@
+"""ORACLE support (test infrastructure): generate tests/golden/*.npz|json by running the UNMODIFIED reference
+(/root/reference) on CPU in the build container.  Re-run with `python -m oracle.make_golden`.
+
+What is recorded (inputs are regenerated from seeds by oracle.rsa_oracle.synth_qkv, so only outputs are stored):
+  gilbert.json        linear_to_hilbert / hilbert_to_linear / neighbour matrices of utils/jenga_gilbert.py
+                      (full arrays for small grids, SHA-1 digests for the BASELINE.json grids)
+  mask_<case>.npz     outputs of each family's _build_block_index_with_importance_optimized run on fp32 CPU
+                      tensors (one_hot mask, probs, nogapr) captured from inside block_sparse_attention_combined,
+                      the rectification factors R and C recovered from the same call, and the visual-row output
+  kernel_fp16.npz     the literal Triton kernel (_triton_block_sparse_attention_onehot) under TRITON_INTERPRET=1
+                      in fp16 on a random block mask (the interpreter has no bf16)
+
+Stand-ins for third-party pieces that cannot run on CPU (named so the goldens stay honest):
+  * flash_attn_varlen_func (flash-attn, unpinned in the reference README; 2.8.3 here) -> per-sequence dense softmax
+  * the Triton kernel inside the *combined* call -> dense masked softmax (its literal semantics are pinned
+    separately by kernel_fp16.npz)
+"""
+from __future__ import annotations
+
+import os
+
+os.environ.setdefault("TRITON_INTERPRET", "1")
+
+import contextlib
+import hashlib
+import json
+import sys
+
+import numpy as np
+import torch
+
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, _REPO)
+
+from oracle import ref_loader  # noqa: E402
+from oracle import rsa_oracle as O  # noqa: E402
+
+GOLD = os.path.join(_REPO, "tests", "golden")
+
+
+def sha(a):
+    return hashlib.sha1(np.ascontiguousarray(a).tobytes()).hexdigest()[:16]
+
+
+# ------------------------------------------------------------------------------------------------ gilbert
+SMALL_GRIDS = [(4, 16, 16), (3, 5, 7), (2, 6, 10), (1, 16, 16), (5, 6, 4), (2, 3, 130), (1, 1, 9)]
+BIG_GRIDS = [(21, 30, 52), (21, 45, 80), (32, 45, 80), (33, 45, 80), (1, 256, 256), (11, 48, 80)]
+
+
+def make_gilbert(big=True):
+    g = ref_loader.load(["jenga_gilbert"])["jenga_gilbert"]
+    out = {"small": [], "big": []}
+    for (t, h, w) in SMALL_GRIDS:
+        with ref_loader.quiet():
+            l2h, h2l = g.gilbert_mapping(t, h, w)
+            nbr = g.gilbert_block_neighbor_mapping(t, h, w)
+        out["small"].append(dict(grid=[t, h, w], l2h=list(map(int, l2h)), h2l=list(map(int, h2l)),
+                                 nbr=np.packbits(nbr.numpy().astype(np.uint8)).tolist(),
+                                 nbr_shape=list(nbr.shape)))
+        # alternative axis order exercised by the same code path
+        with ref_loader.quiet():
+            l2h2, h2l2 = g.gilbert_mapping(t, h, w, axis_order=("t", "h", "w"))
+        out["small"][-1]["h2l_thw"] = list(map(int, h2l2))
+    if big:
+        for (t, h, w) in BIG_GRIDS:
+            with ref_loader.quiet():
+                l2h, h2l = g.gilbert_mapping(t, h, w)
+                nbr = g.gilbert_block_neighbor_mapping(t, h, w)
+            out["big"].append(dict(grid=[t, h, w], sha_h2l=sha(np.asarray(h2l, dtype=np.int64)),
+                                   sha_l2h=sha(np.asarray(l2h, dtype=np.int64)),
+                                   sha_nbr=sha(nbr.numpy().astype(np.uint8)), nbr_nnz=int(nbr.sum()),
+                                   h2l_head=list(map(int, h2l[:6]))))
+            print("gilbert", (t, h, w), out["big"][-1]["sha_h2l"], flush=True)
+    with open(os.path.join(GOLD, "gilbert.json"), "w") as f:
+        json.dump(out, f)
+
+
+# ------------------------------------------------------------------------------------- mask builder + R, C
+def _varlen_dense(q, k, v, cu_q, cu_k):
+    """Stand-in for flash_attn_varlen_func on [(tokens), H, D] tensors."""
+    out = torch.zeros_like(q)
+    for i in range(len(cu_q) - 1):
+        q0, q1, k0, k1 = int(cu_q[i]), int(cu_q[i + 1]), int(cu_k[i]), int(cu_k[i + 1])
+        if q1 <= q0:
+            continue
+        qi = q[q0:q1].transpose(0, 1).float()
+        ki = k[k0:k1].transpose(0, 1).float()
+        vi = v[k0:k1].transpose(0, 1).float()
+        s = (qi @ ki.transpose(1, 2)) * (q.shape[-1] ** -0.5)
+        out[q0:q1] = (torch.softmax(s, -1) @ vi).transpose(0, 1).to(q.dtype)
+    return out
+
+
+def _dense_masked_kernel(q, k, v, seqlens, block_mask, sm_scale, bm=128, bn=128):
+    """Stand-in for the Triton launch inside the combined call (dense masked softmax, fp32)."""
+    b, h, s, d = q.shape
+    out = torch.zeros_like(q)
+    for bi in range(b):
+        for hi in range(h):
+            o = O.masked_attention(q[bi, hi].float().numpy(), k[bi, hi].float().numpy(), v[bi, hi].float().numpy(),
+                                   block_mask[bi, hi].numpy(), int(seqlens[bi]), s)
+            out[bi, hi] = torch.from_numpy(o).to(q.dtype)
+    return out
+
+
+from oracle.cases import CASES, case_inputs  # noqa: E402
+
+
+def run_reference_case(name):
+    fam, (t, h, w), nv, s, text_len, ntrue_d, heads, top_k, p, q, k, v = case_inputs(name)
+    modname = {"wan": "rectified_wan21_attn", "hunyuan": "rectified_hunyuan_attn", "flux": "rectified_flux_attn",
+               "cogvideo": "rectified_cogvideo_attn"}[fam]
+    mods = ref_loader.load([modname, "jenga_gilbert"])
+    ref, g = mods[modname], mods["jenga_gilbert"]
+    with ref_loader.quiet():
+        nbr = g.gilbert_block_neighbor_mapping(t, h, w)
+    cap = {}
+    orig_build = ref._build_block_index_with_importance_optimized
+
+    def build_spy(*a, **kw):
+        r = orig_build(*a, **kw)
+        cap["mask"], cap["probs"], cap["nogapr"] = [x.clone() for x in r]
+        return r
+
+    def fullattn_cpu(q_, k_, v_, mode, drop_rate=0, attn_mask=None, causal=False, cu_seqlens_q=None,
+                     cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None, batch_size=1):
+        pre = lambda x: x.transpose(1, 2).reshape(x.shape[0] * x.shape[2], x.shape[1], x.shape[3])
+        x = _varlen_dense(pre(q_), pre(k_), pre(v_), cu_seqlens_q, cu_seqlens_kv)
+        x = x.view(batch_size, max_seqlen_q, x.shape[-2], x.shape[-1])
+        return x.transpose(1, 2)
+
+    ref._build_block_index_with_importance_optimized = build_spy
+    ref.fullattn = fullattn_cpu
+    tq, tk, tv = (torch.from_numpy(x) for x in (q, k, v))
+    ffb = (nv + 127) // 128 // t if fam == "wan" else None
+    num_true = nv + ntrue_d
+
+    def call(kernel):
+        ref._triton_block_sparse_attention_onehot = kernel
+        kq, kk, kv_ = tq.clone(), tk.clone(), tv.clone()
+        if fam == "wan":
+            return ref.rectified_block_sparse_attention(kq, kk, kv_, None, top_k, block_neighbor_list=nbr,
+                                                        p_remain_rates=p, first_frame_blocks=ffb)
+        if fam == "hunyuan":
+            am = torch.zeros(1, 1, 1, s, dtype=torch.bool)
+            am[..., :num_true] = True
+            cu = torch.tensor([0, num_true, s], dtype=torch.int32)
+            return ref.rectified_block_sparse_attention(kq, kk, kv_, am, top_k, cu_seqlens_q=cu, cu_seqlens_kv=cu,
+                                                        max_seqlen_q=s, max_seqlen_kv=s, block_neighbor_list=nbr,
+                                                        p_remain_rates=p)
+        if fam == "flux":
+            cuq = torch.tensor([0, s, s], dtype=torch.int32)
+            return ref.rectified_block_sparse_attention(kq, kk, kv_, None, top_k, cu_seqlens_q=cuq, cu_seqlens_kv=cuq,
+                                                        max_seqlen_q=s, max_seqlen_kv=s, block_neighbor_list=nbr,
+                                                        p_remain_rates=p, text_length=text_len)
+        cuq = torch.tensor([0, s, s], dtype=torch.int32)
+        return ref.rectified_block_sparse_attention(kq, kk, kv_, None, top_k, cu_seqlens_q=cuq, cu_seqlens_kv=cuq,
+                                                    max_seqlen_q=s, max_seqlen_kv=s, block_neighbor_list=nbr,
+                                                    p_remain_rates=p, text_length=text_len)
+
+    zeros = lambda q_, *a, **kw: torch.zeros_like(q_)
+    ones = lambda q_, *a, **kw: torch.ones_like(q_)
+    out_c = call(zeros)          # visual rows hold C (block-constant)
+    out_rc = call(ones)          # visual rows hold R + C
+    out = call(_dense_masked_kernel)
+    nq = cap["mask"].shape[2]
+    rows_vis = min(nq * 128, s)
+    oc = out_c.reshape(1, s, heads, 128)[0].permute(1, 0, 2)      # [H, S, D]
+    orc = out_rc.reshape(1, s, heads, 128)[0].permute(1, 0, 2)
+    idx = torch.arange(0, rows_vis, 128)
+    c = oc[:, idx]                                                 # [H, NQ, D]
+    r = (orc[:, idx] - c).mean(dim=-1)                             # [H, NQ]  (R + C - C, 128 identical columns)
+    np.savez_compressed(
+        os.path.join(GOLD, f"mask_{name}.npz"),
+        mask=np.packbits(cap["mask"][0].numpy().astype(np.uint8)), mask_shape=np.array(cap["mask"][0].shape),
+        probs=cap["probs"][0].numpy().astype(np.float32),
+        nogapr=np.packbits(cap["nogapr"][0].numpy().astype(np.uint8)),
+        nogapr_shape=np.array(cap["nogapr"][0].shape),
+        R=r.numpy().astype(np.float32), C=c.numpy().astype(np.float32),
+        out=out[0].numpy().astype(np.float32),
+        nbr=np.packbits(nbr.numpy().astype(np.uint8)), nbr_shape=np.array(nbr.shape))
+    print("case", name, "mask density", float(cap["mask"].float().mean()), "nogapr", float(cap["nogapr"].float().mean()),
+          "R min/mean", float(r.min()), float(r.mean()), flush=True)
+
+
+# ------------------------------------------------------------------------------- literal Triton kernel, fp16
+def make_kernel_fp16():
+    class _NullDev(contextlib.nullcontext):
+        def __init__(self, *_a, **_k):
+            super().__init__()
+
+    ref = ref_loader.load(["rectified_wan21_attn"])["rectified_wan21_attn"]
+    torch.manual_seed(11)
+    h, s_valid, s_pad = 2, 1000, 1024
+    q = torch.randn(1, h, s_pad, 128).half()
+    k = torch.randn(1, h, s_pad, 128).half()
+    v = torch.randn(1, h, s_pad, 128).half()
+    q[:, :, s_valid:] = 0
+    k[:, :, s_valid:] = 0
+    v[:, :, s_valid:] = 0
+    mask = torch.rand(1, h, 8, 8) < 0.4
+    mask |= torch.eye(8, dtype=torch.bool)
+    seqlens = torch.tensor([s_valid], dtype=torch.int32)
+    saved = torch.cuda.device
+    torch.cuda.device = _NullDev
+    try:
+        o = ref._triton_block_sparse_attention_onehot(q, k, v, seqlens, mask, 128 ** -0.5, 128, 128)
+    finally:
+        torch.cuda.device = saved
+    np.savez_compressed(os.path.join(GOLD, "kernel_fp16.npz"), q=q.numpy(), k=k.numpy(), v=v.numpy(),
+                        mask=mask.numpy(), seqlen=np.array(s_valid), out=o.numpy())
+    print("kernel_fp16 done", float(o.float().abs().mean()), flush=True)
+
+
+if __name__ == "__main__":
+    os.makedirs(GOLD, exist_ok=True)
+    what = sys.argv[1:] or ["gilbert", "masks", "kernel"]
+    if "gilbert" in what:
+        make_gilbert()
+    if "masks" in what:
+        for n in CASES:
+            run_reference_case(n)
+    if "kernel" in what:
+        make_kernel_fp16()

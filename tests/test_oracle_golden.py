@@ -1,0 +1,124 @@
+"""CPU tests: the oracle (oracle/) against fixtures produced by the reference itself (tests/golden/, made by
+oracle/make_golden.py).  These pin the oracle; the GPU parity tests then compare the CUDA path with it."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import cases as C
+from oracle import gilbert_oracle as G
+from oracle import rsa_oracle as O
+
+
+def _unpack(bits, shape):
+    n = int(np.prod(shape))
+    return np.unpackbits(bits)[:n].reshape(shape).astype(bool)
+
+
+def _geo(fam, nv, s, text_len, ntrue_d, top_k, p, t):
+    if fam == "wan":
+        return O.geometry_wan(s, top_k, p, (nv + 127) // 128 // t)
+    if fam == "hunyuan":
+        return O.geometry_hunyuan(s, nv + ntrue_d, top_k, p)
+    if fam == "flux":
+        return O.geometry_flux(s, text_len, top_k, p)
+    return O.geometry_cogvideo(s, text_len, top_k, p)
+
+
+@pytest.fixture(scope="module")
+def gilbert_gold(gold_dir):
+    with open(os.path.join(gold_dir, "gilbert.json")) as f:
+        return json.load(f)
+
+
+def test_gilbert_small_grids(gilbert_gold):
+    for e in gilbert_gold["small"]:
+        t, h, w = e["grid"]
+        l2h, h2l = G.gilbert_mapping(t, h, w)
+        assert l2h.tolist() == e["l2h"], e["grid"]
+        assert h2l.tolist() == e["h2l"], e["grid"]
+        nbr = G.gilbert_block_neighbors(t, h, w, l2h=l2h)
+        assert np.array_equal(nbr, _unpack(np.array(e["nbr"], dtype=np.uint8), e["nbr_shape"])), e["grid"]
+        _, h2l2 = G.gilbert_mapping(t, h, w, axis_order=("t", "h", "w"))
+        assert h2l2.tolist() == e["h2l_thw"], e["grid"]
+        # Appendix C invariants
+        assert np.array_equal(h2l[l2h], np.arange(t * h * w))
+        assert np.array_equal(nbr, nbr.T) and nbr.diagonal().all()
+
+
+@pytest.mark.parametrize("name", list(C.CASES))
+def test_mask_builder_against_reference(name, gold_dir):
+    fam, (t, h, w), nv, s, text_len, ntrue_d, heads, top_k, p, q, k, v = C.case_inputs(name)
+    g = np.load(os.path.join(gold_dir, f"mask_{name}.npz"))
+    mask_ref = _unpack(g["mask"], g["mask_shape"])
+    nogapr_ref = _unpack(g["nogapr"], g["nogapr_shape"])
+    nbr = _unpack(g["nbr"], g["nbr_shape"])
+    # the oracle's own neighbour matrix equals the reference's
+    assert np.array_equal(G.gilbert_block_neighbors(t, h, w), nbr)
+    geo = _geo(fam, nv, s, text_len, ntrue_d, top_k, p, t)
+    out_ref = g["out"].reshape(s, heads, 128)
+    for hi in range(heads):
+        out, st = O.head_forward(q[0, hi], k[0, hi], v[0, hi], geo, nbr, return_stages=True)
+        assert st["mask"].shape == mask_ref[hi].shape
+        np.testing.assert_allclose(st["probs"], g["probs"][hi], rtol=2e-5, atol=1e-7)
+        # discrete decisions: identical unless the reference sits on a tie (none in these seeds)
+        assert np.array_equal(st["mask"], mask_ref[hi]), f"{name} head {hi}: mask differs"
+        assert np.array_equal(st["nogapr"], nogapr_ref[hi]), f"{name} head {hi}: nogapr differs"
+        np.testing.assert_allclose(st["R"], g["R"][hi], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(st["C"], g["C"][hi], rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(out, out_ref[:, hi], rtol=1e-4, atol=2e-5)
+        # invariants
+        assert np.all(st["mask"].sum(1) >= min(top_k, st["probs"].shape[1]))
+        np.testing.assert_allclose(st["probs"].sum(1), 1.0, atol=1e-5)
+        assert np.all(st["R"] > 0) and np.all(st["R"] <= 1 + 1e-6)
+
+
+def test_triton_kernel_semantics_fp16(gold_dir):
+    """The literal reference kernel (TRITON_INTERPRET, fp16) vs the oracle's dense masked restatement."""
+    import torch
+
+    g = np.load(os.path.join(gold_dir, "kernel_fp16.npz"))
+    rnd = lambda x: x.half().float()
+    seqlen = int(g["seqlen"])
+    for hi in range(g["q"].shape[1]):
+        o = O.masked_attention(g["q"][0, hi].astype(np.float32), g["k"][0, hi].astype(np.float32),
+                               g["v"][0, hi].astype(np.float32), g["mask"][0, hi], seqlen, seqlen, emulate=rnd)
+        ref = g["out"][0, hi].astype(np.float32)
+        assert np.abs(o - ref[:seqlen]).max() <= 1e-3      # 1-2 fp16 ulp at |o| <= 1
+        assert np.all(ref[seqlen:] == 0)                      # padded query rows are never stored (wan21 :105)
+        # and the exact (unrounded) restatement is within the same distance
+        o32 = O.masked_attention(g["q"][0, hi].astype(np.float32), g["k"][0, hi].astype(np.float32),
+                                 g["v"][0, hi].astype(np.float32), g["mask"][0, hi], seqlen, seqlen)
+        assert np.abs(o32 - ref[:seqlen]).max() <= 3e-3
+
+
+def test_dense_limit():
+    """top_k >= NB -> mask all true -> R = 1, C = 0 -> output equals dense attention (Appendix C)."""
+    import torch
+
+    q, k, v = O.synth_qkv(1, 512, 128, "walk", 21)
+    geo = O.geometry_wan(512, 99, 0.3, 0)
+    out, st = O.head_forward(q[0, 0], k[0, 0], v[0, 0], geo, None, return_stages=True)
+    assert st["mask"].all() and np.allclose(st["R"], 1.0, atol=1e-6) and np.abs(st["C"]).max() == 0
+    ref = torch.nn.functional.scaled_dot_product_attention(
+        torch.from_numpy(q[0, 0])[None], torch.from_numpy(k[0, 0])[None], torch.from_numpy(v[0, 0])[None])[0]
+    np.testing.assert_allclose(out, ref.numpy(), atol=2e-5)
+
+
+def test_select_block_num_truncation():
+    # int((1-0.8)*900) = 179, int((1-0.9)*512) = 51, int(0.25*591) = 147
+    assert O.select_block_num(0.8, 900) == 179
+    assert O.select_block_num(0.9, 512) == 51
+    assert O.select_block_num(0.75, 591) == 147
+
+
+def test_selection_tie_break_and_threshold():
+    geo = O.geometry_wan(4 * 128, 1, 0.5, 0)
+    p = np.array([[0.25, 0.25, 0.25, 0.25], [0.1, 0.6, 0.2, 0.1], [0.5, 0.5, 0.0, 0.0], [0.0, 0.0, 0.0, 1.0]],
+                 dtype=np.float32)
+    m, n = O.select_blocks(p, geo, None)
+    # row0: cumsum .25,.5,.75,1 -> two entries <= .5 -> n = 3, ties resolved towards the lower index
+    assert n.tolist() == [3, 1, 2, 1]
+    assert m.tolist() == [[True, True, True, False], [False, True, False, False], [True, True, False, False],
+                          [False, False, False, True]]

@@ -1,0 +1,373 @@
+#!/usr/bin/env python
+"""bench.py -- rectified block-sparse attention call on B200: ms per attention call and dense-equivalent TFLOP/s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3a] [--regime walk] [--impl ours|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one call of the reference's inner surface (rectified_block_sparse_attention) on one batch of synthetic
+bf16 Q/K/V: block pooling -> scores/GAPR -> selection -> C -> block-sparse attention with the fused rectification
+epilogue.  Heads are independent, so at N > 1 the heads of ONE call are sharded across ranks with no collective
+("scaling": "strong"); value = dense-equivalent FLOP of the whole call / max-over-ranks time.
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(REPO, "rectified-spaattn_b200")
+for _p in (REPO, PKG):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+# name: family, grid (t,h,w), text tokens, valid text tokens, heads, sa_drop_rate, first-frame rule
+WORKLOADS = {
+    "c1": dict(desc="synthetic 4x16x16 (1024 tokens), wan path", fam="wan", grid=(4, 16, 16), text=0, text_valid=0,
+               heads=12, drop=0.75, ffb=True),
+    "c2": dict(desc="Wan2.1-T2V-1.3B 480p 81f, 21x30x52 (32760 tokens)", fam="wan", grid=(21, 30, 52), text=0,
+               text_valid=0, heads=12, drop=0.75, ffb=True),
+    "c3a": dict(desc="HunyuanVideo 720p 128f (reference default), 32x45x80 + 256 text = 115456 tokens", fam="hunyuan",
+                grid=(32, 45, 80), text=256, text_valid=200, heads=24, drop=0.8, ffb=False),
+    "c4": dict(desc="Wan2.1-T2V-14B 720p 81f, 21x45x80 (75600 tokens)", fam="wan", grid=(21, 45, 80), text=0,
+               text_valid=0, heads=40, drop=0.75, ffb=True),
+    "c5": dict(desc="Flux.1-dev 4096x4096, 1x256x256 + 512 text = 66048 tokens", fam="flux", grid=(1, 256, 256),
+               text=512, text_valid=512, heads=24, drop=0.9, ffb=False),
+}
+P_REMAIN = 0.3
+FLOP_PER_PAIR = 4 * 128 * 128 * 128  # QK^T + PV of one kept (q-block, kv-block) pair at D = 128
+
+
+def workload_params(name):
+    w = WORKLOADS[name]
+    t, h, ww = w["grid"]
+    nv = t * h * ww
+    s = nv + w["text"]
+    img_blocks = (nv + 127) // 128 if w["fam"] == "wan" else nv // 128
+    top_k = int((1 - w["drop"]) * img_blocks)          # reference scripts/main_hunyuan.py:253 (float truncation)
+    ffb = (img_blocks // t) if w["ffb"] else 0         # scripts/main_wan21t2v.py:259
+    return dict(w, nv=nv, s=s, top_k=top_k, ffb_blocks=ffb, num_true=nv + w["text_valid"],
+                dense_flop_per_head=4.0 * s * s * 128)
+
+
+class ClockSampler(threading.Thread):
+    """Samples nvidia-smi clocks / throttle reasons while the timed region runs (B200_PROFILING.md recipe)."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i",
+                                      str(self.index)], capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        self.stop_flag = True
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        for r in self.rows:
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        busy = [x for x in sm if x > 0]
+        return {"sm_mhz": busy[len(busy) // 2] if busy else None,
+                "sm_max_mhz": int(float(self.rows[0][1])) if self.rows else None,
+                "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(bf16=d["bf16_tflops"], bf16_sustained=d.get("bf16_tflops_sustained"), hbm=d["hbm_gbs"],
+                    source="measured")
+    return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
+
+
+def synth_heads_device(heads, head0, s, regime, dev, seed=0):
+    """Q, K, V [1, heads, s, 128] bf16 on the device (SURVEY 8d regimes), one generator stream per global head."""
+    import torch
+    nb = (s + 127) // 128
+    outs = [torch.empty(1, heads, s, 128, dtype=torch.bfloat16, device=dev) for _ in range(3)]
+    for hi in range(heads):
+        g = torch.Generator(device=dev).manual_seed(seed * 1000 + head0 + hi)
+        for ti in range(3):
+            x = torch.randn(nb * 128, 128, generator=g, device=dev)
+            if ti < 2 and regime != "iid":
+                mu = torch.randn(nb, 128, generator=g, device=dev) * (0.35 if regime == "walk" else 1.0)
+                if regime == "walk":
+                    mu = torch.cumsum(mu, dim=0)
+                x = x + mu.repeat_interleave(128, dim=0)
+            outs[ti][0, hi] = x[:s].to(torch.bfloat16)
+    return outs
+
+
+def product_geometry(wp):
+    from rsa_b200 import geometry as G
+    if wp["fam"] == "wan":
+        return G.wan(wp["s"], wp["ffb_blocks"])
+    if wp["fam"] == "hunyuan":
+        return G.hunyuan(wp["s"], wp["num_true"])
+    if wp["fam"] == "flux":
+        return G.flux(wp["s"], wp["text"])
+    return G.cogvideo(wp["s"], wp["text"])
+
+
+def entry_point(wp):
+    """The reference-facing public call for this family (what a user of the reference calls)."""
+    if wp["fam"] == "wan":
+        from rectified_spaattn.rectified_wan21_attn import rectified_block_sparse_attention as f
+        return lambda q, k, v, nbr: f(q, k, v, None, wp["top_k"], block_neighbor_list=nbr, p_remain_rates=P_REMAIN,
+                                      first_frame_blocks=wp["ffb_blocks"])
+    if wp["fam"] == "hunyuan":
+        from rectified_spaattn.rectified_hunyuan_attn import rectified_block_sparse_attention as f
+        cu = [0, wp["num_true"], wp["s"]]
+        return lambda q, k, v, nbr: f(q, k, v, None, wp["top_k"], cu_seqlens_q=cu, cu_seqlens_kv=cu,
+                                      max_seqlen_q=wp["s"], max_seqlen_kv=wp["s"], block_neighbor_list=nbr,
+                                      p_remain_rates=P_REMAIN)
+    from rectified_spaattn.rectified_flux_attn import rectified_block_sparse_attention as f
+    cu = [0, wp["s"], wp["s"]]
+    return lambda q, k, v, nbr: f(q, k, v, None, wp["top_k"], cu_seqlens_q=cu, cu_seqlens_kv=cu, max_seqlen_q=wp["s"],
+                                  max_seqlen_kv=wp["s"], block_neighbor_list=nbr, p_remain_rates=P_REMAIN,
+                                  text_length=wp["text"])
+
+
+# --------------------------------------------------------------------------------------------- CPU baseline
+def cpu_sample(wp, regime, budget_s=12.0, threads=None):
+    """The oracle (a CPU port of the reference algorithm) on a bounded sample of the workload: ONE head, the mask
+    build for every query block of that head, and the attention for the first n query blocks (n sized to the time
+    budget).  Returns dense-equivalent TFLOP/s extrapolated to the whole head."""
+    import numpy as np
+    import torch
+
+    from oracle import gilbert_oracle as GO  # noqa: F401
+    from oracle import rsa_oracle as O
+    from rsa_b200 import ops as host_ops  # only the pure-CPU geometry helper (no GPU, no kernels)
+
+    if threads:
+        torch.set_num_threads(threads)
+    cores = torch.get_num_threads()
+    s = wp["s"]
+    q, k, v = O.synth_qkv(1, s, 128, regime, 0)
+    q, k, v = q[0, 0], k[0, 0], v[0, 0]
+    t, h, w = wp["grid"]
+    nbr = host_ops.gilbert_block_neighbors(t, h, w).numpy()
+    if wp["fam"] == "wan":
+        geo = O.geometry_wan(s, wp["top_k"], P_REMAIN, wp["ffb_blocks"])
+    elif wp["fam"] == "hunyuan":
+        geo = O.geometry_hunyuan(s, wp["num_true"], wp["top_k"], P_REMAIN)
+    else:
+        geo = O.geometry_flux(s, wp["text"], wp["top_k"], P_REMAIN)
+    t0 = time.perf_counter()
+    nq, nv = geo.nq_blocks, geo.nq_blocks * 128
+    qp, dq = O.pool_stats(q, geo.seq, nq)
+    kp, dk = O.pool_stats(k, geo.kv_zero_from, nq)
+    vp, _ = O.pool_stats(v, geo.kv_zero_from, geo.n_blocks, want_mad=False)
+    kt = k[nv: nv + geo.text_keys] if geo.family == "joint" else None
+    a, nogapr = O.block_scores(qp, dq, kp, dk, kt)
+    p = O.probs_from_scores(a, nq, 128, geo.family == "joint")
+    m, _ = O.select_blocks(p, geo, nbr)
+    O.rectify_factors(p, m, nogapr, vp, geo)
+    t_mask = time.perf_counter() - t0
+    # attention on a growing sample until the budget is used
+    n_done, t_attn = 0, 0.0
+    n = 2
+    while n_done < nq and t_attn < budget_s:
+        n = min(n, nq - n_done)
+        t1 = time.perf_counter()
+        O.masked_attention(q[n_done * 128:], k, v, m[n_done: n_done + n], geo.kv_len, n * 128)
+        t_attn += time.perf_counter() - t1
+        n_done += n
+        n *= 2
+    nqt = geo.n_blocks
+    t_head = t_mask + t_attn * (nqt / n_done)
+    tflops = wp["dense_flop_per_head"] / t_head / 1e12
+    return dict(value=tflops, unit="TFLOP/s (dense-equivalent)", cores=cores, kind="port",
+                sample=f"{wp['name']} one head of {wp['heads']}: mask build for all {nq} query blocks ({t_mask:.2f} s) + "
+                       f"attention of the first {n_done} of {nqt} query blocks ({t_attn:.2f} s), extrapolated to the head",
+                ms_per_call_extrapolated=t_head * wp["heads"] * 1e3)
+
+
+# ------------------------------------------------------------------------------------------------------ main
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3a", choices=list(WORKLOADS))
+    ap.add_argument("--regime", default="walk", choices=["walk", "iid", "cluster"])
+    ap.add_argument("--attn-impl", type=int, default=0, help="0 = tcgen05 kernel (product); 1 = mma.sync cross-check")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wp = workload_params(args.workload)
+    wp["name"] = args.workload
+    config = {"workload": f"{args.workload}: {wp['desc']}", "heads": wp["heads"], "tokens": wp["s"], "head_dim": 128,
+              "top_k": wp["top_k"], "p_remain_rates": P_REMAIN, "regime": args.regime,
+              "parallelism": f"head-parallel x{world}" if world > 1 else "single GPU",
+              "l2": "inputs (Q,K,V >= 0.4 GB) exceed the 126 MB L2; no explicit flush"}
+
+    if args.impl == "reference":
+        # The reference's own CPU implementation of the path = PyTorch eager ops; its Python sources cannot travel
+        # to the GPU box, so this arm times the oracle port (same algorithm) on the host cores, rank 0 only.
+        if rank != 0:
+            return
+        vals = []
+        base = None
+        for i in range(max(1, min(args.steps, 3))):
+            base = cpu_sample(wp, args.regime, budget_s=8.0)
+            vals.append(base["value"])
+        v = sorted(vals)[len(vals) // 2]
+        ms = wp["dense_flop_per_head"] * wp["heads"] / (v * 1e12) * 1e3
+        line = {"impl": "reference", "metric": "dense-equiv TFLOP/s per rectified sparse-attention call", "value": v,
+                "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": ms,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": config, "cpu_baseline": dict(base, value=v),
+                "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import torch
+    import torch.distributed as dist
+
+    from rsa_b200 import native, ops
+
+    assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback on the product path)"
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    assert native.lib().rsa_device_ok() == 1
+    ops.set_attention_impl(args.attn_impl)
+
+    heads = wp["heads"]
+    if heads % world:
+        raise SystemExit(f"{heads} heads do not split over {world} ranks")
+    h_loc = heads // world
+    head0 = rank * h_loc
+    t, h, w = wp["grid"]
+    nbr = ops.gilbert_block_neighbors(t, h, w)
+    q, k, v = synth_heads_device(h_loc, head0, wp["s"], args.regime, dev)
+    geo = product_geometry(wp)
+    plan = ops.Plan(q, k, v, geo, wp["top_k"], P_REMAIN, nbr)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """CUDA events on the launching stream; returns max-over-ranks milliseconds per step."""
+        sync_all()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            tt = torch.tensor([ms], device=dev)
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            ms = float(tt.item())
+        sync_all()
+        return ms
+
+    for _ in range(args.warmup):
+        plan.run()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    ms_step = timed(plan.run, args.steps)
+
+    # per-stage device times (same launches, timed alone) and the roofline of the dominant kernel
+    stages = {}
+    for name, fn in (("pool_stats", plan.pool_stats), ("block_scores", plan.block_scores),
+                     ("block_select", plan.block_select), ("rect_c", plan.rect_c),
+                     ("sparse_attention", plan.sparse_attention)):
+        stages[name] = timed(fn, max(3, args.steps))
+    clocks = sampler.summary() if rank == 0 else None
+    vw = plan.view()
+    pairs = int(vw["kept_cnt"].sum().item())
+    if world > 1:
+        tp = torch.tensor([pairs], device=dev, dtype=torch.int64)
+        dist.all_reduce(tp)
+        pairs_all = int(tp.item())
+    else:
+        pairs_all = pairs
+    nqt = geo.n_blocks
+    density = pairs_all / (heads * nqt * nqt)
+
+    # end to end through the public entry point with HOST buffers (pinned): H2D of Q,K,V + call + D2H of the result
+    e2e = None
+    if not args.no_e2e:
+        call = entry_point(wp)
+        hq, hk, hv = (x.cpu().pin_memory() for x in (q, k, v))
+        ho = torch.empty((1, wp["s"], h_loc * 128), dtype=torch.bfloat16).pin_memory()
+        dq_, dk_, dv_ = (torch.empty_like(x) for x in (q, k, v))
+
+        def e2e_step():
+            dq_.copy_(hq, non_blocking=True)
+            dk_.copy_(hk, non_blocking=True)
+            dv_.copy_(hv, non_blocking=True)
+            o = call(dq_, dk_, dv_, nbr)
+            ho.copy_(o, non_blocking=True)
+
+        for _ in range(2):
+            e2e_step()
+        ms_e2e = timed(e2e_step, max(3, args.steps // 2))
+        bi = 3 * q.numel() * 2 * world
+        bo = ho.numel() * 2 * world
+        e2e = {"value": wp["dense_flop_per_head"] * heads / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s",
+               "ms_per_step": ms_e2e, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo}
+
+    if rank == 0:
+        peaks = measured_peaks()
+        t_attn = stages["sparse_attention"]
+        achieved = FLOP_PER_PAIR * (pairs_all / world) / (t_attn * 1e-3) / 1e12   # per GPU
+        line = {
+            "metric": "dense-equiv TFLOP/s per rectified sparse-attention call", "value":
+                wp["dense_flop_per_head"] * heads / (ms_step * 1e-3) / 1e12,
+            "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": config, "ms_per_attn_call": ms_step, "kept_pair_density": density, "stages_ms": stages,
+            "attention_impl": "tcgen05" if args.attn_impl == 0 else "mma.sync cross-check",
+            "gpu_launches": 5 * args.steps,
+            "roofline": {"bound": "tensor", "kernel": "rect_attn (kernel 4)", "achieved": achieved,
+                         "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
+                         "peak_source": f"{peaks['source']} cuBLAS bf16 burst; sustained {peaks['bf16_sustained']}",
+                         "kept_pairs_per_launch": pairs_all // world, "ms_per_launch": t_attn, "traffic": None},
+            "clocks": clocks,
+        }
+        if e2e:
+            line["e2e"] = e2e
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_sample(wp, args.regime)
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,170 @@
+/* rsa.h -- C ABI of librsa_b200.so: the rectified block-sparse attention hot path for NVIDIA B200 (sm_100a).
+ *
+ * Drop-in boundary for the hot path of BienLuky/Rectified-SpaAttn (reference paths relative to its root).
+ * The reference has no native code; what it runs as PyTorch eager ops + a Triton JIT kernel + flash-attn calls
+ * is exported here as plain C entry points (raw device pointers, explicit sizes/strides, a cudaStream_t passed
+ * as void*, caller-owned workspace, int status codes, no exceptions, no allocation, no host synchronisation).
+ * Each entry point cites the reference interface it replaces.  The Python mirror of the reference modules
+ * (rectified-spaattn_b200/rectified_spaattn/*.py) binds these with ctypes; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions: all tensors are bf16 unless stated, head_dim == 128, block size == 128 tokens.
+ * "BH" = batch * heads (heads are independent end to end).  Strides are in ELEMENTS of the tensor's dtype.
+ */
+#ifndef RSA_H_
+#define RSA_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RSA_VERSION 100
+#define RSA_BLOCK 128
+#define RSA_HEAD_DIM 128
+#define RSA_MAX_ENTRIES 2048 /* max sortable entries per query block: NQ (+1 for the text aggregate) */
+
+enum rsa_status {
+  RSA_OK = 0,
+  RSA_ERR_ARG = -1,         /* null pointer, negative size, inconsistent geometry */
+  RSA_ERR_UNSUPPORTED = -2, /* head_dim != 128, too many blocks, misaligned strides */
+  RSA_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed; see rsa_last_error_string() */
+  RSA_ERR_WORKSPACE = -4    /* workspace pointer null or smaller than rsa_attn_workspace_bytes() */
+};
+
+enum rsa_family {
+  RSA_FAMILY_WAN = 0,  /* video tokens only            (rectified_wan21_attn.py:276-357) */
+  RSA_FAMILY_JOINT = 1 /* video tokens first, text last (rectified_{hunyuan,flux,cogvideo}_attn.py) */
+};
+
+/* Thread-local description of the last failure returned by any rsa_* call on this thread. */
+const char* rsa_last_error_string(void);
+int rsa_version(void);
+/* 1 if the library was built with the tcgen05/TMEM/TMA attention kernel and the current device is sm_100. */
+int rsa_device_ok(void);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Host geometry (pure CPU).  Replaces utils/jenga_gilbert.py:
+ *   gilbert_mapping(t,h,w,axis_order)                 :458-504  -> rsa_gilbert_map
+ *   gilbert_block_neighbor_mapping(t,h,w,block_size)  :613-693  -> rsa_gilbert_block_neighbors
+ * axis_order is a 3-character string over {'w','h','t'} (major, mid, minor), e.g. "wht"; NULL selects the
+ * reference's size-based default (gilbert_xyz2d :34-54).  linear index = z*h*w + y*w + x.
+ * out is a row-major [NB, NB] byte matrix (0/1), NB = ceil(t*h*w / block_size). */
+int rsa_gilbert_map(int t, int h, int w, const char* axis_order, int64_t* linear_to_hilbert,
+                    int64_t* hilbert_to_linear);
+int rsa_gilbert_block_neighbors(int t, int h, int w, int block_size, const char* axis_order, uint8_t* out);
+
+/* ------------------------------------------------------------------------------------------------------
+ * Kernel 1: token permute / unpermute.  Replaces the advanced-index gathers in the patched transformer forward
+ *   hidden_states[:, self.hilbert_order], hidden_states[:, self.linear_to_hilbert]  (scripts/main_hunyuan.py:88-89, :183)
+ * dst[b, i, :] = src[b, index[i], :] for i < n_out.  index: device int64 (the reference keeps torch.long).
+ * row_bytes must be a multiple of 16; src/dst 16-byte aligned; batch strides in bytes. */
+int rsa_permute_rows(const void* src, void* dst, const int64_t* index, int batch, int64_t n_out, int64_t n_src,
+                     int64_t row_bytes, int64_t src_batch_stride_bytes, int64_t dst_batch_stride_bytes,
+                     void* stream);
+
+/* ------------------------------------------------------------------------------------------------------
+ * The attention path.  One descriptor describes one call of the reference's inner surface
+ *   rectified_block_sparse_attention(query, key, value, attn_mask, top_k, ..., block_neighbor_list,
+ *                                    p_remain_rates, first_frame_blocks | text_length)
+ *   (rectified_wan21_attn.py:361-386, rectified_hunyuan_attn.py:393-417, rectified_flux_attn.py:380-405,
+ *    rectified_cogvideo_attn.py:382-407)
+ * after the per-family geometry (hunyuan :313-332, flux :307-317, cogvideo :307-322, wan21 :299-313) has been
+ * reduced to integers by the caller. */
+typedef struct rsa_attn_desc {
+  int32_t batch, heads, seq, head_dim; /* query/key/value are [batch, heads, seq, head_dim] views          */
+  int64_t q_stride[3];                 /* element strides of (batch, head, token); head_dim is contiguous  */
+  int64_t k_stride[3];
+  int64_t v_stride[3];
+  int64_t o_stride[3];                 /* output viewed as [batch, heads, seq, head_dim]; the reference's   */
+                                       /* [B, S, H*D] result is strides (S*H*D, D, H*D)                     */
+  int32_t family;                      /* enum rsa_family                                                   */
+  int32_t n_blocks;                    /* NB  = ceil(seq/128): KV blocks (pad rows count as zeros)          */
+  int32_t nq_blocks;                   /* NQ  = query blocks on the sparse path (= visual blocks)           */
+  int32_t text_keys;                   /* a   = text keys scored as single tokens (`attenable`), 0 for WAN  */
+  int32_t kv_len;                      /* Lkv = keys >= kv_len are never attended (`seqlens`)               */
+  int32_t kv_zero_from;                /* K,V rows >= this pool as zeros (hunyuan masked_fill_ :307-308)    */
+  int32_t text_end_block;              /* first KV block that is never kept                                 */
+  int32_t text_q_valid;                /* text query rows with a defined result; later rows are zero-filled */
+  int32_t top_k;                       /* select_block_num                                                  */
+  float p_remain;                      /* p_remain_rates (compared as fp32)                                 */
+  int32_t first_frame_blocks;          /* WAN only, 0 = none                                                */
+  int32_t nbr_rows, nbr_cols;          /* block_neighbor_list shape; both 0 = None                          */
+  const uint8_t* nbr;                  /* DEVICE pointer, row-major bytes (torch.bool storage)              */
+  int32_t debug_dump_probs;            /* !=0: stage 3b also writes P to the workspace (parity tests)       */
+  int32_t reserved;
+} rsa_attn_desc;
+
+/* Pointers into the caller's workspace (all device memory, fp32 unless noted). */
+typedef struct rsa_ws_view {
+  float* q_pool;      /* [BH, NQ, 128]   block means of Q                  (wan21 :189-190)                 */
+  float* q_mad;       /* [BH, NQ, 128]   mean |Q - Qp| per block           (gapr_mask.py:19,23)             */
+  float* k_cat;       /* [BH, NKC, 128]  rows [0,NQ) = block means of K, rows [NQ,NQ+a) = text keys         */
+  float* k_mad;       /* [BH, NQ, 128]                                     (gapr_mask.py:20,30)             */
+  float* v_pool;      /* [BH, NB, 128]   block means of V                  (wan21 :337)                     */
+  float* scores;      /* [BH, NQ, score_ld]  unscaled Qp.[Kp;Kt]^T         (wan21 :203)                     */
+  uint8_t* nogapr;    /* [BH, NQ, nogapr_ld] bytes, columns [0,NQ)         (gapr_mask.py:42)                */
+  float* probs;       /* [BH, NQ, ent_ld]  P (only if debug_dump_probs)    (wan21 :213 / hunyuan :223)      */
+  float* w_skip;      /* [BH, NQ, ent_ld]  P where not(part) else 0        (wan21 :336)                     */
+  uint32_t* mask_bits;/* [BH, NQT, mask_words] kept-block bitmask, bit j of word j/32 = block j             */
+  uint16_t* kept_idx; /* [BH, NQT, NB] ascending kept block indices (u16)                                    */
+  int32_t* kept_cnt;  /* [BH, NQT]                                                                           */
+  int32_t* n_needed;  /* [BH, NQ]  n_i = max(#{cumsum <= p} + 1, top_k)    (wan21 :224-229)                 */
+  float* R;           /* [BH, NQT]  (1 for text query blocks)              (wan21 :332)                     */
+  float* C;           /* [BH, NQT, 128] (0 for text query blocks)          (wan21 :338)                     */
+  int32_t nkc, score_ld, n_entries, ent_ld, mask_words, nqt, nogapr_ld, reserved;
+} rsa_ws_view;
+
+size_t rsa_attn_workspace_bytes(const rsa_attn_desc* d);
+int rsa_attn_workspace_view(const rsa_attn_desc* d, void* workspace, size_t workspace_bytes, rsa_ws_view* out);
+
+/* Kernel 2: block mean pooling of Q, K, V + GAPR deviation statistics in one pass per tensor.
+ * Replaces Q_blocks.mean / K_blocks.mean (wan21 :189-192), value_pool (:337) and delta_q/delta_k abs().mean()
+ * (gapr_mask.py:19-30).  Fills q_pool, q_mad, k_cat, k_mad, v_pool. */
+int rsa_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* workspace,
+                   size_t workspace_bytes, void* stream);
+
+/* Kernel 3a: pooled score products + GAPR test.  Replaces torch.bmm (wan21 :203) and estimate_pr_gain
+ * (gapr_mask.py:26-42).  Fills scores, nogapr. */
+int rsa_block_scores(const rsa_attn_desc* d, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Kernel 3b: softmax, IPAR re-allocation, sort / cumulative threshold / top-k, neighbour + first-frame + text
+ * unions, R, skipped-block weights; emits the per-row kept-block index lists.  Replaces wan21 :206-271 /
+ * hunyuan :208-277 and the R half of wan21 :329-333.  Tie-break: probability descending, index ascending;
+ * cumulative sum sequential in fp32.  Fills probs (optional), mask_bits, kept_idx, kept_cnt, n_needed, R, w_skip. */
+int rsa_block_select(const rsa_attn_desc* d, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Kernel 3c: C = W_skip . Vp.  Replaces torch.matmul(attn_pool_novalid, value_pool) (wan21 :336-338). */
+int rsa_rect_c(const rsa_attn_desc* d, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Kernel 4: block-sparse attention over the kept lists with the rectification epilogue O = Os*R + C fused into
+ * the output write, text query blocks handled as dense rows.  Replaces _triton_block_sparse_attention_onehot
+ * (wan21 :108-168, kernel :16-105), the epilogue (wan21 :346), the flash-attn call for text rows
+ * (hunyuan :371-380) and the cat/permute/reshape (hunyuan :383-387).  Reads kept_idx, kept_cnt, R, C. */
+int rsa_sparse_attention(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
+                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* All of the above in order on one stream (no host synchronisation; CUDA-graph capturable). */
+int rsa_rectified_attention(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* Kernel 4 alone on a caller-supplied dense block mask (bytes, [BH, n_q_blocks, n_kv_blocks]) -- the literal
+ * surface of _triton_block_sparse_attention_onehot(q, k, v, seqlens, block_mask, sm_scale) (wan21 :108-117).
+ * q/k/v/out are [BH, seq, 128] with the given token strides; R = 1, C = 0.  workspace must hold
+ * rsa_masked_attention_workspace_bytes(). */
+size_t rsa_masked_attention_workspace_bytes(int bh, int n_q_blocks, int n_kv_blocks);
+int rsa_masked_attention(const void* q, const void* k, const void* v, void* out, int bh, int seq_q, int seq_kv,
+                         int kv_len, const int64_t q_stride[2], const int64_t k_stride[2],
+                         const int64_t v_stride[2], const int64_t o_stride[2], const uint8_t* block_mask,
+                         int n_q_blocks, int n_kv_blocks, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Selects the attention kernel implementation for this process: 0 = tcgen05/TMEM/TMA (product path),
+ * 1 = mma.sync cross-check kernel (tests only).  Returns the previous value. */
+int rsa_set_attention_impl(int impl);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RSA_H_ */

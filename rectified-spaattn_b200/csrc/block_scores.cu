@@ -1,0 +1,163 @@
+// block_scores.cu -- kernel 3a: pooled score products and the GAPR gain/error test in one pass.
+// Replaces (reference paths relative to the reference root):
+//   attention_scores_flat = bmm(query_pool, [key_pool; key_text]^T)   rectified_wan21_attn.py:203, hunyuan :205
+//   dot_q = bmm(mean|dQ|, key_pool^T); dot_k = bmm(query_pool, mean|dK|^T)      gapr_mask.py:26, :32
+//   ~(IQ*JK*|A| > IQ*JK*(|dot_q| + |dot_k|))                                    gapr_mask.py:27-42
+// (the IQ*JK = 2^14 factors are exact scalings and cancel bit-exactly in fp32.)
+//
+// fp32 SIMT on purpose: the selection downstream is a discrete decision, so every (i, j) product is ONE fmaf chain
+// over d = 0..127 in that order -- the oracle replicates it bit for bit.  ~16 GFLOP at the HunyuanVideo size;
+// operands (55 MB of pooled statistics) are L2-resident.
+//
+// CTA tile 64 (query blocks) x 64 (key entries), 256 threads, 4x4 micro-tile per thread, d staged through
+// shared memory in chunks of 32 with a [d][row] layout so the inner loop is 4 LDS.128 per 48 FMA.
+#include "rsa_common.cuh"
+
+namespace rsa {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int TI = 64, TJ = 64, DK = 32;
+
+struct ScoreArgs {
+  const float *qp, *dq, *kc, *dk;  // [BH,NQ,128], [BH,NQ,128], [BH,NKC,128], [BH,NQ,128]
+  float* scores;                   // [BH,NQ,score_ld]
+  uint8_t* nogapr;                 // [BH,NQ,nogapr_ld]
+  int nq, nkc, score_ld, nogapr_ld;
+};
+
+__device__ __forceinline__ void stage(float (*dst)[TI], const float* src, int rows_avail, int dc, int tid) {
+  // 64 rows x 32 d: thread -> (row = tid & 63, two float4 along d)
+  const int row = tid & 63;
+#pragma unroll
+  for (int p = 0; p < 2; ++p) {
+    const int q4 = (tid >> 6) + 4 * p;  // 0..7
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row < rows_avail) v = __ldg(reinterpret_cast<const float4*>(src + (int64_t)row * 128 + dc + 4 * q4));
+    dst[4 * q4 + 0][row] = v.x;
+    dst[4 * q4 + 1][row] = v.y;
+    dst[4 * q4 + 2][row] = v.z;
+    dst[4 * q4 + 3][row] = v.w;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads) block_scores_kernel(const ScoreArgs a) {
+  __shared__ __align__(16) float s_qp[DK][TI];
+  __shared__ __align__(16) float s_dq[DK][TI];
+  __shared__ __align__(16) float s_kp[DK][TJ];
+  __shared__ __align__(16) float s_dk[DK][TJ];
+
+  const int bh = blockIdx.z;
+  const int i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const bool need_gapr = j0 < a.nq;  // tiles that only hold text-key columns skip the error products
+
+  const float* qp = a.qp + ((int64_t)bh * a.nq + i0) * 128;
+  const float* dq = a.dq + ((int64_t)bh * a.nq + i0) * 128;
+  const float* kc = a.kc + ((int64_t)bh * a.nkc + j0) * 128;
+  const float* dk = a.dk + ((int64_t)bh * a.nq + j0) * 128;
+  const int rows_i = a.nq - i0;
+  const int rows_j = a.nkc - j0;
+  const int rows_jg = a.nq - j0;  // columns that have deviation statistics
+
+  float A[4][4], E1[4][4], E2[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int v = 0; v < 4; ++v) A[u][v] = E1[u][v] = E2[u][v] = 0.f;
+
+  for (int dc = 0; dc < 128; dc += DK) {
+    __syncthreads();
+    stage(s_qp, qp, rows_i, dc, tid);
+    stage(s_kp, kc, rows_j, dc, tid);
+    if (need_gapr) {
+      stage(s_dq, dq, rows_i, dc, tid);
+      stage(s_dk, dk, rows_jg, dc, tid);
+    }
+    __syncthreads();
+    if (need_gapr) {
+#pragma unroll 8
+      for (int d = 0; d < DK; ++d) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&s_qp[d][4 * ty]);
+        const float4 g4 = *reinterpret_cast<const float4*>(&s_dq[d][4 * ty]);
+        const float4 k4 = *reinterpret_cast<const float4*>(&s_kp[d][4 * tx]);
+        const float4 h4 = *reinterpret_cast<const float4*>(&s_dk[d][4 * tx]);
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
+        const float k[4] = {k4.x, k4.y, k4.z, k4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) {
+            A[u][v] = __fmaf_rn(q[u], k[v], A[u][v]);
+            E1[u][v] = __fmaf_rn(g[u], k[v], E1[u][v]);
+            E2[u][v] = __fmaf_rn(q[u], hh[v], E2[u][v]);
+          }
+      }
+    } else {
+#pragma unroll 8
+      for (int d = 0; d < DK; ++d) {
+        const float4 q4 = *reinterpret_cast<const float4*>(&s_qp[d][4 * ty]);
+        const float4 k4 = *reinterpret_cast<const float4*>(&s_kp[d][4 * tx]);
+        const float q[4] = {q4.x, q4.y, q4.z, q4.w};
+        const float k[4] = {k4.x, k4.y, k4.z, k4.w};
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+#pragma unroll
+          for (int v = 0; v < 4; ++v) A[u][v] = __fmaf_rn(q[u], k[v], A[u][v]);
+      }
+    }
+  }
+
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int i = i0 + 4 * ty + u;
+    if (i >= a.nq) continue;
+    const int j = j0 + 4 * tx;
+    float* srow = a.scores + ((int64_t)bh * a.nq + i) * a.score_ld + j;
+    if (j + 3 < a.nkc) {
+      *reinterpret_cast<float4*>(srow) = make_float4(A[u][0], A[u][1], A[u][2], A[u][3]);
+    } else {
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        if (j + v < a.nkc) srow[v] = A[u][v];
+    }
+    if (need_gapr) {
+      uint8_t* grow = a.nogapr + ((int64_t)bh * a.nq + i) * a.nogapr_ld + j;
+      uint8_t g[4];
+#pragma unroll
+      for (int v = 0; v < 4; ++v)
+        g[v] = (fabsf(A[u][v]) > __fadd_rn(fabsf(E1[u][v]), fabsf(E2[u][v]))) ? 0 : 1;
+      if (j + 3 < a.nq) {
+        *reinterpret_cast<uchar4*>(grow) = make_uchar4(g[0], g[1], g[2], g[3]);
+      } else {
+#pragma unroll
+        for (int v = 0; v < 4; ++v)
+          if (j + v < a.nq) grow[v] = g[v];
+      }
+    }
+  }
+}
+
+}  // namespace
+
+int launch_block_scores(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s) {
+  (void)d;
+  ScoreArgs a;
+  a.qp = (const float*)(ws + L.off_q_pool);
+  a.dq = (const float*)(ws + L.off_q_mad);
+  a.kc = (const float*)(ws + L.off_k_cat);
+  a.dk = (const float*)(ws + L.off_k_mad);
+  a.scores = (float*)(ws + L.off_scores);
+  a.nogapr = (uint8_t*)(ws + L.off_nogapr);
+  a.nq = L.nq;
+  a.nkc = L.nkc;
+  a.score_ld = L.score_ld;
+  a.nogapr_ld = L.nogapr_ld;
+  if (L.nq == 0) return RSA_OK;
+  dim3 grid((L.nkc + TJ - 1) / TJ, (L.nq + TI - 1) / TI, L.bh);
+  block_scores_kernel<<<grid, kThreads, 0, s>>>(a);
+  RSA_CUDA_CHECK(cudaGetLastError());
+  return RSA_OK;
+}
+
+}  // namespace rsa

@@ -1,0 +1,333 @@
+// rsa_api.cu -- the C ABI of librsa_b200.so (declared in include/rsa.h): argument validation, workspace
+// carve-up and stage sequencing.  No allocation, no host synchronisation, everything on the caller's stream.
+#include <math.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "rsa_common.cuh"
+
+namespace rsa {
+
+static thread_local char g_err[512] = "";
+int g_attention_impl = 0;
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int validate_desc(const rsa_attn_desc* d) {
+  if (!d) RSA_FAIL(RSA_ERR_ARG, "descriptor is null");
+  if (d->head_dim != RSA_HEAD_DIM)
+    RSA_FAIL(RSA_ERR_UNSUPPORTED, "head_dim must be 128 (got %d); the reference asserts Lk in {16,32,64,128}", d->head_dim);
+  if (d->batch <= 0 || d->heads <= 0 || d->seq <= 0) RSA_FAIL(RSA_ERR_ARG, "batch/heads/seq must be positive");
+  if ((int64_t)d->batch * d->heads > 65535) RSA_FAIL(RSA_ERR_UNSUPPORTED, "batch*heads > 65535");
+  if (d->family != RSA_FAMILY_WAN && d->family != RSA_FAMILY_JOINT) RSA_FAIL(RSA_ERR_ARG, "unknown family %d", d->family);
+  const int nb = (d->seq + RSA_BLOCK - 1) / RSA_BLOCK;
+  if (d->n_blocks != nb) RSA_FAIL(RSA_ERR_ARG, "n_blocks=%d but ceil(seq/128)=%d", d->n_blocks, nb);
+  if (d->nq_blocks < 0 || d->nq_blocks > nb) RSA_FAIL(RSA_ERR_ARG, "nq_blocks=%d out of [0,%d]", d->nq_blocks, nb);
+  if (d->family == RSA_FAMILY_WAN) {
+    if (d->nq_blocks != nb || d->text_keys != 0) RSA_FAIL(RSA_ERR_ARG, "WAN family needs nq_blocks == n_blocks and text_keys == 0");
+  } else {
+    if (d->nq_blocks >= nb) RSA_FAIL(RSA_ERR_ARG, "JOINT family needs at least one text block");
+    if (d->text_keys < 1 || (int64_t)d->nq_blocks * RSA_BLOCK + d->text_keys > (int64_t)nb * RSA_BLOCK)
+      RSA_FAIL(RSA_ERR_ARG, "text_keys=%d must be in [1, 128*(n_blocks - nq_blocks)]", d->text_keys);
+  }
+  const int n_ent = d->nq_blocks + (d->family == RSA_FAMILY_JOINT ? 1 : 0);
+  if (n_ent > RSA_MAX_ENTRIES) RSA_FAIL(RSA_ERR_UNSUPPORTED, "more than %d sortable blocks per row", RSA_MAX_ENTRIES);
+  if (nb > 65535) RSA_FAIL(RSA_ERR_UNSUPPORTED, "more than 65535 KV blocks");
+  if (d->kv_len < 1 || d->kv_len > d->seq) RSA_FAIL(RSA_ERR_ARG, "kv_len=%d out of [1, seq]", d->kv_len);
+  if (d->kv_zero_from < 0) RSA_FAIL(RSA_ERR_ARG, "kv_zero_from < 0");
+  if (d->text_end_block < d->nq_blocks || d->text_end_block > nb) RSA_FAIL(RSA_ERR_ARG, "text_end_block out of range");
+  if (d->top_k < 0 || d->first_frame_blocks < 0) RSA_FAIL(RSA_ERR_ARG, "top_k / first_frame_blocks negative");
+  if (!(d->p_remain >= 0.f)) RSA_FAIL(RSA_ERR_ARG, "p_remain must be >= 0");
+  if (d->text_q_valid < 0 ||
+      (d->family == RSA_FAMILY_JOINT && d->text_q_valid > d->seq - d->nq_blocks * RSA_BLOCK))
+    RSA_FAIL(RSA_ERR_ARG, "text_q_valid out of range");
+  if ((d->nbr_rows > 0) != (d->nbr_cols > 0) || (d->nbr_rows > 0 && !d->nbr)) RSA_FAIL(RSA_ERR_ARG, "neighbour matrix inconsistent");
+  const int64_t* st[4] = {d->q_stride, d->k_stride, d->v_stride, d->o_stride};
+  for (int t = 0; t < 4; ++t)
+    for (int i = 0; i < 3; ++i)
+      if (st[t][i] < 0 || st[t][i] % 8) RSA_FAIL(RSA_ERR_UNSUPPORTED, "strides must be non-negative multiples of 8 elements (16 bytes)");
+  return RSA_OK;
+}
+
+WsLayout make_layout(const rsa_attn_desc* d) {
+  WsLayout L;
+  L.bh = d->batch * d->heads;
+  L.nq = d->nq_blocks;
+  L.nb = d->n_blocks;
+  L.nqt = d->n_blocks;  // every 128-row query tile (visual + text) gets a list
+  L.a = d->text_keys;
+  L.nkc = L.nq + L.a;
+  L.score_ld = (int)align_up(L.nkc, 4);
+  L.n_entries = L.nq + (d->family == RSA_FAMILY_JOINT ? 1 : 0);
+  L.ent_ld = (int)align_up(L.n_entries, 4);
+  L.mask_words = (L.nb + 31) / 32;
+  L.nogapr_ld = (int)align_up(L.nq > 0 ? L.nq : 1, 4);
+  size_t o = 0;
+  auto take = [&](size_t bytes) {
+    size_t at = o;
+    o = align_up(o + bytes, 256);
+    return at;
+  };
+  const size_t f = sizeof(float);
+  L.off_q_pool = take((size_t)L.bh * L.nq * 128 * f);
+  L.off_q_mad = take((size_t)L.bh * L.nq * 128 * f);
+  L.off_k_cat = take((size_t)L.bh * L.nkc * 128 * f);
+  L.off_k_mad = take((size_t)L.bh * L.nq * 128 * f);
+  L.off_v_pool = take((size_t)L.bh * L.nb * 128 * f);
+  L.off_scores = take((size_t)L.bh * L.nq * L.score_ld * f);
+  L.off_nogapr = take((size_t)L.bh * L.nq * L.nogapr_ld);
+  L.off_probs = take(d->debug_dump_probs ? (size_t)L.bh * L.nq * L.ent_ld * f : 0);
+  L.off_w = take((size_t)L.bh * L.nq * L.ent_ld * f);
+  L.off_mask = take((size_t)L.bh * L.nqt * L.mask_words * 4);
+  L.off_kidx = take((size_t)L.bh * L.nqt * L.nb * 2);
+  L.off_kcnt = take((size_t)L.bh * L.nqt * 4);
+  L.off_nneed = take((size_t)L.bh * (L.nq > 0 ? L.nq : 1) * 4);
+  L.off_R = take((size_t)L.bh * L.nqt * f);
+  L.off_C = take((size_t)L.bh * L.nqt * 128 * f);
+  L.total = o;
+  return L;
+}
+
+int check_ws(const rsa_attn_desc* d, const void* ws, size_t bytes, WsLayout* out) {
+  int rc = validate_desc(d);
+  if (rc != RSA_OK) return rc;
+  *out = make_layout(d);
+  if (!ws) RSA_FAIL(RSA_ERR_WORKSPACE, "workspace is null");
+  if ((uintptr_t)ws % 256) RSA_FAIL(RSA_ERR_WORKSPACE, "workspace must be 256-byte aligned");
+  if (bytes < out->total) RSA_FAIL(RSA_ERR_WORKSPACE, "workspace too small: %zu < %zu", bytes, out->total);
+  return RSA_OK;
+}
+
+static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out, char* ws,
+                          const WsLayout& L, AttnArgs* a) {
+  a->q = (const __nv_bfloat16*)q;
+  a->k = (const __nv_bfloat16*)k;
+  a->v = (const __nv_bfloat16*)v;
+  a->o = (__nv_bfloat16*)out;
+  a->batch = d->batch;
+  a->heads = d->heads;
+  for (int i = 0; i < 3; ++i) {
+    a->qs[i] = d->q_stride[i];
+    a->ks[i] = d->k_stride[i];
+    a->vs[i] = d->v_stride[i];
+    a->os[i] = d->o_stride[i];
+  }
+  a->seq_q = d->seq;
+  a->seq_kv = d->seq;
+  a->kv_len = d->kv_len;
+  a->q_valid = d->family == RSA_FAMILY_JOINT ? d->nq_blocks * RSA_BLOCK + d->text_q_valid : d->seq;
+  if (a->q_valid > d->seq) a->q_valid = d->seq;
+  a->nqt = L.nqt;
+  a->nb = L.nb;
+  a->kept_idx = (const uint16_t*)(ws + L.off_kidx);
+  a->kept_cnt = (const int32_t*)(ws + L.off_kcnt);
+  a->R = (const float*)(ws + L.off_R);
+  a->C = (const float*)(ws + L.off_C);
+  a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.4426950408889634);
+  return RSA_OK;
+}
+
+static int launch_attention(const AttnArgs& a, cudaStream_t s) {
+  return g_attention_impl == 1 ? launch_attention_mma(a, s) : launch_attention_tc5(a, s);
+}
+
+// dense byte mask [bh, nq, nkv] -> ascending u16 lists (one warp per row)
+__global__ void mask_to_lists_kernel(const uint8_t* __restrict__ mask, int rows, int nkv, int kv_blocks_valid,
+                                     uint16_t* __restrict__ kept_idx, int32_t* __restrict__ kept_cnt) {
+  const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (row >= rows) return;
+  const uint8_t* m = mask + (int64_t)row * nkv;
+  uint16_t* out = kept_idx + (int64_t)row * nkv;
+  int base = 0;
+  for (int j0 = 0; j0 < nkv; j0 += 32) {
+    const int j = j0 + lane;
+    const bool on = j < nkv && j < kv_blocks_valid && m[j] != 0;
+    const uint32_t bal = __ballot_sync(0xffffffffu, on);
+    if (on) out[base + __popc(bal & ((1u << lane) - 1u))] = (uint16_t)j;
+    base += __popc(bal);
+  }
+  if (lane == 0) kept_cnt[row] = base;
+}
+
+int launch_mask_to_lists(const uint8_t* mask, int bh, int nq, int nkv, int kv_blocks_valid, uint16_t* kept_idx,
+                         int32_t* kept_cnt, cudaStream_t s) {
+  const int rows = bh * nq;
+  if (rows == 0) return RSA_OK;
+  mask_to_lists_kernel<<<(rows + 7) / 8, 256, 0, s>>>(mask, rows, nkv, kv_blocks_valid, kept_idx, kept_cnt);
+  RSA_CUDA_CHECK(cudaGetLastError());
+  return RSA_OK;
+}
+
+}  // namespace rsa
+
+using namespace rsa;
+
+extern "C" const char* rsa_last_error_string(void) { return g_err; }
+extern "C" int rsa_version(void) { return RSA_VERSION; }
+
+extern "C" int rsa_device_ok(void) {
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  cudaDeviceProp p;
+  if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
+  return p.major == 10 ? 1 : 0;
+}
+
+extern "C" int rsa_set_attention_impl(int impl) {
+  const int prev = g_attention_impl;
+  g_attention_impl = impl == 1 ? 1 : 0;
+  return prev;
+}
+
+extern "C" size_t rsa_attn_workspace_bytes(const rsa_attn_desc* d) {
+  if (validate_desc(d) != RSA_OK) return 0;
+  return make_layout(d).total;
+}
+
+extern "C" int rsa_attn_workspace_view(const rsa_attn_desc* d, void* workspace, size_t bytes, rsa_ws_view* out) {
+  WsLayout L;
+  int rc = check_ws(d, workspace, bytes, &L);
+  if (rc != RSA_OK) return rc;
+  if (!out) RSA_FAIL(RSA_ERR_ARG, "view pointer is null");
+  char* ws = (char*)workspace;
+  out->q_pool = (float*)(ws + L.off_q_pool);
+  out->q_mad = (float*)(ws + L.off_q_mad);
+  out->k_cat = (float*)(ws + L.off_k_cat);
+  out->k_mad = (float*)(ws + L.off_k_mad);
+  out->v_pool = (float*)(ws + L.off_v_pool);
+  out->scores = (float*)(ws + L.off_scores);
+  out->nogapr = (uint8_t*)(ws + L.off_nogapr);
+  out->probs = d->debug_dump_probs ? (float*)(ws + L.off_probs) : nullptr;
+  out->w_skip = (float*)(ws + L.off_w);
+  out->mask_bits = (uint32_t*)(ws + L.off_mask);
+  out->kept_idx = (uint16_t*)(ws + L.off_kidx);
+  out->kept_cnt = (int32_t*)(ws + L.off_kcnt);
+  out->n_needed = (int32_t*)(ws + L.off_nneed);
+  out->R = (float*)(ws + L.off_R);
+  out->C = (float*)(ws + L.off_C);
+  out->nkc = L.nkc;
+  out->score_ld = L.score_ld;
+  out->n_entries = L.n_entries;
+  out->ent_ld = L.ent_ld;
+  out->mask_words = L.mask_words;
+  out->nqt = L.nqt;
+  out->nogapr_ld = L.nogapr_ld;
+  out->reserved = 0;
+  return RSA_OK;
+}
+
+extern "C" int rsa_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* workspace,
+                              size_t bytes, void* stream) {
+  WsLayout L;
+  int rc = check_ws(d, workspace, bytes, &L);
+  if (rc != RSA_OK) return rc;
+  if (!q || !k || !v) RSA_FAIL(RSA_ERR_ARG, "rsa_pool_stats: null tensor");
+  return launch_pool_stats(d, q, k, v, (char*)workspace, L, (cudaStream_t)stream);
+}
+
+extern "C" int rsa_block_scores(const rsa_attn_desc* d, void* workspace, size_t bytes, void* stream) {
+  WsLayout L;
+  int rc = check_ws(d, workspace, bytes, &L);
+  if (rc != RSA_OK) return rc;
+  return launch_block_scores(d, (char*)workspace, L, (cudaStream_t)stream);
+}
+
+extern "C" int rsa_block_select(const rsa_attn_desc* d, void* workspace, size_t bytes, void* stream) {
+  WsLayout L;
+  int rc = check_ws(d, workspace, bytes, &L);
+  if (rc != RSA_OK) return rc;
+  return launch_block_select(d, (char*)workspace, L, (cudaStream_t)stream);
+}
+
+extern "C" int rsa_rect_c(const rsa_attn_desc* d, void* workspace, size_t bytes, void* stream) {
+  WsLayout L;
+  int rc = check_ws(d, workspace, bytes, &L);
+  if (rc != RSA_OK) return rc;
+  return launch_rect_c(d, (char*)workspace, L, (cudaStream_t)stream);
+}
+
+extern "C" int rsa_sparse_attention(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
+                                    void* workspace, size_t bytes, void* stream) {
+  WsLayout L;
+  int rc = check_ws(d, workspace, bytes, &L);
+  if (rc != RSA_OK) return rc;
+  if (!q || !k || !v || !out) RSA_FAIL(RSA_ERR_ARG, "rsa_sparse_attention: null tensor");
+  AttnArgs a;
+  fill_attn_args(d, q, k, v, out, (char*)workspace, L, &a);
+  return launch_attention(a, (cudaStream_t)stream);
+}
+
+extern "C" int rsa_rectified_attention(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
+                                       void* workspace, size_t bytes, void* stream) {
+  WsLayout L;
+  int rc = check_ws(d, workspace, bytes, &L);
+  if (rc != RSA_OK) return rc;
+  if (!q || !k || !v || !out) RSA_FAIL(RSA_ERR_ARG, "rsa_rectified_attention: null tensor");
+  char* ws = (char*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = launch_pool_stats(d, q, k, v, ws, L, s)) != RSA_OK) return rc;
+  if ((rc = launch_block_scores(d, ws, L, s)) != RSA_OK) return rc;
+  if ((rc = launch_block_select(d, ws, L, s)) != RSA_OK) return rc;
+  if ((rc = launch_rect_c(d, ws, L, s)) != RSA_OK) return rc;
+  AttnArgs a;
+  fill_attn_args(d, q, k, v, out, ws, L, &a);
+  return launch_attention(a, s);
+}
+
+extern "C" size_t rsa_masked_attention_workspace_bytes(int bh, int nq, int nkv) {
+  if (bh <= 0 || nq <= 0 || nkv <= 0) return 0;
+  return align_up((size_t)bh * nq * nkv * 2, 256) + align_up((size_t)bh * nq * 4, 256);
+}
+
+extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v, void* out, int bh, int seq_q,
+                                    int seq_kv, int kv_len, const int64_t q_stride[2], const int64_t k_stride[2],
+                                    const int64_t v_stride[2], const int64_t o_stride[2], const uint8_t* block_mask,
+                                    int n_q_blocks, int n_kv_blocks, void* workspace, size_t bytes, void* stream) {
+  if (!q || !k || !v || !out || !block_mask) RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: null pointer");
+  if (bh <= 0 || bh > 65535 || seq_q <= 0 || seq_kv <= 0 || kv_len < 1 || kv_len > seq_kv)
+    RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: bad sizes");
+  if (n_q_blocks != (seq_q + 127) / 128 || n_kv_blocks != (seq_kv + 127) / 128)
+    RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: block counts do not match the sequence lengths");
+  const size_t need = rsa_masked_attention_workspace_bytes(bh, n_q_blocks, n_kv_blocks);
+  if (!workspace || bytes < need || (uintptr_t)workspace % 256) RSA_FAIL(RSA_ERR_WORKSPACE, "rsa_masked_attention: workspace");
+  const int64_t* st[4] = {q_stride, k_stride, v_stride, o_stride};
+  for (int t = 0; t < 4; ++t)
+    for (int i = 0; i < 2; ++i)
+      if (st[t][i] < 0 || st[t][i] % 8) RSA_FAIL(RSA_ERR_UNSUPPORTED, "strides must be multiples of 8 elements");
+  char* ws = (char*)workspace;
+  uint16_t* kidx = (uint16_t*)ws;
+  int32_t* kcnt = (int32_t*)(ws + align_up((size_t)bh * n_q_blocks * n_kv_blocks * 2, 256));
+  cudaStream_t s = (cudaStream_t)stream;
+  int rc = launch_mask_to_lists(block_mask, bh, n_q_blocks, n_kv_blocks, (kv_len + 127) / 128, kidx, kcnt, s);
+  if (rc != RSA_OK) return rc;
+  AttnArgs a;
+  a.q = (const __nv_bfloat16*)q;
+  a.k = (const __nv_bfloat16*)k;
+  a.v = (const __nv_bfloat16*)v;
+  a.o = (__nv_bfloat16*)out;
+  a.batch = 1;
+  a.heads = bh;
+  a.qs[0] = a.ks[0] = a.vs[0] = a.os[0] = 0;
+  a.qs[1] = q_stride[0], a.qs[2] = q_stride[1];
+  a.ks[1] = k_stride[0], a.ks[2] = k_stride[1];
+  a.vs[1] = v_stride[0], a.vs[2] = v_stride[1];
+  a.os[1] = o_stride[0], a.os[2] = o_stride[1];
+  a.seq_q = seq_q;
+  a.seq_kv = seq_kv;
+  a.kv_len = kv_len;
+  a.q_valid = seq_q;
+  a.nqt = n_q_blocks;
+  a.nb = n_kv_blocks;
+  a.kept_idx = kidx;
+  a.kept_cnt = kcnt;
+  a.R = nullptr;
+  a.C = nullptr;
+  a.scale_log2 = (float)((1.0 / sqrt(128.0)) * 1.4426950408889634);
+  return launch_attention(a, s);
+}

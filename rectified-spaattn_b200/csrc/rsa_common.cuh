@@ -1,0 +1,73 @@
+// rsa_common.cuh -- shared host/device helpers for librsa_b200.so (sm_100a only).
+#pragma once
+
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "rsa.h"
+
+namespace rsa {
+
+void set_error(const char* fmt, ...);
+
+#define RSA_FAIL(code, ...)       \
+  do {                            \
+    ::rsa::set_error(__VA_ARGS__);\
+    return (code);                \
+  } while (0)
+
+#define RSA_CUDA_CHECK(expr)                                                            \
+  do {                                                                                  \
+    cudaError_t _e = (expr);                                                            \
+    if (_e != cudaSuccess) RSA_FAIL(RSA_ERR_CUDA, "%s: %s", #expr, cudaGetErrorString(_e)); \
+  } while (0)
+
+inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Workspace carve-up shared by every stage (offsets in bytes from a 256-B aligned base).
+struct WsLayout {
+  int bh, nq, nb, nqt, a, nkc, score_ld, n_entries, ent_ld, mask_words, nogapr_ld;
+  size_t off_q_pool, off_q_mad, off_k_cat, off_k_mad, off_v_pool, off_scores, off_nogapr, off_probs, off_w,
+      off_mask, off_kidx, off_kcnt, off_nneed, off_R, off_C, total;
+};
+
+int validate_desc(const rsa_attn_desc* d);
+WsLayout make_layout(const rsa_attn_desc* d);
+int check_ws(const rsa_attn_desc* d, const void* ws, size_t bytes, WsLayout* out);
+
+// stage launchers (defined in the .cu files)
+int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, const void* v, char* ws,
+                      const WsLayout& L, cudaStream_t s);
+int launch_block_scores(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);
+int launch_block_select(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);
+int launch_rect_c(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);
+
+// Attention kernel arguments common to both implementations.  q/k/v/o are addressed as [bh][token][128].
+struct AttnArgs {
+  const __nv_bfloat16 *q, *k, *v;
+  __nv_bfloat16* o;
+  int batch, heads;         // bh = batch*heads; head index = bh % heads, batch index = bh / heads
+  int64_t qs[3], ks[3], vs[3], os[3];  // element strides (batch, head, token)
+  int seq_q;                // query rows that exist (rows >= seq_q are neither read nor written)
+  int seq_kv;               // key rows that exist in memory
+  int kv_len;               // keys >= kv_len masked to -inf
+  int q_valid;              // query rows >= q_valid are written as zeros
+  int nqt;                  // query tiles per head
+  int nb;                   // kv blocks per head (row length of kept_idx)
+  const uint16_t* kept_idx; // [bh, nqt, nb]
+  const int32_t* kept_cnt;  // [bh, nqt]
+  const float* R;           // [bh, nqt]  or nullptr (=1)
+  const float* C;           // [bh, nqt, 128] or nullptr (=0)
+  float scale_log2;         // head_dim^-0.5 * log2(e)
+};
+
+int launch_attention_mma(const AttnArgs& a, cudaStream_t s);      // mma.sync cross-check kernel
+int launch_attention_tc5(const AttnArgs& a, cudaStream_t s);      // tcgen05 / TMEM / TMA kernel
+int launch_mask_to_lists(const uint8_t* mask, int bh, int nq, int nkv, int kv_blocks_valid, uint16_t* kept_idx,
+                         int32_t* kept_cnt, cudaStream_t s);
+
+extern int g_attention_impl;
+
+}  // namespace rsa

@@ -1,0 +1,91 @@
+"""ctypes binding of librsa_b200.so (C ABI declared in include/rsa.h).
+
+There is no CPU fallback: importing this module without the built library raises, and every call that touches
+the GPU raises RsaError when the library reports a failure."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "librsa_b200.so")
+
+RSA_OK = 0
+FAMILY_WAN, FAMILY_JOINT = 0, 1
+BLOCK = 128
+
+
+class RsaError(RuntimeError):
+    pass
+
+
+class AttnDesc(C.Structure):
+    _fields_ = [
+        ("batch", C.c_int32), ("heads", C.c_int32), ("seq", C.c_int32), ("head_dim", C.c_int32),
+        ("q_stride", C.c_int64 * 3), ("k_stride", C.c_int64 * 3), ("v_stride", C.c_int64 * 3),
+        ("o_stride", C.c_int64 * 3),
+        ("family", C.c_int32), ("n_blocks", C.c_int32), ("nq_blocks", C.c_int32), ("text_keys", C.c_int32),
+        ("kv_len", C.c_int32), ("kv_zero_from", C.c_int32), ("text_end_block", C.c_int32),
+        ("text_q_valid", C.c_int32), ("top_k", C.c_int32), ("p_remain", C.c_float),
+        ("first_frame_blocks", C.c_int32), ("nbr_rows", C.c_int32), ("nbr_cols", C.c_int32),
+        ("nbr", C.c_void_p), ("debug_dump_probs", C.c_int32), ("reserved", C.c_int32),
+    ]
+
+
+class WsView(C.Structure):
+    _fields_ = [(n, C.c_void_p) for n in (
+        "q_pool", "q_mad", "k_cat", "k_mad", "v_pool", "scores", "nogapr", "probs", "w_skip", "mask_bits",
+        "kept_idx", "kept_cnt", "n_needed", "R", "C")] + [(n, C.c_int32) for n in (
+            "nkc", "score_ld", "n_entries", "ent_ld", "mask_words", "nqt", "nogapr_ld", "reserved")]
+
+
+EXPORTS = [
+    "rsa_last_error_string", "rsa_version", "rsa_device_ok", "rsa_gilbert_map", "rsa_gilbert_block_neighbors",
+    "rsa_permute_rows", "rsa_attn_workspace_bytes", "rsa_attn_workspace_view", "rsa_pool_stats",
+    "rsa_block_scores", "rsa_block_select", "rsa_rect_c", "rsa_sparse_attention", "rsa_rectified_attention",
+    "rsa_masked_attention_workspace_bytes", "rsa_masked_attention", "rsa_set_attention_impl",
+]
+
+_lib = None
+
+
+def lib():
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RsaError(
+            f"{LIB_PATH} is missing: build it with `python rectified-spaattn_b200/build_native.py` "
+            "(there is no CPU or PyTorch fallback for this path)")
+    L = C.CDLL(LIB_PATH)
+    p, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
+    L.rsa_last_error_string.restype = C.c_char_p
+    L.rsa_version.restype = i32
+    L.rsa_device_ok.restype = i32
+    L.rsa_gilbert_map.argtypes = [i32, i32, i32, C.c_char_p, p, p]
+    L.rsa_gilbert_block_neighbors.argtypes = [i32, i32, i32, i32, C.c_char_p, p]
+    L.rsa_permute_rows.argtypes = [p, p, p, i32, i64, i64, i64, i64, i64, p]
+    L.rsa_attn_workspace_bytes.argtypes = [C.POINTER(AttnDesc)]
+    L.rsa_attn_workspace_bytes.restype = sz
+    L.rsa_attn_workspace_view.argtypes = [C.POINTER(AttnDesc), p, sz, C.POINTER(WsView)]
+    L.rsa_pool_stats.argtypes = [C.POINTER(AttnDesc), p, p, p, p, sz, p]
+    for n in ("rsa_block_scores", "rsa_block_select", "rsa_rect_c"):
+        getattr(L, n).argtypes = [C.POINTER(AttnDesc), p, sz, p]
+    L.rsa_sparse_attention.argtypes = [C.POINTER(AttnDesc), p, p, p, p, p, sz, p]
+    L.rsa_rectified_attention.argtypes = [C.POINTER(AttnDesc), p, p, p, p, p, sz, p]
+    L.rsa_masked_attention_workspace_bytes.argtypes = [i32, i32, i32]
+    L.rsa_masked_attention_workspace_bytes.restype = sz
+    L.rsa_masked_attention.argtypes = [p, p, p, p, i32, i32, i32, i32, C.POINTER(i64), C.POINTER(i64),
+                                       C.POINTER(i64), C.POINTER(i64), p, i32, i32, p, sz, p]
+    L.rsa_set_attention_impl.argtypes = [i32]
+    for n in EXPORTS:
+        f = getattr(L, n)
+        if f.restype is C.c_int and n not in ("rsa_version", "rsa_device_ok", "rsa_set_attention_impl"):
+            pass
+    _lib = L
+    return L
+
+
+def check(rc, what):
+    if rc != RSA_OK:
+        raise RsaError(f"{what} failed ({rc}): {lib().rsa_last_error_string().decode()}")

@@ -1,0 +1,269 @@
+"""Host-side plumbing over the C ABI: PyTorch supplies device memory and the current CUDA stream, nothing else.
+
+Every function here fails loudly (RsaError / RuntimeError) when the native library is missing or a tensor is
+not on a CUDA device -- there is no eager-PyTorch fallback for the hot path."""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+
+from . import geometry as G
+from . import native as N
+
+BLOCK = 128
+
+
+# --------------------------------------------------------------------------------------------- host geometry
+def gilbert_mapping(t, h, w, axis_order=("w", "h", "t")):
+    """(linear_to_hilbert, hilbert_to_linear) as CPU int64 tensors (utils/jenga_gilbert.py:458-504)."""
+    n = t * h * w
+    l2h = torch.empty(n, dtype=torch.int64)
+    h2l = torch.empty(n, dtype=torch.int64)
+    ao = None if axis_order is None else "".join(axis_order).encode()
+    N.check(N.lib().rsa_gilbert_map(t, h, w, ao, l2h.data_ptr(), h2l.data_ptr()), "rsa_gilbert_map")
+    return l2h, h2l
+
+
+def gilbert_block_neighbors(t, h, w, block_size=128, axis_order=("w", "h", "t")):
+    """bool [NB, NB] CPU tensor (utils/jenga_gilbert.py:613-693)."""
+    nb = (t * h * w + block_size - 1) // block_size
+    out = torch.empty(nb, nb, dtype=torch.uint8)
+    ao = None if axis_order is None else "".join(axis_order).encode()
+    N.check(N.lib().rsa_gilbert_block_neighbors(t, h, w, block_size, ao, out.data_ptr()),
+            "rsa_gilbert_block_neighbors")
+    return out.bool()
+
+
+# --------------------------------------------------------------------------------------------------- permute
+def _need_cuda(x, name):
+    if not (isinstance(x, torch.Tensor) and x.is_cuda):
+        raise RuntimeError(f"{name} must be a CUDA tensor: this path has no CPU implementation")
+
+
+def _stream(dev):
+    return C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def permute_rows(x, index, out=None):
+    """out[b, i, :] = x[b, index[i], :]; x is [B, N, ...] (rows contiguous) or [N, ...]; index int64 on device.
+    Replaces hidden_states[:, self.hilbert_order] (scripts/main_hunyuan.py:88-89, :183)."""
+    _need_cuda(x, "x")
+    squeeze = False
+    if x.dim() == 2:
+        x = x.unsqueeze(0)
+        squeeze = True
+    if x.dim() < 3:
+        raise ValueError("permute_rows expects [B, N, C] or [N, C]")
+    if index.dtype != torch.int64 or not index.is_cuda:
+        index = index.to(device=x.device, dtype=torch.int64)
+    index = index.contiguous()
+    b, n = x.shape[0], x.shape[1]
+    row_shape = x.shape[2:]
+    row_elems = math.prod(row_shape)
+    if x[0].is_contiguous() is False:
+        x = x.contiguous()
+    row_bytes = row_elems * x.element_size()
+    n_out = index.numel()
+    if out is None:
+        out = torch.empty((b, n_out) + tuple(row_shape), dtype=x.dtype, device=x.device)
+    sb = x.stride(0) * x.element_size() if b > 1 else n * row_bytes
+    db = out.stride(0) * out.element_size() if b > 1 else n_out * row_bytes
+    with torch.cuda.device(x.device):
+        N.check(N.lib().rsa_permute_rows(x.data_ptr(), out.data_ptr(), index.data_ptr(), b, n_out, n, row_bytes, sb,
+                                         db, _stream(x.device)), "rsa_permute_rows")
+    return out[0] if squeeze else out
+
+
+# ------------------------------------------------------------------------------------------------- attention
+_nbr_cache = {}
+_ws_cache = {}
+
+
+def _device_neighbors(nbr, device):
+    """uint8 [rows, cols] device copy of block_neighbor_list, cached (the reference re-uploads it every call,
+    rectified_wan21_attn.py:261-262)."""
+    if nbr is None:
+        return None
+    key = (nbr.data_ptr(), tuple(nbr.shape), nbr.device.type, str(device), nbr._version)
+    hit = _nbr_cache.get(key)
+    if hit is not None and hit[0] is nbr:
+        return hit[1]
+    dev = nbr.to(device=device, dtype=torch.bool).contiguous().view(torch.uint8)
+    if len(_nbr_cache) > 16:
+        _nbr_cache.clear()
+    _nbr_cache[key] = (nbr, dev)
+    return dev
+
+
+def _workspace(device, nbytes):
+    key = str(device)
+    ws = _ws_cache.get(key)
+    if ws is None or ws.numel() < nbytes:
+        ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
+        _ws_cache[key] = ws
+    return ws
+
+
+def _strides3(t):
+    # [B, H, S, D] view -> (batch, head, token) element strides; D must be contiguous
+    if t.stride(3) != 1:
+        raise RuntimeError("head_dim must be the contiguous dimension")
+    return (t.stride(0), t.stride(1), t.stride(2))
+
+
+class Plan:
+    """One call's descriptor + workspace; build once per (shape, geometry) and reuse across layers/steps."""
+
+    def __init__(self, q, k, v, geo: G.BlockGeometry, top_k, p_remain, nbr=None, debug_dump_probs=False, out=None):
+        for t, n in ((q, "query"), (k, "key"), (v, "value")):
+            _need_cuda(t, n)
+            if t.dtype != torch.bfloat16:
+                raise RuntimeError(f"{n} must be bfloat16 (got {t.dtype})")
+        b, h, s, d = q.shape
+        if k.shape != q.shape or v.shape != q.shape:
+            raise RuntimeError("query/key/value shapes differ")
+        if d != 128:
+            # same precondition family as the reference's `assert Lk in {16, 32, 64, 128}` (wan21 :121)
+            raise AssertionError("head_dim must be 128")
+        if s != geo.seq:
+            raise ValueError("geometry was built for a different sequence length")
+        self.device = q.device
+        self.shape = (b, h, s, d)
+        self.out = out if out is not None else torch.empty((b, s, h, d), dtype=torch.bfloat16, device=q.device)
+        o4 = self.out.view(b, s, h, d).permute(0, 2, 1, 3)
+        self.nbr_dev = _device_neighbors(nbr, q.device)
+        desc = N.AttnDesc()
+        desc.batch, desc.heads, desc.seq, desc.head_dim = b, h, s, d
+        for name, t in (("q_stride", q), ("k_stride", k), ("v_stride", v), ("o_stride", o4)):
+            st = _strides3(t)
+            arr = getattr(desc, name)
+            for i in range(3):
+                arr[i] = st[i]
+        desc.family = geo.family
+        desc.n_blocks, desc.nq_blocks, desc.text_keys = geo.n_blocks, geo.nq_blocks, geo.text_keys
+        desc.kv_len, desc.kv_zero_from = geo.kv_len, geo.kv_zero_from
+        desc.text_end_block, desc.text_q_valid = geo.text_end_block, geo.text_q_valid
+        desc.top_k, desc.p_remain = int(top_k), float(p_remain)
+        desc.first_frame_blocks = geo.first_frame_blocks
+        if self.nbr_dev is not None:
+            desc.nbr_rows, desc.nbr_cols = self.nbr_dev.shape
+            desc.nbr = self.nbr_dev.data_ptr()
+        desc.debug_dump_probs = 1 if debug_dump_probs else 0
+        self.desc = desc
+        L = N.lib()
+        self.ws_bytes = L.rsa_attn_workspace_bytes(C.byref(desc))
+        if self.ws_bytes == 0:
+            raise N.RsaError("invalid attention descriptor: " + L.rsa_last_error_string().decode())
+        self.ws = _workspace(q.device, self.ws_bytes)
+        self.q, self.k, self.v = q, k, v
+
+    # --- stages (each enqueues on the current stream; no host sync)
+    def _call(self, fn, *args):
+        L = N.lib()
+        with torch.cuda.device(self.device):
+            N.check(getattr(L, fn)(C.byref(self.desc), *args, self.ws.data_ptr(), self.ws_bytes,
+                                   _stream(self.device)), fn)
+
+    def pool_stats(self):
+        self._call("rsa_pool_stats", self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr())
+
+    def block_scores(self):
+        self._call("rsa_block_scores")
+
+    def block_select(self):
+        self._call("rsa_block_select")
+
+    def rect_c(self):
+        self._call("rsa_rect_c")
+
+    def sparse_attention(self):
+        self._call("rsa_sparse_attention", self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(),
+                   self.out.data_ptr())
+        return self.out
+
+    def run(self):
+        self._call("rsa_rectified_attention", self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(),
+                   self.out.data_ptr())
+        return self.out
+
+    # --- workspace views for the parity tests
+    def view(self):
+        v = N.WsView()
+        N.check(N.lib().rsa_attn_workspace_view(C.byref(self.desc), self.ws.data_ptr(), self.ws_bytes, C.byref(v)),
+                "rsa_attn_workspace_view")
+        b, h, _, _ = self.shape
+        bh = b * h
+        g = self.desc
+        base = self.ws.data_ptr()
+
+        def t(ptr, shape, dtype):
+            if not ptr:
+                return None
+            n = math.prod(shape) * torch.empty((), dtype=dtype).element_size()
+            off = ptr - base
+            return self.ws[off: off + n].view(dtype).view(shape)
+
+        nq, nb = g.nq_blocks, g.n_blocks
+        return dict(
+            q_pool=t(v.q_pool, (bh, nq, 128), torch.float32), q_mad=t(v.q_mad, (bh, nq, 128), torch.float32),
+            k_cat=t(v.k_cat, (bh, v.nkc, 128), torch.float32), k_mad=t(v.k_mad, (bh, nq, 128), torch.float32),
+            v_pool=t(v.v_pool, (bh, nb, 128), torch.float32),
+            scores=t(v.scores, (bh, nq, v.score_ld), torch.float32)[:, :, : v.nkc],
+            nogapr=t(v.nogapr, (bh, nq, v.nogapr_ld), torch.uint8)[:, :, :nq],
+            probs=None if not v.probs else t(v.probs, (bh, nq, v.ent_ld), torch.float32)[:, :, : v.n_entries],
+            w_skip=t(v.w_skip, (bh, nq, v.ent_ld), torch.float32)[:, :, : v.n_entries],
+            mask_bits=t(v.mask_bits, (bh, v.nqt, v.mask_words), torch.int32),
+            kept_idx=t(v.kept_idx, (bh, v.nqt, nb), torch.int16),
+            kept_cnt=t(v.kept_cnt, (bh, v.nqt), torch.int32),
+            n_needed=t(v.n_needed, (bh, max(nq, 1)), torch.int32),
+            R=t(v.R, (bh, v.nqt), torch.float32), C=t(v.C, (bh, v.nqt, 128), torch.float32))
+
+    def dense_mask(self):
+        """bool [BH, NQT, NB] reconstructed from the kept-block bitmask (the reference's one_hot layout)."""
+        vw = self.view()
+        bits = vw["mask_bits"]
+        nb = self.desc.n_blocks
+        j = torch.arange(nb, device=bits.device)
+        words = bits[:, :, (j >> 5)]
+        return ((words >> (j & 31)) & 1).bool()
+
+
+def rectified_attention(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfuse=False):
+    """[B,H,S,D] bf16 -> [B,S,H*D] (or [B,S,H,D] with shape_xfuse) -- the reference's return layout
+    (rectified_wan21_attn.py:353-357)."""
+    out = Plan(q, k, v, geo, top_k, p_remain, nbr).run()
+    b, s, h, d = out.shape
+    return out if shape_xfuse else out.view(b, s, h * d)
+
+
+def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None):
+    """Kernel 4 alone on a dense block mask: the surface of _triton_block_sparse_attention_onehot
+    (rectified_wan21_attn.py:108-117).  q,k,v [B,H,S,D] bf16, block_mask bool [B,H,NQ,NB] -> [B,H,S,D]."""
+    _need_cuda(q, "q")
+    b, h, s, d = q.shape
+    assert d in (128,), "head_dim must be 128"
+    if sm_scale is not None and abs(sm_scale - d ** -0.5) > 1e-7:
+        raise ValueError("only sm_scale = head_dim ** -0.5 is supported")
+    q3, k3, v3 = (t.reshape(b * h, t.shape[2], d).contiguous() for t in (q, k, v))
+    skv = k3.shape[1]
+    nqb, nkb = (s + 127) // 128, (skv + 127) // 128
+    if tuple(block_mask.shape[-2:]) != (nqb, nkb):
+        raise ValueError("block_mask shape does not match the sequence lengths")
+    m = block_mask.reshape(b * h, nqb, nkb).to(device=q.device, dtype=torch.bool).contiguous().view(torch.uint8)
+    o = torch.zeros_like(q3)
+    L = N.lib()
+    nbytes = L.rsa_masked_attention_workspace_bytes(b * h, nqb, nkb)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
+    mk = lambda t: (C.c_int64 * 2)(t.stride(0), t.stride(1))
+    with torch.cuda.device(q.device):
+        N.check(L.rsa_masked_attention(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o.data_ptr(), b * h, s, skv,
+                                       int(kv_len), mk(q3), mk(k3), mk(v3), mk(o), m.data_ptr(), nqb, nkb,
+                                       ws.data_ptr(), nbytes, _stream(q.device)), "rsa_masked_attention")
+    return o.view(b, h, s, d)
+
+
+def set_attention_impl(impl):
+    """0 = tcgen05 kernel (product), 1 = mma.sync cross-check kernel (tests only)."""
+    return N.lib().rsa_set_attention_impl(int(impl))

@@ -189,7 +189,8 @@ def cpu_sample(wp, regime, budget_s=12.0, threads=None):
     while n_done < nq and t_attn < budget_s:
         n = min(n, nq - n_done)
         t1 = time.perf_counter()
-        O.masked_attention(q[n_done * 128:], k, v, m[n_done: n_done + n], geo.kv_len, n * 128)
+        O.masked_attention(q[n_done * 128:], k, v, m[n_done: n_done + n], geo.kv_len,
+                           min(n * 128, geo.seq - n_done * 128))
         t_attn += time.perf_counter() - t1
         n_done += n
         n *= 2

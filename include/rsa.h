@@ -164,6 +164,11 @@ int rsa_masked_attention(const void* q, const void* k, const void* v, void* out,
  * 1 = mma.sync cross-check kernel (tests only).  Returns the previous value. */
 int rsa_set_attention_impl(int impl);
 
+/* Bring-up hook (tests only): while non-null, the tcgen05 kernel's CTA for query tile 0 of batch*head 0 writes, as
+ * fp32, S of its first kept block [128x128], the un-normalised O [128x128], the row sums l [128] and the row
+ * maxima m [128] (log2 domain) to this DEVICE buffer of >= 33024 floats. */
+void rsa_debug_set_attention_dump(float* device_buffer);
+
 #ifdef __cplusplus
 }
 #endif

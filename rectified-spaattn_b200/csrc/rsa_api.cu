@@ -10,6 +10,7 @@ namespace rsa {
 
 static thread_local char g_err[512] = "";
 int g_attention_impl = 0;
+float* g_attention_dbg = nullptr;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -129,6 +130,7 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->R = (const float*)(ws + L.off_R);
   a->C = (const float*)(ws + L.off_C);
   a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.4426950408889634);
+  a->dbg = g_attention_dbg;
   return RSA_OK;
 }
 
@@ -184,6 +186,8 @@ extern "C" int rsa_set_attention_impl(int impl) {
   g_attention_impl = impl == 1 ? 1 : 0;
   return prev;
 }
+
+extern "C" void rsa_debug_set_attention_dump(float* device_buffer) { g_attention_dbg = device_buffer; }
 
 extern "C" size_t rsa_attn_workspace_bytes(const rsa_attn_desc* d) {
   if (validate_desc(d) != RSA_OK) return 0;
@@ -329,5 +333,6 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   a.R = nullptr;
   a.C = nullptr;
   a.scale_log2 = (float)((1.0 / sqrt(128.0)) * 1.4426950408889634);
+  a.dbg = g_attention_dbg;
   return launch_attention(a, s);
 }

@@ -44,6 +44,7 @@ EXPORTS = [
     "rsa_permute_rows", "rsa_attn_workspace_bytes", "rsa_attn_workspace_view", "rsa_pool_stats",
     "rsa_block_scores", "rsa_block_select", "rsa_rect_c", "rsa_sparse_attention", "rsa_rectified_attention",
     "rsa_masked_attention_workspace_bytes", "rsa_masked_attention", "rsa_set_attention_impl",
+    "rsa_debug_set_attention_dump",
 ]
 
 _lib = None
@@ -78,6 +79,8 @@ def lib():
     L.rsa_masked_attention.argtypes = [p, p, p, p, i32, i32, i32, i32, C.POINTER(i64), C.POINTER(i64),
                                        C.POINTER(i64), C.POINTER(i64), p, i32, i32, p, sz, p]
     L.rsa_set_attention_impl.argtypes = [i32]
+    L.rsa_debug_set_attention_dump.argtypes = [p]
+    L.rsa_debug_set_attention_dump.restype = None
     for n in EXPORTS:
         f = getattr(L, n)
         if f.restype is C.c_int and n not in ("rsa_version", "rsa_device_ok", "rsa_set_attention_impl"):

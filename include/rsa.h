@@ -166,8 +166,12 @@ int rsa_set_attention_impl(int impl);
 
 /* Bring-up hook (tests only): while non-null, the tcgen05 kernel's CTA for query tile 0 of batch*head 0 writes, as
  * fp32, S of its first kept block [128x128], the un-normalised O [128x128], the row sums l [128] and the row
- * maxima m [128] (log2 domain) to this DEVICE buffer of >= 33024 floats. */
+ * maxima m [128] (log2 domain), then from offset 33024 a clock trace (64 steps x 16 slots, cycles since CTA start) to
+ * this DEVICE buffer of >= 34048 floats. */
 void rsa_debug_set_attention_dump(float* device_buffer);
+/* Bring-up ablations, honoured only while a dump buffer is set: bit 0 = skip the softmax arithmetic (results are
+ * garbage; measures the TMA + tensor pipeline alone), bit 1 = no K/V loads after the first ring fill. */
+void rsa_debug_set_attention_flags(int flags);
 
 #ifdef __cplusplus
 }

@@ -7,18 +7,22 @@
 // (rectified_hunyuan_attn.py:371-380; text tiles simply carry a dense list with R = 1, C = 0) and the final
 // cat / permute / reshape (:383-387; the output is written straight into [B, S, H, D]).
 //
-// One CTA = one 128-row query tile of one (batch, head); two CTAs are co-resident per SM (each owns 256 of the
-// 512 TMEM columns and 112 KB of shared memory), so while one CTA's softmax warps work on S the tensor pipe runs
-// the other CTA's MMAs -- the ping-pong FlashAttention-style kernels build by hand falls out of the hardware
-// arbitration.  Per kept block j of the tile's list:
-//     warp 0 (TMA)      K_j, V_j tiles -> 16 KB shared-memory granules (128 rows x 64 bf16, 128-byte swizzle)
+// One CTA per SM works on TWO adjacent 128-row query tiles of one (batch, head) -- "slots" 0 and 1 -- each with
+// its own kept-block list, its own S/P and O accumulators in TMEM (4 x 128 columns = all 512) and its own softmax
+// warpgroup.  A single MMA-issuing thread alternates between the slots, so the tensor pipe runs slot 1's MMAs
+// while slot 0's softmax warpgroup is busy and vice versa (two co-resident single-tile CTAs lock into phase and
+// halve the throughput: measured).  Per kept block j of a slot's list:
+//     warp 0 (TMA)      K_j, V_j tiles -> 16 KB shared-memory granules (128 rows x 64 bf16, 128-byte swizzle),
+//                       (two per tile = one ring stage; 5 stages shared by both slots, filled in the order the
+//                       MMA warp consumes them)
 //     warp 1 (MMA)      S = Q K_j^T            8 x tcgen05.mma 128x128x16, A and B from shared memory
-//     warps 4-7         S (TMEM) -> registers, running max with lazy rescale of O, p = exp2(s*c - m), row sums,
-//                       P (bf16) -> TMEM over the S columns
-//     warp 1 (MMA)      O += P V_j             16 x tcgen05.mma 128x64x16, A = P from TMEM, B = V_j (MN-major)
-// and at the end warps 4-7 read O from TMEM, apply 1/l, R and C and store bf16 rows.
+//     warps 4-7 / 8-11  S (TMEM) -> registers, running max with lazy rescale of O, p = exp2(s*c - m), row sums,
+//                       P (bf16) -> TMEM over the S columns, handed over in two halves of 64 keys
+//     warp 1 (MMA)      O += P V_j             8 x tcgen05.mma 128x128x16, A = P from TMEM, B = V_j (MN-major)
+// and at the end of a list the slot's warpgroup reads O from TMEM, applies 1/l, R and C and stores bf16 rows.
 #include <cuda.h>
 #include <math.h>
+#include <stdlib.h>
 
 #include "ptx_sm100.cuh"
 #include "rsa_common.cuh"
@@ -28,38 +32,86 @@ namespace {
 
 using namespace ptx;
 
-constexpr int kThreads = 256;
+constexpr int kThreads = 384;    // warp 0 TMA, warp 1 MMA, warp 2 TMEM alloc, warp 3 idle, warps 4-7 / 8-11 softmax
 constexpr int kGranule = 16384;  // 128 rows x 64 bf16
-constexpr int kRing = 5;         // K/V granules in flight
-constexpr int kOffQ = 0;
-constexpr int kOffRing = 2 * kGranule;
-constexpr int kOffBar = kOffRing + kRing * kGranule;
-constexpr int kSmemBytes = kOffBar + 128;
-constexpr uint32_t kTmemCols = 256;  // S / P at [0,128), O at [128,256)
+constexpr int kStages = 5;       // K/V tiles (2 granules each) in flight, shared by both slots
+constexpr int kOffQ = 0;         // Q: [slot][head_dim half] granules
+constexpr int kOffRing = 4 * kGranule;
+constexpr int kOffBar = kOffRing + kStages * 2 * kGranule;
+constexpr int kSmemBytes = kOffBar + 256;
+constexpr uint32_t kTmemCols = 512;       // S/P of slot s at [128 s, +128), O of slot s at [256 + 128 s, +128)
 constexpr float kRescaleThreshold = 8.f;  // log2 units: O and l are rescaled only when the max grows by > 2^8
+// Of every 4 float2 pairs of exponentials, this many are evaluated on the FMA pipe (Cody-Waite range reduction +
+// degree-3 polynomial, max relative error 7.5e-5, far below the bf16 rounding of P) instead of MUFU.EX2.  On B200
+// the FMA pipe turned out to be the scarcer resource for this loop, so the default is 0.
+constexpr int kDefaultPolyPairs = 0;  // measured best on B200 (0: 1209, 1: 1180, 2: 1159, 3: 1066 TFLOP/s); RSA_TC5_POLY overrides
 
 // barrier slots (8 bytes each) inside the kOffBar region
-enum { B_QFULL = 0, B_SFULL = 1, B_PFULL = 2, B_OFULL = 3, B_KVFULL = 4, B_KVEMPTY = 4 + kRing, B_COUNT = 4 + 2 * kRing };
-static_assert(B_COUNT * 8 + 4 <= 128, "barrier region");
+enum {
+  B_QFULL = 0,   // [2]  TMA -> MMA: Q tile of the slot landed
+  B_SFULL = 2,   // [2]  MMA -> softmax: S = Q K^T complete
+  B_PHALF = 4,   // [2][2]  softmax -> MMA: P columns of key half 0 / 1 written (and O rescaled)
+  B_OFULL = 8,   // [2]  MMA -> softmax: last P V complete
+  B_KVFULL = 10,
+  B_KVEMPTY = 10 + kStages,
+  B_COUNT = 10 + 2 * kStages
+};
+static_assert(B_COUNT * 8 + 4 <= 256, "barrier region");
+static_assert(kSmemBytes <= 232448, "shared memory per CTA");
 
 constexpr uint32_t kIdescQK = umma_idesc_bf16(128, 128, false);
-constexpr uint32_t kIdescPV = umma_idesc_bf16(128, 64, true);
+constexpr uint32_t kIdescPV = umma_idesc_bf16(128, 128, true);
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
 
-__global__ void __launch_bounds__(kThreads, 2)
+// 2^x for x <= ~8 on the FMA pipe, two lanes at a time: x = n + f, n = round(x), f in [-0.5, 0.5];
+// 2^f ~ c0 + f (c1 + f (c2 + f c3)); the integer n is added into the exponent field.
+__device__ __forceinline__ float2 exp2_poly2(float2 x) {
+  const float kMagic = 12582912.f;  // 1.5 * 2^23: adding it leaves round(x) in the low mantissa bits
+  x.x = fmaxf(x.x, -125.f);
+  x.y = fmaxf(x.y, -125.f);
+  const float2 t = __fadd2_rn(x, make_float2(kMagic, kMagic));
+  const float2 r = __fadd2_rn(t, make_float2(-kMagic, -kMagic));
+  const float2 f = __ffma2_rn(r, make_float2(-1.f, -1.f), x);
+  float2 p = __ffma2_rn(f, make_float2(0.05517587438225746f, 0.05517587438225746f),
+                        make_float2(0.24261151254177094f, 0.24261151254177094f));
+  p = __ffma2_rn(p, f, make_float2(0.6932601928710938f, 0.6932601928710938f));
+  p = __ffma2_rn(p, f, make_float2(0.9999279975891113f, 0.9999279975891113f));
+  p.x = __int_as_float(__float_as_int(p.x) + (__float_as_int(t.x) << 23));
+  p.y = __int_as_float(__float_as_int(p.y) + (__float_as_int(t.y) << 23));
+  return p;
+}
+
+// kDebug: bring-up instantiation that also dumps S / O / l / m and a clock trace of one CTA (rsa.h,
+// rsa_debug_set_attention_dump); the product instantiation carries none of that code.
+constexpr int kTraceBase = 33024, kTraceSteps = 64, kTraceSlots = 16;
+#define RSA_TRACE(cond, step, slot)                                                                  \
+  do {                                                                                               \
+    if (kDebug && (cond) && (step) >= 0 && (step) < kTraceSteps)                                       \
+      a.dbg[kTraceBase + (step) * kTraceSlots + (slot)] = (float)(clock64() - t0);                     \
+  } while (0)
+
+template <bool kDebug, int kPolyPairs>
+__global__ void __launch_bounds__(kThreads, 1)
 attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int tile = a.nqt - 1 - (int)blockIdx.x;  // dense (text) tiles are the longest: schedule them first
+  // pairs of adjacent query tiles; the last pairs hold the dense (text) tiles, the longest: schedule them first
+  const int pair = (int)gridDim.x - 1 - (int)blockIdx.x;
   const int bh = blockIdx.y;
   const int b = bh / a.heads, h = bh % a.heads;
-  const int64_t lrow = (int64_t)bh * a.nqt + tile;
-  const int cnt = a.kept_cnt[lrow];
-  const uint16_t* __restrict__ list = a.kept_idx + lrow * a.nb;
+  const int tile0 = 2 * pair, tile1 = 2 * pair + 1;
+  const int64_t lrow0 = (int64_t)bh * a.nqt + tile0;
+  const int cnt0 = a.kept_cnt[lrow0];
+  const int cnt1 = tile1 < a.nqt ? a.kept_cnt[lrow0 + 1] : 0;
+  const uint16_t* __restrict__ list0 = a.kept_idx + lrow0 * a.nb;
+  const uint16_t* __restrict__ list1 = list0 + a.nb;
+  const int rounds = max(cnt0, cnt1);
 
+  const long long t0 = kDebug ? clock64() : 0;
+  const bool dbg = kDebug && a.dbg != nullptr && lrow0 == 0;
   const uint32_t sbase = smem_u32(smem);
   const uint32_t bar0 = sbase + kOffBar;
   auto bar = [&](int i) { return bar0 + 8u * (uint32_t)i; };
@@ -69,11 +121,14 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     prefetch_tensormap(&tmQ);
     prefetch_tensormap(&tmK);
     prefetch_tensormap(&tmV);
-    mbar_init(bar(B_QFULL), 1);
-    mbar_init(bar(B_SFULL), 1);
-    mbar_init(bar(B_PFULL), 128);
-    mbar_init(bar(B_OFULL), 1);
-    for (int i = 0; i < kRing; ++i) {
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(bar(B_QFULL + s), 1);
+      mbar_init(bar(B_SFULL + s), 1);
+      mbar_init(bar(B_PHALF + 2 * s), 128);
+      mbar_init(bar(B_PHALF + 2 * s + 1), 128);
+      mbar_init(bar(B_OFULL + s), 1);
+    }
+    for (int i = 0; i < kStages; ++i) {
       mbar_init(bar(B_KVFULL + i), 1);
       mbar_init(bar(B_KVEMPTY + i), 1);
     }
@@ -89,196 +144,296 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const uint32_t tmem = *tmem_slot;
 
   if (warp < 4) {
-    setmaxnreg_dec<40>();
-    if (warp == 0 && cnt > 0) {
+    setmaxnreg_dec<56>();
+    if (warp == 0 && rounds > 0) {
       // ------------------------------------------------------------------------------------ TMA producer
+      // Same deterministic order as the MMA warp: round r, slot s: V_s(r-1) then K_s(r); one ring stage = one
+      // whole 128 x 128 tile (two granules, one barrier).
       if (lane == 0) {
-        mbar_arrive_expect_tx(bar(B_QFULL), 2 * kGranule);
-        tma_load_4d(sbase + kOffQ, &tmQ, bar(B_QFULL), 0, tile * 128, h, b);
-        tma_load_4d(sbase + kOffQ + kGranule, &tmQ, bar(B_QFULL), 64, tile * 128, h, b);
+        if (cnt0 > 0) {
+          mbar_arrive_expect_tx(bar(B_QFULL), 2 * kGranule);
+          tma_load_4d(sbase + kOffQ, &tmQ, bar(B_QFULL), 0, tile0 * 128, h, b);
+          tma_load_4d(sbase + kOffQ + kGranule, &tmQ, bar(B_QFULL), 64, tile0 * 128, h, b);
+        }
+        if (cnt1 > 0) {
+          mbar_arrive_expect_tx(bar(B_QFULL + 1), 2 * kGranule);
+          tma_load_4d(sbase + kOffQ + 2 * kGranule, &tmQ, bar(B_QFULL + 1), 0, tile1 * 128, h, b);
+          tma_load_4d(sbase + kOffQ + 3 * kGranule, &tmQ, bar(B_QFULL + 1), 64, tile1 * 128, h, b);
+        }
       }
-      int n = 0;  // granule counter: ring slot n % kRing, use n / kRing
-      for (int i0 = 0; i0 < cnt; i0 += 32) {
-        const int mine = (i0 + lane < cnt) ? (int)list[i0 + lane] : 0;
-        const int nn = min(32, cnt - i0);
-        for (int j = 0; j < nn; ++j) {
-          const int kv0 = __shfl_sync(0xffffffffu, mine, j) * 128;
-          if (lane == 0) {
+      int n = 0;  // stage counter: ring stage n % kStages, use n / kStages
+      int mine0 = 0, mine1 = 0, prev0 = 0, prev1 = 0;
+      for (int r = 0; r <= rounds; ++r) {
+        if ((r & 31) == 0) {
+          mine0 = (r + lane < cnt0) ? (int)list0[r + lane] : 0;
+          mine1 = (r + lane < cnt1) ? (int)list1[r + lane] : 0;
+        }
+        const int cur0 = __shfl_sync(0xffffffffu, mine0, r & 31);
+        const int cur1 = __shfl_sync(0xffffffffu, mine1, r & 31);
+        if (lane == 0) {
 #pragma unroll
-            for (int t = 0; t < 4; ++t, ++n) {  // K half 0, K half 1, V half 0, V half 1
-              const int slot = n % kRing;
-              mbar_wait(bar(B_KVEMPTY + slot), ((n / kRing) & 1) ^ 1);
-              mbar_arrive_expect_tx(bar(B_KVFULL + slot), kGranule);
-              tma_load_4d(sbase + kOffRing + slot * kGranule, t < 2 ? (const void*)&tmK : (const void*)&tmV,
-                          bar(B_KVFULL + slot), (t & 1) * 64, kv0, h, b);
+          for (int s = 0; s < 2; ++s) {
+            const int cnt = s ? cnt1 : cnt0;
+#pragma unroll
+            for (int t = 0; t < 2; ++t) {  // t = 0: V tile of block r-1; t = 1: K tile of block r
+              if (t == 0 ? (r >= 1 && r <= cnt) : (r < cnt)) {
+                const int row = (t == 0 ? (s ? prev1 : prev0) : (s ? cur1 : cur0)) * 128;
+                const void* map = t == 0 ? (const void*)&tmV : (const void*)&tmK;
+                const int st = n % kStages;
+                const uint32_t dst = sbase + kOffRing + st * 2 * kGranule;
+                mbar_wait(bar(B_KVEMPTY + st), ((n / kStages) & 1) ^ 1);
+                if (kDebug && (a.dbg_flags & 2) && n >= kStages) {  // ablation: no K/V traffic after the first fill
+                  mbar_arrive(bar(B_KVFULL + st));
+                } else {
+                  mbar_arrive_expect_tx(bar(B_KVFULL + st), 2 * kGranule);
+                  tma_load_4d(dst, map, bar(B_KVFULL + st), 0, row, h, b);
+                  tma_load_4d(dst + kGranule, map, bar(B_KVFULL + st), 64, row, h, b);
+                }
+                ++n;
+              }
             }
+          }
+        }
+        prev0 = cur0;
+        prev1 = cur1;
+        __syncwarp();
+      }
+    } else if (warp == 1 && rounds > 0) {
+      // -------------------------------------------------------------------------------------- MMA issuer
+      // The whole warp walks the schedule (so every descriptor is warp-uniform); one elected lane issues.
+      const bool leader = elect_one();
+      int n = 0;
+      for (int r = 0; r <= rounds; ++r) {
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int cnt = s ? cnt1 : cnt0;
+          const uint32_t tS = tmem + 128 * s, tO = tmem + 256 + 128 * s;
+          const bool do_pv = r >= 1 && r <= cnt, do_qk = r < cnt;
+          if (do_pv) {
+            // O += P V for block r-1; key halves (P columns) in the order the softmax warpgroup releases them.
+            // V's head_dim halves are the two granules of the stage: one N = 128 MN-major descriptor, LBO 16 KB.
+            const int st = n % kStages;
+            const uint64_t vd = smem_desc_sw128(sbase + kOffRing + st * 2 * kGranule, kGranule);
+            mbar_wait(bar(B_KVFULL + st), (n / kStages) & 1);
+            mbar_wait(bar(B_PHALF + 2 * s), (r - 1) & 1);
+            tc_fence_after();
+            RSA_TRACE(dbg && s == 0 && leader, r - 1, 9);
+            if (leader) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)  // 16 keys = 16 rows of 128 B; P: 16 bf16 = 8 TMEM columns
+                umma_ts(tO, tS + ks * 8, vd + 128 * ks, kIdescPV, (r > 1 || ks > 0) ? 1u : 0u);
+            }
+            mbar_wait(bar(B_PHALF + 2 * s + 1), (r - 1) & 1);
+            tc_fence_after();
+            if (leader) {
+#pragma unroll
+              for (int ks = 4; ks < 8; ++ks) umma_ts(tO, tS + ks * 8, vd + 128 * ks, kIdescPV, 1u);
+              umma_commit(bar(B_KVEMPTY + st));
+              if (r == cnt) umma_commit(bar(B_OFULL + s));
+            }
+            ++n;
+            RSA_TRACE(dbg && s == 0 && leader, r - 1, 11);
+          }
+          if (do_qk) {
+            // S = Q K^T for block r: head_dim halves 0 / 1 = granules 0 / 1 of the stage (and of Q)
+            const int st = n % kStages;
+            const uint64_t kd = smem_desc_sw128(sbase + kOffRing + st * 2 * kGranule);
+            const uint64_t qd = smem_desc_sw128(sbase + kOffQ + 2 * s * kGranule);
+            if (r == 0) mbar_wait(bar(B_QFULL + s), 0);
+            mbar_wait(bar(B_KVFULL + st), (n / kStages) & 1);
+            tc_fence_after();
+            RSA_TRACE(dbg && s == 0 && leader, r, 12);
+            if (leader) {
+#pragma unroll
+              for (int ks = 0; ks < 8; ++ks) {  // 16 head_dim elements = 32 bytes inside the swizzle atom
+                const uint32_t off = (ks >> 2) * (kGranule >> 4) + 2 * (ks & 3);
+                umma_ss(tS, qd + off, kd + off, kIdescQK, ks != 0);
+              }
+              umma_commit(bar(B_KVEMPTY + st));
+              umma_commit(bar(B_SFULL + s));
+            }
+            ++n;
+            RSA_TRACE(dbg && s == 0 && leader, r, 8);
           }
           __syncwarp();
         }
       }
-    } else if (warp == 1 && lane == 0 && cnt > 0) {
-      // -------------------------------------------------------------------------------------- MMA issuer
-      const uint64_t qd0 = smem_desc_sw128(sbase + kOffQ), qd1 = smem_desc_sw128(sbase + kOffQ + kGranule);
-      const uint32_t tS = tmem, tO = tmem + 128;
-      mbar_wait(bar(B_QFULL), 0);
-      int n = 0;
-      for (int i = 0; i < cnt; ++i) {
-        // S = Q K^T : head_dim halves 0 and 1 live in consecutive granules
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf, ++n) {
-          const int slot = n % kRing;
-          mbar_wait(bar(B_KVFULL + slot), (n / kRing) & 1);
-          tc_fence_after();
-          const uint64_t kd = smem_desc_sw128(sbase + kOffRing + slot * kGranule);
-          const uint64_t qd = hf ? qd1 : qd0;
-#pragma unroll
-          for (int ks = 0; ks < 4; ++ks)  // 16 head_dim elements = 32 bytes inside the swizzle atom
-            umma_ss(tS, qd + 2 * ks, kd + 2 * ks, kIdescQK, (hf | ks) != 0);
-          umma_commit(bar(B_KVEMPTY + slot));
-        }
-        umma_commit(bar(B_SFULL));
-        // O += P V : output columns [0,64) from V half 0, [64,128) from V half 1
-        mbar_wait(bar(B_PFULL), i & 1);
-        tc_fence_after();
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf, ++n) {
-          const int slot = n % kRing;
-          mbar_wait(bar(B_KVFULL + slot), (n / kRing) & 1);
-          tc_fence_after();
-          const uint64_t vd = smem_desc_sw128(sbase + kOffRing + slot * kGranule);
-#pragma unroll
-          for (int ks = 0; ks < 8; ++ks)  // 16 keys = 16 rows of 128 bytes; P: 16 bf16 = 8 TMEM columns
-            umma_ts(tO + hf * 64, tS + ks * 8, vd + 128 * ks, kIdescPV, (i | ks) != 0);
-          umma_commit(bar(B_KVEMPTY + slot));
-        }
-      }
-      umma_commit(bar(B_OFULL));
     }
   } else {
-    // ------------------------------------------------------------------- softmax + epilogue warpgroup
-    setmaxnreg_inc<216>();
-    const int quarter = warp & 3;  // TMEM lanes [32*quarter, +32) belong to this warp
+    // ------------------------------------------------------------------- softmax + epilogue warpgroups
+    setmaxnreg_inc<224>();
+    const int s = (warp - 4) >> 2;  // slot
+    const int quarter = warp & 3;   // TMEM lanes [32*quarter, +32) belong to this warp
     const int row = quarter * 32 + lane;
-    const uint32_t tS = tmem + ((uint32_t)(quarter * 32) << 16);
-    const uint32_t tO = tS + 128;
+    const int tile = s ? tile1 : tile0;
+    const int cnt = s ? cnt1 : cnt0;
+    const uint16_t* __restrict__ list = s ? list1 : list0;
+    const int64_t lrow = lrow0 + s;
+    const uint32_t tS = tmem + 128 * s + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t tO = tS + 256;
     const float scale = a.scale_log2;
+    const float2 scale2 = make_float2(scale, scale);
     float m_ref = -INFINITY, l = 0.f;
     const int lim_last = cnt > 0 ? a.kv_len - (int)list[cnt - 1] * 128 : 128;  // valid keys in the last block
-    const bool dbg = a.dbg != nullptr && lrow == 0;
+    const bool tr = dbg && s == 0 && row == 0;
 
-    for (int i = 0; i < cnt; ++i) {
-      mbar_wait(bar(B_SFULL), i & 1);
-      tc_fence_after();
-      uint32_t s[128];
-      tmem_ld32(tS + 0, s + 0);
-      tmem_ld32(tS + 32, s + 32);
-      tmem_ld32(tS + 64, s + 64);
-      tmem_ld32(tS + 96, s + 96);
-      tmem_wait_ld();
-      if (dbg && i == 0) {
-#pragma unroll
-        for (int c = 0; c < 128; ++c) a.dbg[row * 128 + c] = u2f(s[c]);
-      }
-      if (i == cnt - 1 && lim_last < 128) {  // keys >= kv_len -> -inf (wan21 :75-87)
-#pragma unroll
-        for (int c = 0; c < 128; ++c)
-          if (c >= lim_last) s[c] = 0xff800000u;
-      }
-      float mx0 = u2f(s[0]), mx1 = u2f(s[1]), mx2 = u2f(s[2]), mx3 = u2f(s[3]);
-#pragma unroll
-      for (int c = 4; c < 128; c += 4) {
-        mx0 = fmaxf(mx0, u2f(s[c]));
-        mx1 = fmaxf(mx1, u2f(s[c + 1]));
-        mx2 = fmaxf(mx2, u2f(s[c + 2]));
-        mx3 = fmaxf(mx3, u2f(s[c + 3]));
-      }
-      const float mx_s = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale;
-      if (i == 0) {
-        m_ref = mx_s;
-      } else {
-        const bool need = mx_s > m_ref + kRescaleThreshold;
-        if (__any_sync(0xffffffffu, need)) {  // tcgen05.ld/st are warp-collective: rescale the warp's 32 rows
-          const float alpha = need ? ex2(m_ref - mx_s) : 1.f;
-          if (need) m_ref = mx_s;
-          l *= alpha;
-#pragma unroll
-          for (int c4 = 0; c4 < 4; ++c4) {
-            uint32_t o[32];
-            tmem_ld32(tO + c4 * 32, o);
-            tmem_wait_ld();
-#pragma unroll
-            for (int j = 0; j < 32; ++j) o[j] = f2u(u2f(o[j]) * alpha);
-            tmem_st32(tO + c4 * 32, o);
-          }
+    if (tile < a.nqt) {
+      for (int i = 0; i < cnt; ++i) {
+        RSA_TRACE(tr, i, 0);
+        mbar_wait(bar(B_SFULL + s), i & 1);
+        tc_fence_after();
+        RSA_TRACE(tr, i, 1);
+        if (kDebug && (a.dbg_flags & 1)) {  // ablation: no softmax work, hand P (garbage) straight back
+          tc_fence_before();
+          mbar_arrive(bar(B_PHALF + 2 * s));
+          mbar_arrive(bar(B_PHALF + 2 * s + 1));
+          continue;
         }
-      }
-      const float neg_m = -m_ref;
-      float l0 = 0.f, l1 = 0.f, l2 = 0.f, l3 = 0.f;
-#pragma unroll
-      for (int c16 = 0; c16 < 4; ++c16) {  // 32 S columns -> 16 packed P columns
-        uint32_t pk[16];
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          const int c = c16 * 32 + j;
-          const float p0 = ex2(fmaf(u2f(s[c]), scale, neg_m));
-          const float p1 = ex2(fmaf(u2f(s[c + 1]), scale, neg_m));
-          const float p2 = ex2(fmaf(u2f(s[c + 2]), scale, neg_m));
-          const float p3 = ex2(fmaf(u2f(s[c + 3]), scale, neg_m));
-          l0 += p0;
-          l1 += p1;
-          l2 += p2;
-          l3 += p3;
-          pk[j / 2] = pack_bf16x2(p0, p1);
-          pk[j / 2 + 1] = pack_bf16x2(p2, p3);
-        }
-        tmem_st16(tS + c16 * 16, pk);
-      }
-      l += (l0 + l1) + (l2 + l3);
-      tmem_wait_st();
-      tc_fence_before();
-      mbar_arrive(bar(B_PFULL));
-    }
-
-    // ------------------------------------------------------------------------------------------ epilogue
-    const float R = a.R ? a.R[lrow] : 1.f;
-    const float inv = l > 0.f ? R / l : 0.f;
-    const float* __restrict__ crow = a.C ? a.C + lrow * 128 : nullptr;
-    const int grow = tile * 128 + row;
-    const bool store = grow < a.seq_q, zero = grow >= a.q_valid;
-    __nv_bfloat16* orow = a.o + b * a.os[0] + h * a.os[1] + (int64_t)grow * a.os[2];
-    if (cnt > 0) {
-      mbar_wait(bar(B_OFULL), 0);
-      tc_fence_after();
-    }
-#pragma unroll
-    for (int c4 = 0; c4 < 4; ++c4) {
-      uint32_t o[32];
-      if (cnt > 0) {
-        tmem_ld32(tO + c4 * 32, o);
+        uint32_t sr[128];
+        tmem_ld32(tS + 0, sr + 0);
+        tmem_ld32(tS + 32, sr + 32);
         tmem_wait_ld();
-      } else {
+        tmem_ld32(tS + 64, sr + 64);  // in flight while the first half is reduced
+        tmem_ld32(tS + 96, sr + 96);
+        const bool partial = i == cnt - 1 && lim_last < 128;  // keys >= kv_len -> -inf (wan21 :75-87)
+        if (partial) {
 #pragma unroll
-        for (int j = 0; j < 32; ++j) o[j] = 0u;
-      }
-      if (dbg) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) a.dbg[16384 + row * 128 + c4 * 32 + j] = u2f(o[j]);
-        if (c4 == 0) {
-          a.dbg[32768 + row] = l;
-          a.dbg[32768 + 128 + row] = m_ref;
+          for (int c = 0; c < 64; ++c)
+            if (c >= lim_last) sr[c] = 0xff800000u;
         }
-      }
-      if (store) {
+        float mx0 = u2f(sr[0]), mx1 = u2f(sr[1]), mx2 = u2f(sr[2]), mx3 = u2f(sr[3]);
 #pragma unroll
-        for (int j = 0; j < 32; j += 8) {
-          uint32_t w[4];
+        for (int c = 4; c < 64; c += 4) {
+          mx0 = fmaxf(mx0, u2f(sr[c]));
+          mx1 = fmaxf(mx1, u2f(sr[c + 1]));
+          mx2 = fmaxf(mx2, u2f(sr[c + 2]));
+          mx3 = fmaxf(mx3, u2f(sr[c + 3]));
+        }
+        tmem_wait_ld();
+        RSA_TRACE(tr, i, 2);
+        if (kDebug && dbg && s == 0 && i == 0) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const int c = c4 * 32 + j + 2 * e;
-            const float c0 = crow ? crow[c] : 0.f, c1 = crow ? crow[c + 1] : 0.f;
-            w[e] = zero ? 0u : pack_bf16x2(fmaf(u2f(o[j + 2 * e]), inv, c0), fmaf(u2f(o[j + 2 * e + 1]), inv, c1));
+          for (int c = 0; c < 128; ++c) a.dbg[row * 128 + c] = u2f(sr[c]);
+        }
+        if (partial) {
+#pragma unroll
+          for (int c = 64; c < 128; ++c)
+            if (c >= lim_last) sr[c] = 0xff800000u;
+        }
+#pragma unroll
+        for (int c = 64; c < 128; c += 4) {
+          mx0 = fmaxf(mx0, u2f(sr[c]));
+          mx1 = fmaxf(mx1, u2f(sr[c + 1]));
+          mx2 = fmaxf(mx2, u2f(sr[c + 2]));
+          mx3 = fmaxf(mx3, u2f(sr[c + 3]));
+        }
+        const float mx_s = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3)) * scale;
+        if (i == 0) {
+          m_ref = mx_s;
+        } else {
+          const bool need = mx_s > m_ref + kRescaleThreshold;
+          if (__any_sync(0xffffffffu, need)) {  // tcgen05.ld/st are warp-collective: rescale the warp's 32 rows
+            const float alpha = need ? ex2(m_ref - mx_s) : 1.f;
+            const float2 alpha2 = make_float2(alpha, alpha);
+            if (need) m_ref = mx_s;
+            l *= alpha;
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              uint32_t o[32];
+              tmem_ld32(tO + c4 * 32, o);
+              tmem_wait_ld();
+#pragma unroll
+              for (int j = 0; j < 32; j += 2) {
+                const float2 v = __fmul2_rn(make_float2(u2f(o[j]), u2f(o[j + 1])), alpha2);
+                o[j] = f2u(v.x);
+                o[j + 1] = f2u(v.y);
+              }
+              tmem_st32(tO + c4 * 32, o);
+            }
           }
-          *reinterpret_cast<uint4*>(orow + c4 * 32 + j) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        RSA_TRACE(tr, i, 3);
+        const float2 negm2 = make_float2(-m_ref, -m_ref);
+        float2 la = make_float2(0.f, 0.f), lb = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int c16 = 0; c16 < 4; ++c16) {  // 32 S columns -> 16 packed P columns
+          uint32_t pk[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            float2 x[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c16 * 32 + j + 2 * e;
+              x[e] = __ffma2_rn(make_float2(u2f(sr[c]), u2f(sr[c + 1])), scale2, negm2);
+            }
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              if (e >= 4 - kPolyPairs) {
+                x[e] = exp2_poly2(x[e]);
+              } else {
+                x[e].x = ex2(x[e].x);
+                x[e].y = ex2(x[e].y);
+              }
+            }
+            la = __fadd2_rn(la, __fadd2_rn(x[0], x[1]));
+            lb = __fadd2_rn(lb, __fadd2_rn(x[2], x[3]));
+#pragma unroll
+            for (int e = 0; e < 4; ++e) pk[j / 2 + e] = pack_bf16x2(x[e].x, x[e].y);
+          }
+          tmem_st16(tS + c16 * 16, pk);
+          if (c16 & 1) {  // 64 keys done: hand this half of P to the MMA thread
+            tmem_wait_st();
+            tc_fence_before();
+            mbar_arrive(bar(B_PHALF + 2 * s + (c16 >> 1)));
+            if (c16 == 1) RSA_TRACE(tr, i, 4);
+          }
+        }
+        la = __fadd2_rn(la, lb);
+        l += la.x + la.y;
+        RSA_TRACE(tr, i, 5);
+      }
+
+      // ---------------------------------------------------------------------------------------- epilogue
+      const float R = a.R ? a.R[lrow] : 1.f;
+      const float inv = l > 0.f ? R / l : 0.f;
+      const float* __restrict__ crow = a.C ? a.C + lrow * 128 : nullptr;
+      const int grow = tile * 128 + row;
+      const bool store = grow < a.seq_q, zero = grow >= a.q_valid;
+      __nv_bfloat16* orow = a.o + b * a.os[0] + h * a.os[1] + (int64_t)grow * a.os[2];
+      if (cnt > 0) {
+        mbar_wait(bar(B_OFULL + s), 0);
+        tc_fence_after();
+      }
+#pragma unroll
+      for (int c4 = 0; c4 < 4; ++c4) {
+        uint32_t o[32];
+        if (cnt > 0) {
+          tmem_ld32(tO + c4 * 32, o);
+          tmem_wait_ld();
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) o[j] = 0u;
+        }
+        if (kDebug && dbg && s == 0) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) a.dbg[16384 + row * 128 + c4 * 32 + j] = u2f(o[j]);
+          if (c4 == 0) {
+            a.dbg[32768 + row] = l;
+            a.dbg[32768 + 128 + row] = m_ref;
+          }
+        }
+        if (store) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 8) {
+            uint32_t w[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const int c = c4 * 32 + j + 2 * e;
+              const float c0 = crow ? crow[c] : 0.f, c1 = crow ? crow[c + 1] : 0.f;
+              w[e] = zero ? 0u : pack_bf16x2(fmaf(u2f(o[j + 2 * e]), inv, c0), fmaf(u2f(o[j + 2 * e + 1]), inv, c1));
+            }
+            *reinterpret_cast<uint4*>(orow + c4 * 32 + j) = make_uint4(w[0], w[1], w[2], w[3]);
+          }
         }
       }
     }
@@ -334,26 +489,47 @@ int make_map(CUtensorMap* m, const __nv_bfloat16* base, int batch, int heads, in
   return RSA_OK;
 }
 
+template <bool kDebug, int kPolyPairs>
+int launch(dim3 grid, cudaStream_t s, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
+           const AttnArgs& a) {
+  static bool configured = false;  // one flag per instantiation
+  if (!configured) {
+    RSA_CUDA_CHECK(cudaFuncSetAttribute(attn_tc5_kernel<kDebug, kPolyPairs>,
+                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    configured = true;
+  }
+  attn_tc5_kernel<kDebug, kPolyPairs><<<grid, kThreads, kSmemBytes, s>>>(tq, tk, tv, a);
+  RSA_CUDA_CHECK(cudaGetLastError());
+  return RSA_OK;
+}
+
+int poly_pairs() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RSA_TC5_POLY");
+    v = (e && e[0] >= '0' && e[0] <= '4' && !e[1]) ? e[0] - '0' : kDefaultPolyPairs;
+  }
+  return v;
+}
+
 }  // namespace
 
 int launch_attention_tc5(const AttnArgs& a, cudaStream_t s) {
-  static bool configured = false;
-  if (!configured) {
-    RSA_CUDA_CHECK(cudaFuncSetAttribute(attn_tc5_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    RSA_CUDA_CHECK(cudaFuncSetAttribute(attn_tc5_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                        cudaSharedmemCarveoutMaxShared));
-    configured = true;
-  }
   if (a.nqt == 0) return RSA_OK;
   CUtensorMap tq, tk, tv;
   int rc;
   if ((rc = make_map(&tq, a.q, a.batch, a.heads, a.seq_q, a.qs)) != RSA_OK) return rc;
   if ((rc = make_map(&tk, a.k, a.batch, a.heads, a.seq_kv, a.ks)) != RSA_OK) return rc;
   if ((rc = make_map(&tv, a.v, a.batch, a.heads, a.seq_kv, a.vs)) != RSA_OK) return rc;
-  dim3 grid(a.nqt, a.batch * a.heads);
-  attn_tc5_kernel<<<grid, kThreads, kSmemBytes, s>>>(tq, tk, tv, a);
-  RSA_CUDA_CHECK(cudaGetLastError());
-  return RSA_OK;
+  const dim3 grid((a.nqt + 1) / 2, a.batch * a.heads);
+  if (a.dbg) return launch<true, kDefaultPolyPairs>(grid, s, tq, tk, tv, a);
+  switch (poly_pairs()) {
+    case 1: return launch<false, 1>(grid, s, tq, tk, tv, a);
+    case 3: return launch<false, 3>(grid, s, tq, tk, tv, a);
+    case 4: return launch<false, 4>(grid, s, tq, tk, tv, a);
+    case 2: return launch<false, 2>(grid, s, tq, tk, tv, a);
+    default: return launch<false, 0>(grid, s, tq, tk, tv, a);
+  }
 }
 
 }  // namespace rsa

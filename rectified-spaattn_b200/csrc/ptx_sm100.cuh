@@ -30,13 +30,26 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       "{\n"
       ".reg .pred P1;\n"
       "LAB_WAIT:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
       "@P1 bra DONE;\n"
       "bra LAB_WAIT;\n"
       "DONE:\n"
       "}\n" ::"r"(bar),
-      "r"(parity)
+      "r"(parity), "r"(0x989680u)  // suspend-time hint: let the hardware park the thread instead of spinning
       : "memory");
+}
+
+// True in exactly one lane of a converged warp; lets ptxas keep the surrounding values in uniform registers.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ----------------------------------------------------------------------------------------------------- TMA
@@ -103,10 +116,13 @@ __device__ __forceinline__ void umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64
 //   * a K-major operand   [rows = M or N, 64 k-elements per row]   (Q and K tiles of S = Q K^T), and
 //   * an MN-major operand [rows = k, 64 n-elements per row]        (the V tile of O = P V);
 // which of the two it is lives in the instruction descriptor.  Fields (cute::UMMA::SmemDescriptor):
-//   [0,14) start >> 4, [16,30) leading byte offset >> 4 (unused here: one swizzle atom wide), [32,46) stride byte
+//   [0,14) start >> 4, [16,30) leading byte offset >> 4, [32,46) stride byte
 //   offset >> 4 = 1024 >> 4, [46,48) version = 1, [61,64) layout = 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
+// lbo_bytes: distance between consecutive 64-element swizzle atoms along the MN dimension of an MN-major operand
+// wider than one atom (N = 128 over two granules); ignored by the hardware for the K-major tiles used here.
+__device__ __forceinline__ uint64_t smem_desc_sw128(uint32_t saddr, uint32_t lbo_bytes = 16) {
+  return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(lbo_bytes >> 4) << 16) | (64ull << 32) | (1ull << 46) |
+         (2ull << 61);
 }
 
 // Instruction descriptor, kind::f16 (cute::UMMA::InstrDescriptor): c_format F32 (bit 4), a/b format BF16

@@ -11,6 +11,7 @@ namespace rsa {
 static thread_local char g_err[512] = "";
 int g_attention_impl = 0;
 float* g_attention_dbg = nullptr;
+int g_attention_dbg_flags = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -131,6 +132,7 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->C = (const float*)(ws + L.off_C);
   a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.4426950408889634);
   a->dbg = g_attention_dbg;
+  a->dbg_flags = g_attention_dbg_flags;
   return RSA_OK;
 }
 
@@ -188,6 +190,7 @@ extern "C" int rsa_set_attention_impl(int impl) {
 }
 
 extern "C" void rsa_debug_set_attention_dump(float* device_buffer) { g_attention_dbg = device_buffer; }
+extern "C" void rsa_debug_set_attention_flags(int flags) { g_attention_dbg_flags = flags; }
 
 extern "C" size_t rsa_attn_workspace_bytes(const rsa_attn_desc* d) {
   if (validate_desc(d) != RSA_OK) return 0;
@@ -334,5 +337,6 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   a.C = nullptr;
   a.scale_log2 = (float)((1.0 / sqrt(128.0)) * 1.4426950408889634);
   a.dbg = g_attention_dbg;
+  a.dbg_flags = g_attention_dbg_flags;
   return launch_attention(a, s);
 }

@@ -61,6 +61,7 @@ struct AttnArgs {
   const float* R;           // [bh, nqt]  or nullptr (=1)
   const float* C;           // [bh, nqt, 128] or nullptr (=0)
   float scale_log2;         // head_dim^-0.5 * log2(e)
+  int dbg_flags;            // bring-up ablations (rsa_debug_set_attention_flags), only read by the debug kernel
   float* dbg;               // bring-up dump of tile 0 / bh 0 (rsa_debug_set_attention_dump), normally null
 };
 
@@ -71,5 +72,6 @@ int launch_mask_to_lists(const uint8_t* mask, int bh, int nq, int nkv, int kv_bl
 
 extern int g_attention_impl;
 extern float* g_attention_dbg;
+extern int g_attention_dbg_flags;
 
 }  // namespace rsa

@@ -44,7 +44,7 @@ EXPORTS = [
     "rsa_permute_rows", "rsa_attn_workspace_bytes", "rsa_attn_workspace_view", "rsa_pool_stats",
     "rsa_block_scores", "rsa_block_select", "rsa_rect_c", "rsa_sparse_attention", "rsa_rectified_attention",
     "rsa_masked_attention_workspace_bytes", "rsa_masked_attention", "rsa_set_attention_impl",
-    "rsa_debug_set_attention_dump",
+    "rsa_debug_set_attention_dump", "rsa_debug_set_attention_flags",
 ]
 
 _lib = None
@@ -81,6 +81,8 @@ def lib():
     L.rsa_set_attention_impl.argtypes = [i32]
     L.rsa_debug_set_attention_dump.argtypes = [p]
     L.rsa_debug_set_attention_dump.restype = None
+    L.rsa_debug_set_attention_flags.argtypes = [i32]
+    L.rsa_debug_set_attention_flags.restype = None
     for n in EXPORTS:
         f = getattr(L, n)
         if f.restype is C.c_int and n not in ("rsa_version", "rsa_device_ok", "rsa_set_attention_impl"):

@@ -38,7 +38,7 @@ def one_block():
     g = torch.Generator().manual_seed(0)
     q, k, v = (torch.randn(1, 1, 128, 128, generator=g).to(torch.bfloat16).to(dev) for _ in range(3))
     mask = torch.ones(1, 1, 1, 1, dtype=torch.bool, device=dev)
-    dbg = torch.zeros(33024, dtype=torch.float32, device=dev)
+    dbg = torch.zeros(34048, dtype=torch.float32, device=dev)
     L.rsa_debug_set_attention_dump(C.c_void_p(dbg.data_ptr()))
     o = run(q, k, v, mask, 128, 0)
     L.rsa_debug_set_attention_dump(None)
@@ -120,3 +120,47 @@ if __name__ == "__main__":
     if "perf" in what:
         perf(8, 16384, 0.25)
         perf(4, 65536, 0.22)
+
+
+def trace(h=8, s=16384, dens=0.25, flags=0):
+    """Clock trace of one CTA in the middle of a busy launch (slots: see attn_tc5.cu RSA_TRACE)."""
+    print(f"== trace h={h} S={s} density={dens}", flush=True)
+    g = torch.Generator(device=dev).manual_seed(1)
+    q, k, v = (torch.randn(1, h, s, 128, generator=g, device=dev).to(torch.bfloat16) for _ in range(3))
+    nb = (s + 127) // 128
+    mask = (torch.rand(1, h, nb, nb, generator=g, device=dev) < dens) | torch.eye(nb, dtype=torch.bool, device=dev)
+    dbg = torch.zeros(34048, dtype=torch.float32, device=dev)
+    run(q, k, v, mask, s, 0)
+    L.rsa_debug_set_attention_dump(C.c_void_p(dbg.data_ptr()))
+    L.rsa_debug_set_attention_flags(flags)
+    run(q, k, v, mask, s, 0)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(5):
+        ops.masked_attention(q, k, v, mask, s)
+    e1.record()
+    torch.cuda.synchronize()
+    L.rsa_debug_set_attention_flags(0)
+    L.rsa_debug_set_attention_dump(None)
+    print(f"  debug kernel, flags={flags}: {e0.elapsed_time(e1) / 5:.3f} ms per call "
+          f"({int(mask.sum()) * 8388608 / (e0.elapsed_time(e1) / 5) / 1e9:.0f} TFLOP/s-equivalent)")
+    t = dbg[33024:].view(64, 16).cpu().double()
+    names = ["sm:wait_s", "sm:got_s", "sm:ld_done", "sm:max_done", "sm:half0", "sm:done", "", "", "mma:qk_issued",
+             "mma:got_p0", "", "mma:pv_issued", "mma:k_in"]
+    print("  step " + " ".join(f"{n:>13}" for n in names if n))
+    for i in range(4, 16):
+        print(f"  {i:4d} " + " ".join(f"{int(t[i, j]):13d}" for j, n in enumerate(names) if n))
+    a, b = t[8:24], t[9:25]
+    f = lambda x: f"{x.mean():.0f}"
+    print(f"  period {f(b[:,1]-a[:,1])}; wait_s {f(a[:,1]-a[:,0])}; ld {f(a[:,2]-a[:,1])}; max {f(a[:,3]-a[:,2])}; "
+          f"exp half0 {f(a[:,4]-a[:,3])}; exp half1 {f(a[:,5]-a[:,4])}; half0->mma got_p0 {f(a[:,9]-a[:,4])}; "
+          f"got_p0->pv_issued {f(a[:,11]-a[:,9])}; pv_issued->qk_issued(next) {f(b[:,8]-a[:,11])}; "
+          f"qk_issued->got_s {f(b[:,1]-b[:,8])}")
+
+
+if __name__ == "__main__" and "trace" in sys.argv[1:]:
+    trace()
+if __name__ == "__main__" and "ablate" in sys.argv[1:]:
+    trace(4, 65536, 0.22, flags=0)
+    trace(4, 65536, 0.22, flags=1)
+    trace(4, 65536, 0.22, flags=3)

@@ -1,0 +1,167 @@
+"""Shared pieces of the eight `Rectified*SpaAttnProcessor2_0` classes (not part of the reference's surface).
+
+The processors follow the diffusers `AttnProcessor` protocol exactly like the reference's (same constructor arguments,
+attributes, `__call__` signature, return values, warm-up gates and step counters -- SURVEY.md 3.4); what surrounds the
+hot path (QKV / output projections of the caller's `attn` module, QK norms, RoPE) stays plain PyTorch on the caller's
+modules, and the attention itself goes through the per-family `rectified_block_sparse_attention` /
+`fullattn(mode="flash")`, i.e. the sm_100a kernels.  diffusers is not imported: the three RoPE conventions the
+reference takes from it (or defines inline) are restated here.
+"""
+from typing import Optional
+
+import torch
+import torch.nn.functional as F
+
+
+def heads_first(x, heads):
+    """[B, S, H*D] -> [B, H, S, D] (reference: `unflatten(2, (heads, -1)).transpose(1, 2)`)."""
+    return x.unflatten(2, (heads, -1)).transpose(1, 2)
+
+
+def rope_real(x, freqs):
+    """diffusers.models.embeddings.apply_rotary_emb with use_real=True, use_real_unbind_dim=-1 (what
+    rectified_hunyuan_attn.py:460-478, rectified_flux_attn.py:483-486 and rectified_cogvideo_attn.py:460-469 call):
+    x [B, H, S, D], freqs = (cos, sin) each [S, D]; pairs are (x[2i], x[2i+1])."""
+    cos, sin = freqs
+    cos, sin = cos[None, None].to(x.device), sin[None, None].to(x.device)
+    xr, xi = x.reshape(*x.shape[:-1], -1, 2).unbind(-1)
+    rot = torch.stack([-xi, xr], dim=-1).flatten(3)
+    return (x.float() * cos + rot.float() * sin).to(x.dtype)
+
+
+def rope_complex(x, freqs):
+    """The inline helper of rectified_wan21_attn.py:433-438: complex multiply in float64, x [B, H, S, D]."""
+    dtype = torch.float32 if x.device.type == "mps" else torch.float64
+    xc = torch.view_as_complex(x.to(dtype).unflatten(3, (-1, 2)))
+    return torch.view_as_real(xc * freqs).flatten(3, 4).type_as(x)
+
+
+def rope_cos_sin(x, freqs_cos, freqs_sin):
+    """The inline helper of rectified_wan22_attn.py:52-64 (x [B, S, H, D], interleaved cos/sin tables)."""
+    x1, x2 = x.unflatten(-1, (-1, 2)).unbind(-1)
+    cos, sin = freqs_cos[..., 0::2], freqs_sin[..., 1::2]
+    out = torch.empty_like(x)
+    out[..., 0::2] = x1 * cos - x2 * sin
+    out[..., 1::2] = x1 * sin + x2 * cos
+    return out.type_as(x)
+
+
+def kv_valid(attention_mask, s_k):
+    """`attention_mask.sum().item() if attention_mask else S_k` of the reference (one host sync when a mask is given)."""
+    if attention_mask is None:
+        return int(s_k)
+    return int(attention_mask.sum().item())
+
+
+def image_cross_attention(attn, query, encoder_hidden_states_img):
+    """Wan I2V: dense attention of all queries over the 257 CLIP image tokens (rectified_wan21_attn.py:445-458).
+    Dense, tiny KV: not part of the sparse path, left to PyTorch SDPA.  query is [B, H, S, D]."""
+    key_img = attn.norm_added_k(attn.add_k_proj(encoder_hidden_states_img))
+    value_img = attn.add_v_proj(encoder_hidden_states_img)
+    key_img, value_img = heads_first(key_img, attn.heads), heads_first(value_img, attn.heads)
+    out = F.scaled_dot_product_attention(query, key_img, value_img, attn_mask=None, dropout_p=0.0, is_causal=False)
+    return out.transpose(1, 2).flatten(2, 3).type_as(query)
+
+
+def split_wan_context(attn, encoder_hidden_states):
+    """(image part, text part) of the Wan cross-attention context; 512 = text encoder context length, hard-coded
+    in the reference (rectified_wan21_attn.py:411-416)."""
+    if getattr(attn, "add_k_proj", None) is None or encoder_hidden_states is None:
+        return None, encoder_hidden_states
+    n_img = encoder_hidden_states.shape[1] - 512
+    return encoder_hidden_states[:, :n_img], encoder_hidden_states[:, n_img:]
+
+
+def dense(fullattn, query, key, value, mode, attention_mask, s_k):
+    """The reference's dense branch: fullattn(...) then `.transpose(1, 2).reshape(B, S_q, -1)`."""
+    b, _, s_q, _ = query.shape
+    cu_q = [0, s_q, s_q]
+    cu_kv = [0, s_k, key.shape[2]]
+    out = fullattn(query, key, value, mode=mode, drop_rate=0.0, attn_mask=attention_mask, causal=False,
+                   cu_seqlens_q=cu_q, cu_seqlens_kv=cu_kv, max_seqlen_q=s_q, max_seqlen_kv=key.shape[2],
+                   batch_size=b)
+    return out.transpose(1, 2).reshape(b, s_q, -1)
+
+
+class ProcessorBase:
+    """Constructor arguments and mutable per-layer state shared by every reference processor
+    (e.g. rectified_wan21_attn.py:390-401)."""
+
+    steps_per_cycle = 50  # `current_step` wraps to 0 after this many calls
+
+    def __init__(self, mode, select_block_num, block_neighbor_list, p_remain_rates, processor_id=0):
+        self.mode = mode
+        self.select_block_num = select_block_num
+        self.block_neighbor_list = block_neighbor_list
+        self.p_remain_rates = p_remain_rates
+        self.current_step = 0
+        self.processor_id = processor_id
+        if not hasattr(F, "scaled_dot_product_attention"):
+            raise ImportError(f"{type(self).__name__} requires PyTorch 2.0. To use it, please upgrade PyTorch to 2.0.")
+
+    def _tick(self):
+        self.current_step += 1
+        if self.current_step == self.steps_per_cycle:
+            self.current_step = 0
+
+
+class WanProcessorBase(ProcessorBase):
+    """Wan2.1 T2V / I2V and Wan2.2 TI2V / T2V / I2V self-attention processors; they differ only in the warm-up gate,
+    the RoPE convention and the step wrap."""
+
+    steps_per_cycle = 100
+    rope = "complex"  # "complex" (Wan2.1) | "cos_sin" (Wan2.2)
+
+    def __init__(self, mode, select_block_num, block_neighbor_list, p_remain_rates, processor_id=0,
+                 first_frame_blocks=0):
+        super().__init__(mode, select_block_num, block_neighbor_list, p_remain_rates, processor_id)
+        self.first_frame_blocks = first_frame_blocks
+
+    def sparse_now(self) -> bool:
+        raise NotImplementedError
+
+    def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
+                 attention_mask: Optional[torch.Tensor] = None, rotary_emb=None) -> torch.Tensor:
+        from .attn import fullattn
+        from .rectified_wan21_attn import rectified_block_sparse_attention
+
+        enc_img, encoder_hidden_states = split_wan_context(attn, encoder_hidden_states)
+        if encoder_hidden_states is None:
+            encoder_hidden_states = hidden_states
+        query = attn.to_q(hidden_states)
+        key = attn.to_k(encoder_hidden_states)
+        value = attn.to_v(encoder_hidden_states)
+        if getattr(attn, "norm_q", None) is not None:
+            query = attn.norm_q(query)
+        if getattr(attn, "norm_k", None) is not None:
+            key = attn.norm_k(key)
+        if self.rope == "cos_sin":
+            query, key, value = (t.unflatten(2, (attn.heads, -1)) for t in (query, key, value))
+            if rotary_emb is not None:
+                query, key = rope_cos_sin(query, *rotary_emb), rope_cos_sin(key, *rotary_emb)
+            query, key, value = query.transpose(1, 2), key.transpose(1, 2), value.transpose(1, 2)
+        else:
+            query, key, value = (heads_first(t, attn.heads) for t in (query, key, value))
+            if rotary_emb is not None:
+                query, key = rope_complex(query, rotary_emb), rope_complex(key, rotary_emb)
+        hidden_img = image_cross_attention(attn, query, enc_img) if enc_img is not None else None
+
+        s_k = kv_valid(attention_mask, key.shape[2])
+        if self.mode == "sparse" and self.sparse_now():
+            hidden_states = rectified_block_sparse_attention(
+                query, key, value, attn_mask=attention_mask, top_k=self.select_block_num,
+                max_seqlen_q=query.shape[2], max_seqlen_kv=key.shape[2], block_neighbor_list=self.block_neighbor_list,
+                p_remain_rates=self.p_remain_rates, first_frame_blocks=self.first_frame_blocks)
+        elif self.mode == "sparse":
+            hidden_states = dense(fullattn, query, key, value, "flash", attention_mask, s_k)
+        elif self.mode in ("flash", "torch", "vanilla"):
+            hidden_states = dense(fullattn, query, key, value, self.mode, attention_mask, s_k)
+        else:
+            raise ImportError("Undefined Attention Processor! Just support sparse, flash, torch, vanilla.")
+        hidden_states = hidden_states.type_as(query)
+        self._tick()
+        if hidden_img is not None:
+            hidden_states = hidden_states + hidden_img
+        hidden_states = attn.to_out[0](hidden_states)
+        hidden_states = attn.to_out[1](hidden_states)
+        return hidden_states

@@ -13,7 +13,7 @@ import torch.nn.functional as F
 from rsa_b200 import ops as _ops
 
 MEMORY_LAYOUT = {
-    "flash": (lambda x: x, lambda x: x.transpose(1, 2)),
+    "flash": (lambda x: x, lambda x: x),  # kernel 4 reads [b,a,s,d] through strides: no varlen repacking
     "torch": (lambda x: x, lambda x: x),
     "vanilla": (lambda x: x, lambda x: x),
 }
@@ -52,15 +52,14 @@ def _flash_like(q, k, v, cu_seqlens_q, cu_seqlens_kv, batch_size):
 
 def fullattn(q, k, v, mode="flash", drop_rate=0, attn_mask=None, causal=False, cu_seqlens_q=None,
              cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None, batch_size=1):
-    """q [b,a,s,d], k/v [b,a,s1,d].  Returns [b,s,a,d] for mode "flash" and [b,a,s,d] otherwise, exactly like the
-    reference (attn.py:60-154: the flash branch views the varlen result as [b, s, a, d])."""
+    """q [b,a,s,d], k/v [b,a,s1,d] -> [b,a,s,d] in every mode, like the reference (attn.py:60-154: the flash
+    branch views the varlen result as [b, s, a, d] and its post-layout transposes it back)."""
     if mode == "flash":
         if causal or drop_rate:
             raise NotImplementedError("causal / dropout are unused on this path")
         if batch_size != 1 and cu_seqlens_q is not None:
             raise NotImplementedError("varlen batches > 1 are not used by any reference script")
-        x = _flash_like(q, k, v, cu_seqlens_q, cu_seqlens_kv, batch_size)
-        return x.transpose(1, 2)
+        return _flash_like(q, k, v, cu_seqlens_q, cu_seqlens_kv, batch_size)
     if mode == "torch":
         if attn_mask is not None and attn_mask.dtype != torch.bool:
             attn_mask = attn_mask.to(q.dtype)

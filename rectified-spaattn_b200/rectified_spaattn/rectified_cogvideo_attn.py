@@ -37,3 +37,43 @@ def rectified_block_sparse_attention(query, key, value, attn_mask, top_k, block_
         query, key, value, attn_mask, top_k, block_size_M, block_size_N, cu_seqlens_q, cu_seqlens_kv,
         max_seqlen_q, max_seqlen_kv, block_neighbor_list=block_neighbor_list, shape_xfuse=shape_xfuse,
         prob_threshold=p_remain_rates, text_length=text_length)
+
+
+from . import _processors as _P  # noqa: E402
+from .attn import fullattn as _fullattn  # noqa: E402
+
+
+class RectifiedCogVideoXVideoSpaAttnProcessor2_0(_P.ProcessorBase):
+    """CogVideoX1.5 processor (reference :410-523): text tokens moved LAST, RoPE on the video tokens only, sparse from
+    call 5 on; returns (hidden_states, encoder_hidden_states) split after the output projection."""
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states, attention_mask=None, image_rotary_emb=None):
+        n_txt = encoder_hidden_states.size(1)
+        hidden_states = torch.cat([hidden_states, encoder_hidden_states], dim=1)
+        b, s, _ = hidden_states.shape
+        if attention_mask is not None:
+            attention_mask = attn.prepare_attention_mask(attention_mask, s, b)
+            attention_mask = attention_mask.view(b, attn.heads, -1, attention_mask.shape[-1])
+        query, key, value = (_P.heads_first(f(hidden_states), attn.heads) for f in (attn.to_q, attn.to_k, attn.to_v))
+        if getattr(attn, "norm_q", None) is not None:
+            query = attn.norm_q(query)
+        if getattr(attn, "norm_k", None) is not None:
+            key = attn.norm_k(key)
+        if image_rotary_emb is not None:
+            query = torch.cat([_P.rope_real(query[:, :, :-n_txt], image_rotary_emb), query[:, :, -n_txt:]], dim=2)
+            if not getattr(attn, "is_cross_attention", False):
+                key = torch.cat([_P.rope_real(key[:, :, :-n_txt], image_rotary_emb), key[:, :, -n_txt:]], dim=2)
+
+        s_k = _P.kv_valid(attention_mask, key.shape[2])
+        if self.mode == "sparse" and self.current_step >= 5:
+            cu = [0, s_k, key.shape[2]]
+            hidden_states = rectified_block_sparse_attention(
+                query, key, value, attn_mask=attention_mask, top_k=self.select_block_num, cu_seqlens_q=cu,
+                cu_seqlens_kv=cu, max_seqlen_q=s, max_seqlen_kv=key.shape[2],
+                block_neighbor_list=self.block_neighbor_list, p_remain_rates=self.p_remain_rates, text_length=n_txt)
+        else:
+            hidden_states = _P.dense(_fullattn, query, key, value, "flash", attention_mask, s_k)
+        hidden_states = hidden_states.to(query.dtype)
+        self._tick()
+        hidden_states = attn.to_out[1](attn.to_out[0](hidden_states))
+        return hidden_states.split([hidden_states.size(1) - n_txt, n_txt], dim=1)

@@ -36,3 +36,53 @@ def rectified_block_sparse_attention(query, key, value, attn_mask, top_k, block_
         query, key, value, attn_mask, top_k, block_size_M, block_size_N, cu_seqlens_q, cu_seqlens_kv,
         max_seqlen_q, max_seqlen_kv, block_neighbor_list=block_neighbor_list, shape_xfuse=shape_xfuse,
         prob_threshold=p_remain_rates, text_length=text_length)
+
+
+from . import _processors as _P  # noqa: E402
+from .attn import fullattn as _fullattn  # noqa: E402
+
+
+class RectifiedFluxSpaAttnProcessor2_0(_P.ProcessorBase):
+    """Flux.1-dev processor (reference :408-542): text tokens moved LAST ("Jenga attention"), RoPE over the whole
+    joint sequence, sparse except in single-stream blocks 37..56 (the last 20), which stay dense."""
+
+    def __init__(self, mode, select_block_num, block_neighbor_list, p_remain_rates, processor_id=0, text_length=256):
+        super().__init__(mode, select_block_num, block_neighbor_list, p_remain_rates, processor_id)
+        self.text_length = text_length
+
+    def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, image_rotary_emb=None):
+        query, key, value = (_P.heads_first(f(hidden_states), attn.heads) for f in (attn.to_q, attn.to_k, attn.to_v))
+        if getattr(attn, "norm_q", None) is not None:
+            query = attn.norm_q(query)
+        if getattr(attn, "norm_k", None) is not None:
+            key = attn.norm_k(key)
+        if encoder_hidden_states is not None:  # dual-stream block: context projections, appended last
+            eq, ek, ev = (_P.heads_first(f(encoder_hidden_states), attn.heads)
+                          for f in (attn.add_q_proj, attn.add_k_proj, attn.add_v_proj))
+            if getattr(attn, "norm_added_q", None) is not None:
+                eq = attn.norm_added_q(eq)
+            if getattr(attn, "norm_added_k", None) is not None:
+                ek = attn.norm_added_k(ek)
+            query, key, value = (torch.cat([a, b], dim=2) for a, b in ((query, eq), (key, ek), (value, ev)))
+        if image_rotary_emb is not None:
+            query, key = _P.rope_real(query, image_rotary_emb), _P.rope_real(key, image_rotary_emb)
+
+        s_k = _P.kv_valid(attention_mask, key.shape[2])
+        if self.mode == "sparse" and (self.processor_id < 37 or self.processor_id >= 57):
+            cu = [0, s_k, key.shape[2]]
+            hidden_states = rectified_block_sparse_attention(
+                query, key, value, attn_mask=attention_mask, top_k=self.select_block_num, cu_seqlens_q=cu,
+                cu_seqlens_kv=cu, max_seqlen_q=query.shape[2], max_seqlen_kv=key.shape[2],
+                block_neighbor_list=self.block_neighbor_list, p_remain_rates=self.p_remain_rates,
+                text_length=self.text_length)
+        else:
+            hidden_states = _P.dense(_fullattn, query, key, value, "flash", attention_mask, s_k)
+        hidden_states = hidden_states.to(query.dtype)
+        self._tick()
+        if encoder_hidden_states is not None:
+            n_txt = encoder_hidden_states.shape[1]
+            hidden_states, encoder_hidden_states = hidden_states[:, :-n_txt], hidden_states[:, -n_txt:]
+            hidden_states = attn.to_out[1](attn.to_out[0](hidden_states))
+            encoder_hidden_states = attn.to_add_out(encoder_hidden_states)
+            return hidden_states, encoder_hidden_states
+        return hidden_states

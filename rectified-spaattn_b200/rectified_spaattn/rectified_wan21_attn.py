@@ -63,3 +63,21 @@ def rectified_block_sparse_attention(query, key, value, attn_mask, top_k, block_
         query, key, value, attn_mask, top_k, block_size_M, block_size_N, cu_seqlens_q, cu_seqlens_kv,
         max_seqlen_q, max_seqlen_kv, block_neighbor_list=block_neighbor_list, shape_xfuse=shape_xfuse,
         prob_threshold=p_remain_rates, first_frame_blocks=first_frame_blocks)
+
+
+from . import _processors as _P  # noqa: E402
+
+
+class RectifiedWanT2VSpaAttnProcessor2_0(_P.WanProcessorBase):
+    """Wan2.1 T2V self-attention processor (reference :389-509): sparse from layer 2 on and from call 10 on
+    (5 denoising steps x cond/uncond), dense ("flash") before; `current_step` wraps at 100."""
+
+    def sparse_now(self):
+        return self.processor_id >= 2 and self.current_step >= 10
+
+
+class RectifiedWanI2VSpaAttnProcessor2_0(_P.WanProcessorBase):
+    """Wan2.1 I2V (reference :512-632): sparse from layer 2 on at every step; adds the CLIP image cross-attention."""
+
+    def sparse_now(self):
+        return self.processor_id >= 2

@@ -1,0 +1,152 @@
+"""The eight Rectified*SpaAttnProcessor2_0 classes keep the reference's constructor arguments, attributes, gates,
+step counters and return values.  CPU tests cover the host logic; the GPU tests run every
+processor on a fake `Attention` module and check the sparse path in its dense limit (select_block_num >= NB =>
+every block kept, R = 1, C = 0) against the same processor in mode "torch" (plain SDPA through the same projections)."""
+import math
+
+import pytest
+import torch
+
+from fake_attention import FakeAttention
+from helpers import cos_sim
+from rectified_spaattn import rectified_cogvideo_attn as cog
+from rectified_spaattn import rectified_flux_attn as flux
+from rectified_spaattn import rectified_hunyuan_attn as hun
+from rectified_spaattn import rectified_wan21_attn as wan21
+from rectified_spaattn import rectified_wan22_attn as wan22
+
+
+# ------------------------------------------------------------------------------------------------ host logic
+def test_constructors_and_attributes():
+    p = wan21.RectifiedWanT2VSpaAttnProcessor2_0("sparse", 64, None, 0.3, processor_id=5, first_frame_blocks=12)
+    assert (p.mode, p.select_block_num, p.p_remain_rates, p.current_step, p.processor_id, p.first_frame_blocks) == \
+        ("sparse", 64, 0.3, 0, 5, 12)
+    p = wan22.RectifiedWanT2VSpaAttnProcessor2_0("sparse", 147, None, 0.3, 7, 28, warm_steps=10)
+    assert p.warm_steps == 10 and p.steps_per_cycle == 80
+    p = flux.RectifiedFluxSpaAttnProcessor2_0("sparse", 51, None, 0.3, processor_id=3, text_length=512)
+    assert p.text_length == 512
+    for cls in (hun.RectifiedHunyuanVideoSpaAttnProcessor2_0, cog.RectifiedCogVideoXVideoSpaAttnProcessor2_0):
+        q = cls("sparse", 179, None, 0.3, processor_id=1)
+        assert q.block_neighbor_list is None and q.current_step == 0
+
+
+def test_warmup_gates_match_reference():
+    t2v = wan21.RectifiedWanT2VSpaAttnProcessor2_0("sparse", 1, None, 0.3, processor_id=2)
+    assert not t2v.sparse_now()
+    t2v.current_step = 10
+    assert t2v.sparse_now()
+    t2v.processor_id = 1
+    assert not t2v.sparse_now()                                          # first two layers stay dense
+    i2v = wan21.RectifiedWanI2VSpaAttnProcessor2_0("sparse", 1, None, 0.3, processor_id=2)
+    assert i2v.sparse_now()                                              # no step warm-up for I2V
+    a14 = wan22.RectifiedWanI2VSpaAttnProcessor2_0("sparse", 1, None, 0.3, processor_id=40, warm_steps=4)
+    a14.current_step = 50
+    assert not a14.sparse_now()                                          # layers 0, 1, 40, 41 stay dense
+    a14.processor_id = 42
+    assert a14.sparse_now()
+    a14.current_step = 3
+    assert not a14.sparse_now()
+    for _ in range(77):
+        a14._tick()
+    assert a14.current_step == 0                                         # 3 + 77 = 80 -> wraps
+
+
+def test_rope_helpers_agree():
+    from rectified_spaattn import _processors as P
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(1, 2, 8, 16, generator=g)
+    ang = torch.rand(8, 8, generator=g) * 6.28
+    cos, sin = ang.cos().repeat_interleave(2, dim=1), ang.sin().repeat_interleave(2, dim=1)
+    a = P.rope_real(x, (cos, sin))
+    b = P.rope_complex(x, torch.polar(torch.ones(8, 8, dtype=torch.float64), ang.double())[None, None])
+    c = P.rope_cos_sin(x.transpose(1, 2), cos[None, :, None], sin[None, :, None]).transpose(1, 2)
+    assert torch.allclose(a, b, atol=1e-5) and torch.allclose(a, c, atol=1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ on the GPU
+def _mk(dev, *a, **kw):
+    torch.manual_seed(0)
+    return FakeAttention(*a, **kw).to(dev).to(torch.bfloat16)
+
+
+def _rope_tables(n, d, dev):
+    ang = torch.rand(n, d // 2, device=dev) * 6.28
+    return ang.cos().repeat_interleave(2, dim=1), ang.sin().repeat_interleave(2, dim=1), ang
+
+
+def _close(a, b):
+    a, b = a.float().cpu().numpy(), b.float().cpu().numpy()
+    assert cos_sim(a, b) >= 0.999 and abs(a - b).max() <= 4e-2 * max(1.0, abs(b).max())
+
+
+@pytest.mark.gpu
+def test_wan_processors_dense_limit():
+    dev = torch.device("cuda:0")
+    dim, heads, s = 256, 2, 1000
+    x = torch.randn(1, s, dim, device=dev).to(torch.bfloat16)
+    cos, sin, ang = _rope_tables(s, 128, dev)
+    for cls, rope, kw in ((wan21.RectifiedWanT2VSpaAttnProcessor2_0, "complex", {}),
+                          (wan21.RectifiedWanI2VSpaAttnProcessor2_0, "complex", dict(image_ctx=True)),
+                          (wan22.RectifiedWanTI2VSpaAttnProcessor2_0, "cos_sin", {}),
+                          (wan22.RectifiedWanT2VSpaAttnProcessor2_0, "cos_sin", {})):
+        attn = _mk(dev, dim, heads, norm="inner", **kw)
+        emb = torch.polar(torch.ones_like(ang, dtype=torch.float64), ang.double())[None, None] if rope == "complex" \
+            else (cos[None, :, None], sin[None, :, None])
+        enc = torch.randn(1, 257 + 512, dim, device=dev).to(torch.bfloat16) if kw else None
+        sp = cls("sparse", 99, None, 0.3, processor_id=3, first_frame_blocks=2)
+        ref = cls("torch", 99, None, 0.3, processor_id=3, first_frame_blocks=2)
+        sp.current_step = 20
+        with torch.no_grad():
+            if kw:   # I2V: self-attention keys come from hidden_states only when no text context is passed
+                out, want = sp(attn, x, None, None, emb), ref(attn, x, None, None, emb)
+            else:
+                out, want = sp(attn, x, None, None, emb), ref(attn, x, None, None, emb)
+        assert out.shape == (1, s, dim) and sp.current_step == 21
+        _close(out, want)
+        # warm-up call (dense through kernel 4 as "flash") gives the same answer
+        warm = cls("sparse", 99, None, 0.3, processor_id=0, first_frame_blocks=2)
+        with torch.no_grad():
+            _close(warm(attn, x, None, None, emb), want)
+    with pytest.raises(ImportError):
+        wan21.RectifiedWanT2VSpaAttnProcessor2_0("bogus", 1, None, 0.3)(attn, x, None, None, None)
+
+
+@pytest.mark.gpu
+def test_joint_text_processors_dense_limit():
+    dev = torch.device("cuda:0")
+    dim, heads, nv = 256, 2, 1024
+    x = torch.randn(1, nv, dim, device=dev).to(torch.bfloat16)
+    cos, sin, _ = _rope_tables(nv, 128, dev)
+    # HunyuanVideo dual-stream block: 256 text tokens, 200 valid
+    attn = _mk(dev, dim, heads, added=True)
+    txt = torch.randn(1, 256, dim, device=dev).to(torch.bfloat16)
+    mask = (torch.arange(nv + 256, device=dev) < nv + 200).view(1, 1, 1, -1)
+    sp = hun.RectifiedHunyuanVideoSpaAttnProcessor2_0("sparse", 99, None, 0.3)
+    ref = hun.RectifiedHunyuanVideoSpaAttnProcessor2_0("torch", 99, None, 0.3)
+    with torch.no_grad():
+        h, e = sp(attn, x, txt, mask, (cos, sin))
+        hr, er = ref(attn, x, txt, mask.expand(1, 1, nv + 256, nv + 256), (cos, sin))
+    assert h.shape == (1, nv, dim) and e.shape == (1, 256, dim) and sp.current_step == 1
+    _close(h, hr)
+    _close(e[:, :200], er[:, :200])            # padded text rows are undefined in the reference, zeros here
+    # Flux dual-stream block, 512 text tokens, RoPE over the joint sequence
+    cos2, sin2, _ = _rope_tables(nv + 512, 128, dev)
+    txt = torch.randn(1, 512, dim, device=dev).to(torch.bfloat16)
+    sp = flux.RectifiedFluxSpaAttnProcessor2_0("sparse", 99, None, 0.3, processor_id=1, text_length=512)
+    dn = flux.RectifiedFluxSpaAttnProcessor2_0("sparse", 99, None, 0.3, processor_id=40, text_length=512)  # dense layer
+    with torch.no_grad():
+        h, e = sp(attn, x, txt, None, (cos2, sin2))
+        hd, ed = dn(attn, x, txt, None, (cos2, sin2))
+    _close(h, hd)
+    _close(e, ed)
+    # CogVideoX: 226 text tokens (ragged: 1024 + 226 = 1250 tokens), sparse from call 5 on
+    attn = _mk(dev, dim, heads)
+    txt = torch.randn(1, 226, dim, device=dev).to(torch.bfloat16)
+    sp = cog.RectifiedCogVideoXVideoSpaAttnProcessor2_0("sparse", 99, None, 0.3)
+    with torch.no_grad():
+        hd, ed = sp(attn, x, txt, None, (cos, sin))      # call 0: dense
+        sp.current_step = 5
+        h, e = sp(attn, x, txt, None, (cos, sin))        # sparse, dense limit
+    assert h.shape == (1, nv, dim) and e.shape == (1, 226, dim)
+    _close(h, hd)
+    _close(e, ed)

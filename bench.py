@@ -73,7 +73,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(0.05)
 
     def summary(self):
         self.stop_flag = True
@@ -87,6 +87,16 @@ class ClockSampler(threading.Thread):
         return {"sm_mhz": busy[len(busy) // 2] if busy else None,
                 "sm_max_mhz": int(float(self.rows[0][1])) if self.rows else None,
                 "samples": len(self.rows), "reasons": sorted(reasons)}
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per launch of kernel 4 from the committed ncu --set full capture of this workload (or None)."""
+    p = os.path.join(REPO, "profiles", f"r01_ncu_summary_{workload}.json")
+    if not os.path.exists(p):
+        return None
+    k = json.load(open(p))["kernels"].get("attn_tc5_kernel", {})
+    rd, wr = k.get("dram__bytes_read.sum [Gbyte]"), k.get("dram__bytes_write.sum [Mbyte]")
+    return None if rd is None or wr is None else rd * 1e9 + wr * 1e6
 
 
 def measured_peaks():
@@ -207,7 +217,7 @@ def cpu_sample(wp, regime, budget_s=12.0, threads=None):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3a", choices=list(WORKLOADS))
@@ -357,8 +367,12 @@ def main():
             "gpu_launches": 5 * args.steps,
             "roofline": {"bound": "tensor", "kernel": "rect_attn (kernel 4)", "achieved": achieved,
                          "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
-                         "peak_source": f"{peaks['source']} cuBLAS bf16 burst; sustained {peaks['bf16_sustained']}",
-                         "kept_pairs_per_launch": pairs_all // world, "ms_per_launch": t_attn, "traffic": None},
+                         "peak_source": f"{peaks['source']} cuBLAS bf16 burst (kernel timed alone, back to back); "
+                                        f"sustained peak {peaks['bf16_sustained']}",
+                         "frac_of_sustained_peak": achieved / peaks["bf16_sustained"] if peaks["bf16_sustained"] else None,
+                         "flop_per_kept_pair": FLOP_PER_PAIR, "kept_pairs_per_launch": pairs_all // world,
+                         "ms_per_launch": t_attn, "traffic": ncu_traffic(args.workload) if world == 1 else None,
+                         "traffic_note": "DRAM read+write bytes of one launch, ncu --set full, profiles/r01_ncu_summary_*.json"},
             "clocks": clocks,
         }
         if e2e:

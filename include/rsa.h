@@ -115,6 +115,9 @@ typedef struct rsa_ws_view {
   float* R;           /* [BH, NQT]  (1 for text query blocks)              (wan21 :332)                     */
   float* C;           /* [BH, NQT, 128] (0 for text query blocks)          (wan21 :338)                     */
   int32_t nkc, score_ld, n_entries, ent_ld, mask_words, nqt, nogapr_ld, reserved;
+  uint16_t* sched_idx;   /* [BH, NQT, NB] the order kernel 4 walks each list in: for the pair of query tiles (2p, 2p+1)  */
+                         /* first the blocks both keep (ascending; K/V tiles loaded once for both), then the rest       */
+  int32_t* pair_shared;  /* [BH, ceil(NQT/2)] length of that common prefix                                              */
 } rsa_ws_view;
 
 size_t rsa_attn_workspace_bytes(const rsa_attn_desc* d);
@@ -142,7 +145,8 @@ int rsa_rect_c(const rsa_attn_desc* d, void* workspace, size_t workspace_bytes, 
 /* Kernel 4: block-sparse attention over the kept lists with the rectification epilogue O = Os*R + C fused into
  * the output write, text query blocks handled as dense rows.  Replaces _triton_block_sparse_attention_onehot
  * (wan21 :108-168, kernel :16-105), the epilogue (wan21 :346), the flash-attn call for text rows
- * (hunyuan :371-380) and the cat/permute/reshape (hunyuan :383-387).  Reads kept_idx, kept_cnt, R, C. */
+ * (hunyuan :371-380) and the cat/permute/reshape (hunyuan :383-387).  Reads kept_idx, kept_cnt, R, C; writes the
+ * pair schedule (sched_idx, pair_shared) it walks. */
 int rsa_sparse_attention(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
                          void* workspace, size_t workspace_bytes, void* stream);
 

@@ -106,8 +106,11 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int64_t lrow0 = (int64_t)bh * a.nqt + tile0;
   const int cnt0 = a.kept_cnt[lrow0];
   const int cnt1 = tile1 < a.nqt ? a.kept_cnt[lrow0 + 1] : 0;
-  const uint16_t* __restrict__ list0 = a.kept_idx + lrow0 * a.nb;
+  // the pair schedule (rsa_api.cu: pair_schedule_kernel): both lists start with the nsh blocks the two tiles have in
+  // common, in the same order, so over rounds [0, nsh) one K tile and one V tile serve both slots
+  const uint16_t* __restrict__ list0 = a.sched_idx + lrow0 * a.nb;
   const uint16_t* __restrict__ list1 = list0 + a.nb;
+  const int nsh = a.pair_shared[(int64_t)bh * gridDim.x + pair];
   const int rounds = max(cnt0, cnt1);
 
   const long long t0 = kDebug ? clock64() : 0;
@@ -176,7 +179,8 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const int cnt = s ? cnt1 : cnt0;
 #pragma unroll
             for (int t = 0; t < 2; ++t) {  // t = 0: V tile of block r-1; t = 1: K tile of block r
-              if (t == 0 ? (r >= 1 && r <= cnt) : (r < cnt)) {
+              const bool shared = s == 1 && (t == 0 ? r - 1 < nsh : r < nsh);  // slot 0 already loaded this tile
+              if ((t == 0 ? (r >= 1 && r <= cnt) : (r < cnt)) && !shared) {
                 const int row = (t == 0 ? (s ? prev1 : prev0) : (s ? cur1 : cur0)) * 128;
                 const void* map = t == 0 ? (const void*)&tmV : (const void*)&tmK;
                 const int st = n % kStages;
@@ -203,6 +207,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // The whole warp walks the schedule (so every descriptor is warp-uniform); one elected lane issues.
       const bool leader = elect_one();
       int n = 0;
+      int st_v0 = 0, par_v0 = 0, st_k0 = 0, par_k0 = 0;  // slot 0's stages of this round (slot 1 re-uses them when shared)
       for (int r = 0; r <= rounds; ++r) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -212,9 +217,14 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
           if (do_pv) {
             // O += P V for block r-1; key halves (P columns) in the order the softmax warpgroup releases them.
             // V's head_dim halves are the two granules of the stage: one N = 128 MN-major descriptor, LBO 16 KB.
-            const int st = n % kStages;
+            const bool reuse = s == 1 && r - 1 < nsh;  // V tile shared with slot 0
+            const int st = reuse ? st_v0 : n % kStages;
+            const int par = reuse ? par_v0 : (n / kStages) & 1;
+            if (!reuse) ++n;
+            if (s == 0) st_v0 = st, par_v0 = par;
+            const bool release = !(s == 0 && r - 1 < nsh);  // the last user frees the stage
             const uint64_t vd = smem_desc_sw128(sbase + kOffRing + st * 2 * kGranule, kGranule);
-            mbar_wait(bar(B_KVFULL + st), (n / kStages) & 1);
+            mbar_wait(bar(B_KVFULL + st), par);
             mbar_wait(bar(B_PHALF + 2 * s), (r - 1) & 1);
             tc_fence_after();
             RSA_TRACE(dbg && s == 0 && leader, r - 1, 9);
@@ -228,19 +238,23 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (leader) {
 #pragma unroll
               for (int ks = 4; ks < 8; ++ks) umma_ts(tO, tS + ks * 8, vd + 128 * ks, kIdescPV, 1u);
-              umma_commit(bar(B_KVEMPTY + st));
+              if (release) umma_commit(bar(B_KVEMPTY + st));
               if (r == cnt) umma_commit(bar(B_OFULL + s));
             }
-            ++n;
             RSA_TRACE(dbg && s == 0 && leader, r - 1, 11);
           }
           if (do_qk) {
             // S = Q K^T for block r: head_dim halves 0 / 1 = granules 0 / 1 of the stage (and of Q)
-            const int st = n % kStages;
+            const bool reuse = s == 1 && r < nsh;  // K tile shared with slot 0
+            const int st = reuse ? st_k0 : n % kStages;
+            const int par = reuse ? par_k0 : (n / kStages) & 1;
+            if (!reuse) ++n;
+            if (s == 0) st_k0 = st, par_k0 = par;
+            const bool release = !(s == 0 && r < nsh);
             const uint64_t kd = smem_desc_sw128(sbase + kOffRing + st * 2 * kGranule);
             const uint64_t qd = smem_desc_sw128(sbase + kOffQ + 2 * s * kGranule);
             if (r == 0) mbar_wait(bar(B_QFULL + s), 0);
-            mbar_wait(bar(B_KVFULL + st), (n / kStages) & 1);
+            mbar_wait(bar(B_KVFULL + st), par);
             tc_fence_after();
             RSA_TRACE(dbg && s == 0 && leader, r, 12);
             if (leader) {
@@ -249,10 +263,9 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const uint32_t off = (ks >> 2) * (kGranule >> 4) + 2 * (ks & 3);
                 umma_ss(tS, qd + off, kd + off, kIdescQK, ks != 0);
               }
-              umma_commit(bar(B_KVEMPTY + st));
+              if (release) umma_commit(bar(B_KVEMPTY + st));
               umma_commit(bar(B_SFULL + s));
             }
-            ++n;
             RSA_TRACE(dbg && s == 0 && leader, r, 8);
           }
           __syncwarp();
@@ -274,12 +287,12 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const float scale = a.scale_log2;
     const float2 scale2 = make_float2(scale, scale);
     float m_ref = -INFINITY, l = 0.f;
-    const int lim_last = cnt > 0 ? a.kv_len - (int)list[cnt - 1] * 128 : 128;  // valid keys in the last block
     const bool tr = dbg && s == 0 && row == 0;
 
     if (tile < a.nqt) {
       for (int i = 0; i < cnt; ++i) {
         RSA_TRACE(tr, i, 0);
+        const int lim = a.kv_len - (int)list[i] * 128;  // valid keys in this block (the schedule is not ascending)
         mbar_wait(bar(B_SFULL + s), i & 1);
         tc_fence_after();
         RSA_TRACE(tr, i, 1);
@@ -295,11 +308,11 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_wait_ld();
         tmem_ld32(tS + 64, sr + 64);  // in flight while the first half is reduced
         tmem_ld32(tS + 96, sr + 96);
-        const bool partial = i == cnt - 1 && lim_last < 128;  // keys >= kv_len -> -inf (wan21 :75-87)
+        const bool partial = lim < 128;  // keys >= kv_len -> -inf (wan21 :75-87); at most one block of a list
         if (partial) {
 #pragma unroll
           for (int c = 0; c < 64; ++c)
-            if (c >= lim_last) sr[c] = 0xff800000u;
+            if (c >= lim) sr[c] = 0xff800000u;
         }
         float mx0 = u2f(sr[0]), mx1 = u2f(sr[1]), mx2 = u2f(sr[2]), mx3 = u2f(sr[3]);
 #pragma unroll
@@ -318,7 +331,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (partial) {
 #pragma unroll
           for (int c = 64; c < 128; ++c)
-            if (c >= lim_last) sr[c] = 0xff800000u;
+            if (c >= lim) sr[c] = 0xff800000u;
         }
 #pragma unroll
         for (int c = 64; c < 128; c += 4) {

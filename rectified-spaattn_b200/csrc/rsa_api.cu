@@ -91,6 +91,8 @@ WsLayout make_layout(const rsa_attn_desc* d) {
   L.off_nneed = take((size_t)L.bh * (L.nq > 0 ? L.nq : 1) * 4);
   L.off_R = take((size_t)L.bh * L.nqt * f);
   L.off_C = take((size_t)L.bh * L.nqt * 128 * f);
+  L.off_sched = take((size_t)L.bh * L.nqt * L.nb * 2);
+  L.off_pshared = take((size_t)L.bh * ((L.nqt + 1) / 2) * 4);
   L.total = o;
   return L;
 }
@@ -128,6 +130,8 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->nb = L.nb;
   a->kept_idx = (const uint16_t*)(ws + L.off_kidx);
   a->kept_cnt = (const int32_t*)(ws + L.off_kcnt);
+  a->sched_idx = (uint16_t*)(ws + L.off_sched);
+  a->pair_shared = (int32_t*)(ws + L.off_pshared);
   a->R = (const float*)(ws + L.off_R);
   a->C = (const float*)(ws + L.off_C);
   a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.4426950408889634);
@@ -137,7 +141,83 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
 }
 
 static int launch_attention(const AttnArgs& a, cudaStream_t s) {
-  return g_attention_impl == 1 ? launch_attention_mma(a, s) : launch_attention_tc5(a, s);
+  if (g_attention_impl == 1) return launch_attention_mma(a, s);
+  int rc = launch_pair_schedule(a, s);
+  return rc != RSA_OK ? rc : launch_attention_tc5(a, s);
+}
+
+// Pair schedule for kernel 4: query tiles (2p, 2p+1) of a head are processed by one CTA.  Attention over a set of
+// kept blocks does not depend on the order they are visited in, so each list is re-ordered as [blocks both tiles keep,
+// ascending] + [the rest, ascending]; over the common prefix one K tile and one V tile serve both tiles.
+__global__ void __launch_bounds__(128) pair_schedule_kernel(const uint16_t* __restrict__ kept_idx,
+                                                            const int32_t* __restrict__ kept_cnt, int nqt, int nb,
+                                                            uint16_t* __restrict__ sched_idx,
+                                                            int32_t* __restrict__ pair_shared) {
+  __shared__ uint32_t bm[2][2048];  // one bit per KV block (nb <= 65535)
+  __shared__ int warp_tot[2][4];
+  __shared__ int n_common;
+  const int pair = blockIdx.x, bh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int npairs = (nqt + 1) / 2;
+  const int64_t row0 = (int64_t)bh * nqt + 2 * pair;
+  const bool has1 = 2 * pair + 1 < nqt;
+  const int cnt[2] = {kept_cnt[row0], has1 ? kept_cnt[row0 + 1] : 0};
+  const int words = (nb + 31) / 32;
+  for (int w = tid; w < words; w += 128) bm[0][w] = bm[1][w] = 0u;
+  if (tid == 0) n_common = 0;
+  __syncthreads();
+  for (int t = 0; t < 2; ++t)
+    for (int i = tid; i < cnt[t]; i += 128) {
+      const int x = kept_idx[(row0 + t) * nb + i];
+      atomicOr(&bm[t][x >> 5], 1u << (x & 31));
+    }
+  __syncthreads();
+  int c = 0;
+  for (int w = tid; w < words; w += 128) c += __popc(bm[0][w] & bm[1][w]);
+  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (lane == 0 && c) atomicAdd(&n_common, c);
+  __syncthreads();
+  const int ncom = n_common;
+  if (tid == 0) pair_shared[(int64_t)bh * npairs + pair] = ncom;
+  for (int t = 0; t < 2; ++t) {
+    const uint16_t* src = kept_idx + (row0 + t) * nb;
+    uint16_t* dst = sched_idx + (row0 + t) * nb;
+    int base_c = 0, base_r = ncom;  // next output slot among the common / the remaining blocks
+    for (int i0 = 0; i0 < cnt[t]; i0 += 128) {
+      const int i = i0 + tid;
+      const bool ok = i < cnt[t];
+      const int x = ok ? (int)src[i] : 0;
+      const bool com = ok && ((bm[t ^ 1][x >> 5] >> (x & 31)) & 1u);
+      const uint32_t bc = __ballot_sync(0xffffffffu, com), br = __ballot_sync(0xffffffffu, ok && !com);
+      if (lane == 0) {
+        warp_tot[0][warp] = __popc(bc);
+        warp_tot[1][warp] = __popc(br);
+      }
+      __syncthreads();
+      int pc = 0, pr = 0, tc = 0, trm = 0;
+      for (int w = 0; w < 4; ++w) {
+        if (w < warp) {
+          pc += warp_tot[0][w];
+          pr += warp_tot[1][w];
+        }
+        tc += warp_tot[0][w];
+        trm += warp_tot[1][w];
+      }
+      const uint32_t below = (1u << lane) - 1u;
+      if (com) dst[base_c + pc + __popc(bc & below)] = (uint16_t)x;
+      else if (ok) dst[base_r + pr + __popc(br & below)] = (uint16_t)x;
+      base_c += tc;
+      base_r += trm;
+      __syncthreads();
+    }
+  }
+}
+
+int launch_pair_schedule(const AttnArgs& a, cudaStream_t s) {
+  if (a.nqt == 0) return RSA_OK;
+  dim3 grid((a.nqt + 1) / 2, a.batch * a.heads);
+  pair_schedule_kernel<<<grid, 128, 0, s>>>(a.kept_idx, a.kept_cnt, a.nqt, a.nb, a.sched_idx, a.pair_shared);
+  RSA_CUDA_CHECK(cudaGetLastError());
+  return RSA_OK;
 }
 
 // dense byte mask [bh, nq, nkv] -> ascending u16 lists (one warp per row)
@@ -226,6 +306,8 @@ extern "C" int rsa_attn_workspace_view(const rsa_attn_desc* d, void* workspace, 
   out->nqt = L.nqt;
   out->nogapr_ld = L.nogapr_ld;
   out->reserved = 0;
+  out->sched_idx = (uint16_t*)(ws + L.off_sched);
+  out->pair_shared = (int32_t*)(ws + L.off_pshared);
   return RSA_OK;
 }
 
@@ -289,7 +371,9 @@ extern "C" int rsa_rectified_attention(const rsa_attn_desc* d, const void* q, co
 
 extern "C" size_t rsa_masked_attention_workspace_bytes(int bh, int nq, int nkv) {
   if (bh <= 0 || nq <= 0 || nkv <= 0) return 0;
-  return align_up((size_t)bh * nq * nkv * 2, 256) + align_up((size_t)bh * nq * 4, 256);
+  // kept lists + counts + pair schedule + common-prefix lengths
+  return 2 * align_up((size_t)bh * nq * nkv * 2, 256) + align_up((size_t)bh * nq * 4, 256) +
+         align_up((size_t)bh * ((nq + 1) / 2) * 4, 256);
 }
 
 extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v, void* out, int bh, int seq_q,
@@ -308,8 +392,11 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
     for (int i = 0; i < 2; ++i)
       if (st[t][i] < 0 || st[t][i] % 8) RSA_FAIL(RSA_ERR_UNSUPPORTED, "strides must be multiples of 8 elements");
   char* ws = (char*)workspace;
+  const size_t list_bytes = align_up((size_t)bh * n_q_blocks * n_kv_blocks * 2, 256);
   uint16_t* kidx = (uint16_t*)ws;
-  int32_t* kcnt = (int32_t*)(ws + align_up((size_t)bh * n_q_blocks * n_kv_blocks * 2, 256));
+  uint16_t* sched = (uint16_t*)(ws + list_bytes);
+  int32_t* kcnt = (int32_t*)(ws + 2 * list_bytes);
+  int32_t* pshared = (int32_t*)(ws + 2 * list_bytes + align_up((size_t)bh * n_q_blocks * 4, 256));
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_mask_to_lists(block_mask, bh, n_q_blocks, n_kv_blocks, (kv_len + 127) / 128, kidx, kcnt, s);
   if (rc != RSA_OK) return rc;
@@ -333,6 +420,8 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   a.nb = n_kv_blocks;
   a.kept_idx = kidx;
   a.kept_cnt = kcnt;
+  a.sched_idx = sched;
+  a.pair_shared = pshared;
   a.R = nullptr;
   a.C = nullptr;
   a.scale_log2 = (float)((1.0 / sqrt(128.0)) * 1.4426950408889634);

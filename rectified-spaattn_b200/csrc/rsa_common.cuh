@@ -30,7 +30,7 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 struct WsLayout {
   int bh, nq, nb, nqt, a, nkc, score_ld, n_entries, ent_ld, mask_words, nogapr_ld;
   size_t off_q_pool, off_q_mad, off_k_cat, off_k_mad, off_v_pool, off_scores, off_nogapr, off_probs, off_w,
-      off_mask, off_kidx, off_kcnt, off_nneed, off_R, off_C, total;
+      off_mask, off_kidx, off_kcnt, off_nneed, off_R, off_C, off_sched, off_pshared, total;
 };
 
 int validate_desc(const rsa_attn_desc* d);
@@ -58,6 +58,8 @@ struct AttnArgs {
   int nb;                   // kv blocks per head (row length of kept_idx)
   const uint16_t* kept_idx; // [bh, nqt, nb]
   const int32_t* kept_cnt;  // [bh, nqt]
+  uint16_t* sched_idx;      // [bh, nqt, nb]  pair schedule written by launch_pair_schedule, walked by kernel 4
+  int32_t* pair_shared;     // [bh, ceil(nqt/2)]
   const float* R;           // [bh, nqt]  or nullptr (=1)
   const float* C;           // [bh, nqt, 128] or nullptr (=0)
   float scale_log2;         // head_dim^-0.5 * log2(e)
@@ -67,6 +69,7 @@ struct AttnArgs {
 
 int launch_attention_mma(const AttnArgs& a, cudaStream_t s);      // mma.sync cross-check kernel
 int launch_attention_tc5(const AttnArgs& a, cudaStream_t s);      // tcgen05 / TMEM / TMA kernel
+int launch_pair_schedule(const AttnArgs& a, cudaStream_t s);  // kept lists -> sched_idx / pair_shared
 int launch_mask_to_lists(const uint8_t* mask, int bh, int nq, int nkv, int kv_blocks_valid, uint16_t* kept_idx,
                          int32_t* kept_cnt, cudaStream_t s);
 

@@ -36,7 +36,8 @@ class WsView(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "q_pool", "q_mad", "k_cat", "k_mad", "v_pool", "scores", "nogapr", "probs", "w_skip", "mask_bits",
         "kept_idx", "kept_cnt", "n_needed", "R", "C")] + [(n, C.c_int32) for n in (
-            "nkc", "score_ld", "n_entries", "ent_ld", "mask_words", "nqt", "nogapr_ld", "reserved")]
+            "nkc", "score_ld", "n_entries", "ent_ld", "mask_words", "nqt", "nogapr_ld", "reserved")] + [
+                ("sched_idx", C.c_void_p), ("pair_shared", C.c_void_p)]
 
 
 EXPORTS = [

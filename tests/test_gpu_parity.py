@@ -178,6 +178,35 @@ def test_end_to_end_vs_oracle(dev, name, impl):
     assert cos_sim(out, ref) >= COS_OUT
 
 
+@pytest.mark.parametrize("name", ["wan_c1", "hunyuan_mid", "cog_small"])
+def test_pair_schedule_is_a_permutation_with_common_prefix(dev, name):
+    """Kernel 4 walks each kept list as [blocks the tile pair (2p, 2p+1) has in common] + [the rest]; the order of
+    blocks does not change the attention result, the common prefix lets one K/V tile serve both tiles."""
+    case = load_case(name)
+    plan = _plan(case, dev, dump=False)
+    plan.run()
+    torch.cuda.synchronize()
+    vw = plan.view()
+    cnt = vw["kept_cnt"].cpu().numpy()
+    kept = vw["kept_idx"].cpu().numpy().astype(np.int64) & 0xFFFF
+    sched = vw["sched_idx"].cpu().numpy().astype(np.int64) & 0xFFFF
+    nsh = vw["pair_shared"].cpu().numpy()
+    bh, nqt = cnt.shape
+    for h in range(bh):
+        for t in range(nqt):
+            assert sorted(sched[h, t, : cnt[h, t]]) == list(kept[h, t, : cnt[h, t]])
+        for p in range((nqt + 1) // 2):
+            a = set(kept[h, 2 * p, : cnt[h, 2 * p]])
+            b = set(kept[h, 2 * p + 1, : cnt[h, 2 * p + 1]]) if 2 * p + 1 < nqt else set()
+            n = nsh[h, p]
+            assert n == len(a & b)
+            assert list(sched[h, 2 * p, :n]) == sorted(a & b)
+            if 2 * p + 1 < nqt:
+                assert list(sched[h, 2 * p + 1, :n]) == sorted(a & b)
+                assert list(sched[h, 2 * p + 1, n: cnt[h, 2 * p + 1]]) == sorted(b - a)
+            assert list(sched[h, 2 * p, n: cnt[h, 2 * p]]) == sorted(a - b)
+
+
 @pytest.mark.parametrize("impl", _impls())
 def test_dense_limit_equals_sdpa(dev, impl):
     """top_k >= NB => every block kept => R = 1, C = 0 => plain dense attention."""

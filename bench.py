@@ -225,6 +225,7 @@ def main():
     ap.add_argument("--attn-impl", type=int, default=0, help="0 = tcgen05 kernel (product); 1 = mma.sync cross-check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--host-chunk", type=int, default=2, help="heads per chunk of the pipelined host-buffer call")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -330,15 +331,22 @@ def main():
     nqt = geo.n_blocks
     density = pairs_all / (heads * nqt * nqt)
 
-    # end to end through the public entry point with HOST buffers (pinned): H2D of Q,K,V + call + D2H of the result
+    # end to end through the public entry point with HOST buffers (pinned): the per-family call receives host tensors
+    # and returns a host tensor; inside, rsa_rectified_attention_host pipelines H2D | kernels | D2H over chunks of
+    # heads.  For comparison the same call with three blocking-order copies around a device call ("serial").
     e2e = None
     if not args.no_e2e:
         call = entry_point(wp)
+        ops.HOST_HEADS_PER_CHUNK = args.host_chunk
         hq, hk, hv = (x.cpu().pin_memory() for x in (q, k, v))
         ho = torch.empty((1, wp["s"], h_loc * 128), dtype=torch.bfloat16).pin_memory()
         dq_, dk_, dv_ = (torch.empty_like(x) for x in (q, k, v))
+        res = {}
 
         def e2e_step():
+            res["o"] = call(hq, hk, hv, nbr)
+
+        def serial_step():
             dq_.copy_(hq, non_blocking=True)
             dk_.copy_(hk, non_blocking=True)
             dv_.copy_(hv, non_blocking=True)
@@ -347,11 +355,26 @@ def main():
 
         for _ in range(2):
             e2e_step()
-        ms_e2e = timed(e2e_step, max(3, args.steps // 2))
+            serial_step()
+        n_e2e = max(3, args.steps // 2)
+        ms_e2e = timed(e2e_step, n_e2e)
+        ms_serial = timed(serial_step, max(3, args.steps // 4))
+
+        def h2d_only():
+            dq_.copy_(hq, non_blocking=True)
+            dk_.copy_(hk, non_blocking=True)
+            dv_.copy_(hv, non_blocking=True)
+
+        ms_h2d = timed(h2d_only, 3)
+        assert torch.equal(res["o"].view(torch.int16), ho.view(torch.int16)), "pipelined and serial results differ"
         bi = 3 * q.numel() * 2 * world
         bo = ho.numel() * 2 * world
         e2e = {"value": wp["dense_flop_per_head"] * heads / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s",
-               "ms_per_step": ms_e2e, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo}
+               "ms_per_step": ms_e2e, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
+               "path": f"public per-family entry point on pinned host tensors -> rsa_rectified_attention_host, "
+                       f"{args.host_chunk} head(s) per chunk, H2D | kernels | D2H on three streams",
+               "ms_per_step_unpipelined": ms_serial,
+               "h2d_only_ms": ms_h2d}
 
     if rank == 0:
         peaks = measured_peaks()
@@ -364,7 +387,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config, "ms_per_attn_call": ms_step, "kept_pair_density": density, "stages_ms": stages,
             "attention_impl": "tcgen05" if args.attn_impl == 0 else "mma.sync cross-check",
-            "gpu_launches": 5 * args.steps,
+            "gpu_launches": 6 * args.steps,
             "roofline": {"bound": "tensor", "kernel": "rect_attn (kernel 4)", "achieved": achieved,
                          "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
                          "peak_source": f"{peaks['source']} cuBLAS bf16 burst (kernel timed alone, back to back); "

@@ -154,6 +154,18 @@ int rsa_sparse_attention(const rsa_attn_desc* d, const void* q, const void* k, c
 int rsa_rectified_attention(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* The whole call on HOST buffers: query/key/value/out are host pointers (page-locked memory gives the full PCIe rate;
+ * pageable memory is correct but serialises), described by the same descriptor (strides = the host tensors').  Heads
+ * are independent, so the call is cut into chunks of heads_per_chunk heads and pipelined on three streams: H2D of
+ * chunk c+1 | kernels 2-4 of chunk c (on `stream`) | D2H of chunk c-1, over double-buffered staging carved from
+ * device_scratch (rsa_host_call_scratch_bytes).  desc->nbr stays a DEVICE pointer.  Only enqueues work; the result is
+ * complete when `stream` reaches the point of return.  The two copy streams and six events per device are created on
+ * first use and kept (the only global state besides the error string).  Replaces, for a caller holding host tensors,
+ * `q.cuda(); k.cuda(); v.cuda(); rectified_block_sparse_attention(...).cpu()` around hunyuan :393-417. */
+size_t rsa_host_call_scratch_bytes(const rsa_attn_desc* d, int heads_per_chunk);
+int rsa_rectified_attention_host(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
+                                 int heads_per_chunk, void* device_scratch, size_t scratch_bytes, void* stream);
+
 /* Kernel 4 alone on a caller-supplied dense block mask (bytes, [BH, n_q_blocks, n_kv_blocks]) -- the literal
  * surface of _triton_block_sparse_attention_onehot(q, k, v, seqlens, block_mask, sm_scale) (wan21 :108-117).
  * q/k/v/out are [BH, seq, 128] with the given token strides; R = 1, C = 0.  workspace must hold

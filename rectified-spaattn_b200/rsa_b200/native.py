@@ -45,7 +45,8 @@ EXPORTS = [
     "rsa_permute_rows", "rsa_attn_workspace_bytes", "rsa_attn_workspace_view", "rsa_pool_stats",
     "rsa_block_scores", "rsa_block_select", "rsa_rect_c", "rsa_sparse_attention", "rsa_rectified_attention",
     "rsa_masked_attention_workspace_bytes", "rsa_masked_attention", "rsa_set_attention_impl",
-    "rsa_debug_set_attention_dump", "rsa_debug_set_attention_flags",
+    "rsa_debug_set_attention_dump", "rsa_debug_set_attention_flags", "rsa_host_call_scratch_bytes",
+    "rsa_rectified_attention_host",
 ]
 
 _lib = None
@@ -79,6 +80,9 @@ def lib():
     L.rsa_masked_attention_workspace_bytes.restype = sz
     L.rsa_masked_attention.argtypes = [p, p, p, p, i32, i32, i32, i32, C.POINTER(i64), C.POINTER(i64),
                                        C.POINTER(i64), C.POINTER(i64), p, i32, i32, p, sz, p]
+    L.rsa_host_call_scratch_bytes.argtypes = [C.POINTER(AttnDesc), i32]
+    L.rsa_host_call_scratch_bytes.restype = sz
+    L.rsa_rectified_attention_host.argtypes = [C.POINTER(AttnDesc), p, p, p, p, i32, p, sz, p]
     L.rsa_set_attention_impl.argtypes = [i32]
     L.rsa_debug_set_attention_dump.argtypes = [p]
     L.rsa_debug_set_attention_dump.restype = None

@@ -134,23 +134,8 @@ class Plan:
         self.out = out if out is not None else torch.empty((b, s, h, d), dtype=torch.bfloat16, device=q.device)
         o4 = self.out.view(b, s, h, d).permute(0, 2, 1, 3)
         self.nbr_dev = _device_neighbors(nbr, q.device)
-        desc = N.AttnDesc()
-        desc.batch, desc.heads, desc.seq, desc.head_dim = b, h, s, d
-        for name, t in (("q_stride", q), ("k_stride", k), ("v_stride", v), ("o_stride", o4)):
-            st = _strides3(t)
-            arr = getattr(desc, name)
-            for i in range(3):
-                arr[i] = st[i]
-        desc.family = geo.family
-        desc.n_blocks, desc.nq_blocks, desc.text_keys = geo.n_blocks, geo.nq_blocks, geo.text_keys
-        desc.kv_len, desc.kv_zero_from = geo.kv_len, geo.kv_zero_from
-        desc.text_end_block, desc.text_q_valid = geo.text_end_block, geo.text_q_valid
-        desc.top_k, desc.p_remain = int(top_k), float(p_remain)
-        desc.first_frame_blocks = geo.first_frame_blocks
-        if self.nbr_dev is not None:
-            desc.nbr_rows, desc.nbr_cols = self.nbr_dev.shape
-            desc.nbr = self.nbr_dev.data_ptr()
-        desc.debug_dump_probs = 1 if debug_dump_probs else 0
+        desc = _fill_desc(N.AttnDesc(), (b, h, s, d), [_strides3(t) for t in (q, k, v, o4)], geo, top_k, p_remain,
+                          self.nbr_dev, debug_dump_probs)
         self.desc = desc
         L = N.lib()
         self.ws_bytes = L.rsa_attn_workspace_bytes(C.byref(desc))
@@ -232,9 +217,81 @@ class Plan:
         return ((words >> (j & 31)) & 1).bool()
 
 
+def _fill_desc(desc, shape, strides, geo, top_k, p_remain, nbr_dev, debug_dump_probs=False):
+    b, h, s, d = shape
+    desc.batch, desc.heads, desc.seq, desc.head_dim = b, h, s, d
+    for name, st in zip(("q_stride", "k_stride", "v_stride", "o_stride"), strides):
+        arr = getattr(desc, name)
+        for i in range(3):
+            arr[i] = st[i]
+    desc.family = geo.family
+    desc.n_blocks, desc.nq_blocks, desc.text_keys = geo.n_blocks, geo.nq_blocks, geo.text_keys
+    desc.kv_len, desc.kv_zero_from = geo.kv_len, geo.kv_zero_from
+    desc.text_end_block, desc.text_q_valid = geo.text_end_block, geo.text_q_valid
+    desc.top_k, desc.p_remain = int(top_k), float(p_remain)
+    desc.first_frame_blocks = geo.first_frame_blocks
+    if nbr_dev is not None:
+        desc.nbr_rows, desc.nbr_cols = nbr_dev.shape
+        desc.nbr = nbr_dev.data_ptr()
+    desc.debug_dump_probs = 1 if debug_dump_probs else 0
+    return desc
+
+
+_host_scratch = {}
+HOST_HEADS_PER_CHUNK = 2
+
+
+def rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfuse=False, heads_per_chunk=None,
+                             out=None, device=None):
+    """The same call for PAGE-LOCKED HOST tensors (rsa_rectified_attention_host): chunks of heads stream through
+    H2D -> kernels -> D2H on three CUDA streams of `device` (default: the current device).  Returns a pinned host
+    tensor in the reference's layout; it is complete once the current stream of `device` is synchronised."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("no CUDA device: this path has no CPU implementation")
+    device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    for t, n in ((q, "query"), (k, "key"), (v, "value")):
+        if t.is_cuda or t.dtype != torch.bfloat16:
+            raise RuntimeError(f"{n} must be a bfloat16 host tensor")
+        if not t.is_pinned():
+            raise RuntimeError(f"{n} must be page-locked (tensor.pin_memory()): the copies run asynchronously")
+    b, h, s, d = q.shape
+    if k.shape != q.shape or v.shape != q.shape:
+        raise RuntimeError("query/key/value shapes differ")
+    if d != 128:
+        raise AssertionError("head_dim must be 128")
+    if s != geo.seq:
+        raise ValueError("geometry was built for a different sequence length")
+    if out is None:
+        out = torch.empty((b, s, h, d), dtype=torch.bfloat16, pin_memory=True)
+    elif out.is_cuda or not out.is_pinned() or out.numel() != b * s * h * d or out.dtype != torch.bfloat16:
+        raise RuntimeError("out must be a pinned bfloat16 host tensor of B*S*H*D elements")
+    o4 = out.view(b, s, h, d).permute(0, 2, 1, 3)
+    nbr_dev = _device_neighbors(nbr, device)
+    desc = _fill_desc(N.AttnDesc(), (b, h, s, d), [_strides3(t) for t in (q, k, v, o4)], geo, top_k, p_remain,
+                      nbr_dev)
+    hc = int(heads_per_chunk or HOST_HEADS_PER_CHUNK)
+    L = N.lib()
+    need = L.rsa_host_call_scratch_bytes(C.byref(desc), hc)
+    if need == 0:
+        raise N.RsaError("invalid attention descriptor: " + L.rsa_last_error_string().decode())
+    scratch = _host_scratch.get(str(device))
+    if scratch is None or scratch.numel() < need:
+        scratch = torch.empty(need, dtype=torch.uint8, device=device)
+        _host_scratch[str(device)] = scratch
+    with torch.cuda.device(device):
+        N.check(L.rsa_rectified_attention_host(C.byref(desc), q.data_ptr(), k.data_ptr(), v.data_ptr(),
+                                               out.data_ptr(), hc, scratch.data_ptr(), scratch.numel(),
+                                               _stream(device)), "rsa_rectified_attention_host")
+    out = out.view(b, s, h, d)
+    return out if shape_xfuse else out.view(b, s, h * d)
+
+
 def rectified_attention(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfuse=False):
     """[B,H,S,D] bf16 -> [B,S,H*D] (or [B,S,H,D] with shape_xfuse) -- the reference's return layout
-    (rectified_wan21_attn.py:353-357)."""
+    (rectified_wan21_attn.py:353-357).  Host (pinned) tensors take the pipelined host-buffer entry point and come
+    back as a pinned host tensor; the arithmetic runs on the GPU either way."""
+    if isinstance(q, torch.Tensor) and not q.is_cuda and torch.cuda.is_available():
+        return rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr, shape_xfuse)
     out = Plan(q, k, v, geo, top_k, p_remain, nbr).run()
     b, s, h, d = out.shape
     return out if shape_xfuse else out.view(b, s, h * d)

@@ -258,3 +258,58 @@ def test_entry_points_keep_reference_signatures(dev):
     assert o.shape == (1, 1250, 256)
     with pytest.raises(NotImplementedError):
         wan.rectified_block_sparse_attention(q, k, v, None, 2, block_size_M=64)
+
+
+# ------------------------------------------------------------------------------ host-buffer (pipelined) call
+@pytest.mark.parametrize("name,hc", [("hunyuan_small", 1), ("wan_ragged", 2), ("cog_small", 1), ("hunyuan_mid", 3)])
+def test_host_buffer_call_equals_device_call(dev, name, hc):
+    """rsa_rectified_attention_host pipelines chunks of heads (H2D | kernels | D2H); heads are independent, so the
+    result must be bit-identical to one device-resident call over all heads -- including a tail chunk (3 heads in
+    chunks of 2) and chunks larger than the head count."""
+    from rsa_b200 import ops
+    case = load_case(name)
+    # wan_ragged runs with 3 heads (its 2 + a copy of head 0) so that chunks of 2 leave a tail chunk of 1
+    q, k, v = (torch.from_numpy(np.concatenate([case[n], case[n][:, :1]], axis=1) if hc == 2 else case[n])
+               .to(torch.bfloat16) for n in ("q", "k", "v"))
+    geo = product_geometry(case["fam"], case["nv"], case["s"], case["text_len"], case["ntrue_d"], case["grid"][0])
+    nbr = torch.from_numpy(case["nbr"])
+    want = ops.rectified_attention(q.to(dev), k.to(dev), v.to(dev), geo, case["top_k"], case["p"], nbr).cpu()
+    hq, hk, hv = (t.pin_memory() for t in (q, k, v))
+    got = ops.rectified_attention_host(hq, hk, hv, geo, case["top_k"], case["p"], nbr, heads_per_chunk=hc)
+    torch.cuda.synchronize()
+    assert not got.is_cuda and got.is_pinned() and got.shape == want.shape
+    assert torch.equal(got.view(torch.int16), want.view(torch.int16))
+    # twice in a row on the same scratch (slot reuse across calls), and a [B,H,S,D]-strided host output
+    b, h, s, d = q.shape
+    out_hm = torch.empty(b, h, s, d, dtype=torch.bfloat16).pin_memory()
+    from rsa_b200 import native as N
+    import ctypes as CT
+    desc = ops._fill_desc(N.AttnDesc(), (b, h, s, d), [ops._strides3(t) for t in (hq, hk, hv, out_hm)], geo,
+                          case["top_k"], case["p"], ops._device_neighbors(nbr, dev))
+    L = N.lib()
+    need = L.rsa_host_call_scratch_bytes(CT.byref(desc), hc)
+    scratch = torch.empty(need, dtype=torch.uint8, device=dev)
+    for _ in range(2):
+        N.check(L.rsa_rectified_attention_host(CT.byref(desc), hq.data_ptr(), hk.data_ptr(), hv.data_ptr(),
+                                               out_hm.data_ptr(), hc, scratch.data_ptr(), need,
+                                               CT.c_void_p(torch.cuda.current_stream().cuda_stream)), "host call")
+    torch.cuda.synchronize()
+    assert torch.equal(out_hm.permute(0, 2, 1, 3).reshape(want.shape).view(torch.int16), want.view(torch.int16))
+
+
+def test_entry_point_accepts_pinned_host_tensors(dev):
+    """The per-family public call with page-locked host tensors returns a pinned host tensor (GPU arithmetic);
+    pageable host tensors are refused rather than silently serialised."""
+    from rectified_spaattn import rectified_hunyuan_attn as hun
+    case = load_case("hunyuan_small")
+    q, k, v = (torch.from_numpy(case[n]).to(torch.bfloat16) for n in ("q", "k", "v"))
+    nbr = torch.from_numpy(case["nbr"])
+    s, nt = case["s"], case["nv"] + case["ntrue_d"]
+    kw = dict(attn_mask=None, top_k=case["top_k"], cu_seqlens_q=[0, nt, s], cu_seqlens_kv=[0, nt, s], max_seqlen_q=s,
+              max_seqlen_kv=s, block_neighbor_list=nbr, p_remain_rates=case["p"])
+    want = hun.rectified_block_sparse_attention(q.to(dev), k.to(dev), v.to(dev), **kw).cpu()
+    got = hun.rectified_block_sparse_attention(q.pin_memory(), k.pin_memory(), v.pin_memory(), **kw)
+    torch.cuda.synchronize()
+    assert got.is_pinned() and torch.equal(got.view(torch.int16), want.view(torch.int16))
+    with pytest.raises(RuntimeError):
+        hun.rectified_block_sparse_attention(q, k, v, **kw)

@@ -33,6 +33,9 @@ WORKLOADS = {
                text_valid=0, heads=12, drop=0.75, ffb=True),
     "c3a": dict(desc="HunyuanVideo 720p 128f (reference default), 32x45x80 + 256 text = 115456 tokens", fam="hunyuan",
                 grid=(32, 45, 80), text=256, text_valid=200, heads=24, drop=0.8, ffb=False),
+    "c3b": dict(desc="HunyuanVideo 720p 129f (BASELINE.json configs[2]), 33x45x80 + 256 text = 119056 tokens; the "
+                     "ragged visual segment (928 blocks + 16 tokens) is zero-padded to 929 blocks inside the kernels",
+                fam="hunyuan", grid=(33, 45, 80), text=256, text_valid=200, heads=24, drop=0.8, ffb=False),
     "c4": dict(desc="Wan2.1-T2V-14B 720p 81f, 21x45x80 (75600 tokens)", fam="wan", grid=(21, 45, 80), text=0,
                text_valid=0, heads=40, drop=0.75, ffb=True),
     "c5": dict(desc="Flux.1-dev 4096x4096, 1x256x256 + 512 text = 66048 tokens", fam="flux", grid=(1, 256, 256),
@@ -184,7 +187,10 @@ def cpu_sample(wp, regime, budget_s=12.0, threads=None):
         geo = O.geometry_flux(s, wp["text"], wp["top_k"], P_REMAIN)
     t0 = time.perf_counter()
     nq, nv = geo.nq_blocks, geo.nq_blocks * 128
-    qp, dq = O.pool_stats(q, geo.seq, nq)
+    q, k, v = O.padded_inputs(q, k, v, geo)          # identity unless the visual segment is ragged (c3b)
+    hole = (nv - geo.gap, nv) if geo.gap else None
+    seq_v = geo.seq + geo.gap
+    qp, dq = O.pool_stats(q, seq_v, nq)
     kp, dk = O.pool_stats(k, geo.kv_zero_from, nq)
     vp, _ = O.pool_stats(v, geo.kv_zero_from, geo.n_blocks, want_mad=False)
     kt = k[nv: nv + geo.text_keys] if geo.family == "joint" else None
@@ -200,7 +206,7 @@ def cpu_sample(wp, regime, budget_s=12.0, threads=None):
         n = min(n, nq - n_done)
         t1 = time.perf_counter()
         O.masked_attention(q[n_done * 128:], k, v, m[n_done: n_done + n], geo.kv_len,
-                           min(n * 128, geo.seq - n_done * 128))
+                           min(n * 128, seq_v - n_done * 128), hole=hole)
         t_attn += time.perf_counter() - t1
         n_done += n
         n *= 2

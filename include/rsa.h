@@ -94,7 +94,16 @@ typedef struct rsa_attn_desc {
   int32_t nbr_rows, nbr_cols;          /* block_neighbor_list shape; both 0 = None                          */
   const uint8_t* nbr;                  /* DEVICE pointer, row-major bytes (torch.bool storage)              */
   int32_t debug_dump_probs;            /* !=0: stage 3b also writes P to the workspace (parity tests)       */
-  int32_t reserved;
+  int32_t vis_len;                     /* JOINT: visual tokens; text token i lives at memory row vis_len+i. */
+                                       /* 0 = nq_blocks*128 (block-aligned visual segment, the only case    */
+                                       /* the reference runs, hunyuan :356).  Otherwise nq_blocks =         */
+                                       /* ceil(vis_len/128): the last visual block is completed with        */
+                                       /* gap = nq_blocks*128 - vis_len zero rows (the Wan/CogVideoX rule,  */
+                                       /* wan21 :299-302: pooled as zeros, never attended, never written),  */
+                                       /* n_blocks = nq_blocks + ceil((seq - vis_len)/128), and kv_len,     */
+                                       /* kv_zero_from, text_end_block refer to that PADDED layout (visual  */
+                                       /* token t at t, text token i at nq_blocks*128 + i).  seq and the    */
+                                       /* strides always describe the tensors as they lie in memory.        */
 } rsa_attn_desc;
 
 /* Pointers into the caller's workspace (all device memory, fp32 unless noted). */

@@ -11,7 +11,13 @@ CASES = {
     "flux_small": ("flux", (1, 32, 32), 512, 512, 2, 1, 0.3, "walk", 6),
     "cog_small": ("cogvideo", (4, 16, 16), 226, 226, 2, 2, 0.3, "walk", 7),
     "hunyuan_mid": ("hunyuan", (8, 16, 32), 256, 77, 2, 6, 0.3, "walk", 8),
+    # ragged visual segment (780 = 6 blocks + 12 tokens), the small analogue of HunyuanVideo 129 frames (118 800 + 256):
+    # the reference cannot run it as given (it raises, rectified_hunyuan_attn.py:356); see geometry_hunyuan
+    "hunyuan_ragged": ("hunyuan", (5, 12, 13), 256, 200, 2, 2, 0.3, "walk", 9),
 }
+
+# cases the unmodified reference cannot run on the caller's tensors (fixtures are made on the explicitly padded layout)
+REFERENCE_NEEDS_PADDED_LAYOUT = ("hunyuan_ragged",)
 
 
 def case_inputs(name):

@@ -10,6 +10,11 @@ What is recorded (inputs are regenerated from seeds by oracle.rsa_oracle.synth_q
   kernel_fp16.npz     the literal Triton kernel (_triton_block_sparse_attention_onehot) under TRITON_INTERPRET=1
                       in fp16 on a random block mask (the interpreter has no bf16)
 
+Ragged HunyuanVideo case (hunyuan_ragged): the reference raises on it (:356), so it is run on the explicitly padded
+layout [visual | zero rows up to the block boundary | text] with num_true shifted by the pad; mask, probs, nogapr, R
+and C then come from the unmodified reference code, and the two attention stand-ins below additionally skip the pad
+keys (the extension's rule, geometry_hunyuan).  The stored output has the pad rows removed.
+
 Stand-ins for third-party pieces that cannot run on CPU (named so the goldens stay honest):
   * flash_attn_varlen_func (flash-attn, unpinned in the reference README; 2.8.3 here) -> per-sequence dense softmax
   * the Triton kernel inside the *combined* call -> dense masked softmax (its literal semantics are pinned
@@ -76,6 +81,9 @@ def make_gilbert(big=True):
 
 
 # ------------------------------------------------------------------------------------- mask builder + R, C
+HOLE = None  # (first, end) pad rows inside the sequence that no query may attend; set for the ragged case only
+
+
 def _varlen_dense(q, k, v, cu_q, cu_k):
     """Stand-in for flash_attn_varlen_func on [(tokens), H, D] tensors."""
     out = torch.zeros_like(q)
@@ -83,9 +91,12 @@ def _varlen_dense(q, k, v, cu_q, cu_k):
         q0, q1, k0, k1 = int(cu_q[i]), int(cu_q[i + 1]), int(cu_k[i]), int(cu_k[i + 1])
         if q1 <= q0:
             continue
+        keys = torch.arange(k0, k1)
+        if HOLE is not None:
+            keys = keys[(keys < HOLE[0]) | (keys >= HOLE[1])]
         qi = q[q0:q1].transpose(0, 1).float()
-        ki = k[k0:k1].transpose(0, 1).float()
-        vi = v[k0:k1].transpose(0, 1).float()
+        ki = k[keys].transpose(0, 1).float()
+        vi = v[keys].transpose(0, 1).float()
         s = (qi @ ki.transpose(1, 2)) * (q.shape[-1] ** -0.5)
         out[q0:q1] = (torch.softmax(s, -1) @ vi).transpose(0, 1).to(q.dtype)
     return out
@@ -98,7 +109,7 @@ def _dense_masked_kernel(q, k, v, seqlens, block_mask, sm_scale, bm=128, bn=128)
     for bi in range(b):
         for hi in range(h):
             o = O.masked_attention(q[bi, hi].float().numpy(), k[bi, hi].float().numpy(), v[bi, hi].float().numpy(),
-                                   block_mask[bi, hi].numpy(), int(seqlens[bi]), s)
+                                   block_mask[bi, hi].numpy(), int(seqlens[bi]), s, hole=HOLE)
             out[bi, hi] = torch.from_numpy(o).to(q.dtype)
     return out
 
@@ -131,6 +142,15 @@ def run_reference_case(name):
 
     ref._build_block_index_with_importance_optimized = build_spy
     ref.fullattn = fullattn_cpu
+    global HOLE
+    HOLE = None
+    s_in = s
+    gap = (-nv) % 128 if fam == "hunyuan" else 0
+    if gap:
+        q, k, v = (np.concatenate([x[:, :, :nv], np.zeros_like(x[:, :, :gap]), x[:, :, nv:]], axis=2) for x in (q, k, v))
+        HOLE = (nv, nv + gap)
+        s = s + gap
+        ntrue_d = ntrue_d + gap
     tq, tk, tv = (torch.from_numpy(x) for x in (q, k, v))
     ffb = (nv + 127) // 128 // t if fam == "wan" else None
     num_true = nv + ntrue_d
@@ -170,6 +190,11 @@ def run_reference_case(name):
     idx = torch.arange(0, rows_vis, 128)
     c = oc[:, idx]                                                 # [H, NQ, D]
     r = (orc[:, idx] - c).mean(dim=-1)                             # [H, NQ]  (R + C - C, 128 identical columns)
+    out_rows = out[0]
+    if gap:
+        out_rows = torch.cat([out_rows[:nv], out_rows[nv + gap:]], dim=0)
+        assert out_rows.shape[0] == s_in
+    HOLE = None
     np.savez_compressed(
         os.path.join(GOLD, f"mask_{name}.npz"),
         mask=np.packbits(cap["mask"][0].numpy().astype(np.uint8)), mask_shape=np.array(cap["mask"][0].shape),
@@ -177,7 +202,7 @@ def run_reference_case(name):
         nogapr=np.packbits(cap["nogapr"][0].numpy().astype(np.uint8)),
         nogapr_shape=np.array(cap["nogapr"][0].shape),
         R=r.numpy().astype(np.float32), C=c.numpy().astype(np.float32),
-        out=out[0].numpy().astype(np.float32),
+        out=out_rows.numpy().astype(np.float32),
         nbr=np.packbits(nbr.numpy().astype(np.uint8)), nbr_shape=np.array(nbr.shape))
     print("case", name, "mask density", float(cap["mask"].float().mean()), "nogapr", float(cap["nogapr"].float().mean()),
           "R min/mean", float(r.min()), float(r.mean()), flush=True)
@@ -219,6 +244,7 @@ if __name__ == "__main__":
         make_gilbert()
     if "masks" in what:
         for n in CASES:
-            run_reference_case(n)
+            if n in what or not any(w in CASES for w in what):   # `masks <case> ...` regenerates only those
+                run_reference_case(n)
     if "kernel" in what:
         make_kernel_fp16()

@@ -228,6 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_mma_kernel(const AttnArgs a)
 }  // namespace
 
 int launch_attention_mma(const AttnArgs& a, cudaStream_t s) {
+  if (a.gap != 0) RSA_FAIL(RSA_ERR_UNSUPPORTED, "the mma.sync cross-check kernel handles block-aligned visual segments only");
   static bool configured = false;
   if (!configured) {
     RSA_CUDA_CHECK(cudaFuncSetAttribute(attn_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));

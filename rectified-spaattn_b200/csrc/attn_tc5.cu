@@ -95,7 +95,10 @@ constexpr int kTraceBase = 33024, kTraceSteps = 64, kTraceSlots = 16;
 template <bool kDebug, int kPolyPairs>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                const __grid_constant__ CUtensorMap tmV, const AttnArgs a) {
+                const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQt,
+                const __grid_constant__ CUtensorMap tmKt, const __grid_constant__ CUtensorMap tmVt, const AttnArgs a) {
+  // tmQ/tmK/tmV cover the visual rows [0, vis_len) (rows past the end read as zeros = the padding of the last visual
+  // block); tmQt/tmKt/tmVt cover the text rows, which start at memory row vis_len (RowMap, rsa_common.cuh).
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // pairs of adjacent query tiles; the last pairs hold the dense (text) tiles, the longest: schedule them first
@@ -124,6 +127,10 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     prefetch_tensormap(&tmQ);
     prefetch_tensormap(&tmK);
     prefetch_tensormap(&tmV);
+    if (a.nq_vis < a.nb) {
+      prefetch_tensormap(&tmKt);
+      prefetch_tensormap(&tmVt);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(bar(B_QFULL + s), 1);
       mbar_init(bar(B_SFULL + s), 1);
@@ -153,15 +160,17 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       // Same deterministic order as the MMA warp: round r, slot s: V_s(r-1) then K_s(r); one ring stage = one
       // whole 128 x 128 tile (two granules, one barrier).
       if (lane == 0) {
-        if (cnt0 > 0) {
-          mbar_arrive_expect_tx(bar(B_QFULL), 2 * kGranule);
-          tma_load_4d(sbase + kOffQ, &tmQ, bar(B_QFULL), 0, tile0 * 128, h, b);
-          tma_load_4d(sbase + kOffQ + kGranule, &tmQ, bar(B_QFULL), 64, tile0 * 128, h, b);
-        }
-        if (cnt1 > 0) {
-          mbar_arrive_expect_tx(bar(B_QFULL + 1), 2 * kGranule);
-          tma_load_4d(sbase + kOffQ + 2 * kGranule, &tmQ, bar(B_QFULL + 1), 0, tile1 * 128, h, b);
-          tma_load_4d(sbase + kOffQ + 3 * kGranule, &tmQ, bar(B_QFULL + 1), 64, tile1 * 128, h, b);
+#pragma unroll
+        for (int s = 0; s < 2; ++s) {
+          const int tile = s ? tile1 : tile0;
+          if ((s ? cnt1 : cnt0) > 0) {
+            const bool txt = tile >= a.nq_vis;
+            const void* map = txt ? (const void*)&tmQt : (const void*)&tmQ;
+            const int row = (txt ? tile - a.nq_vis : tile) * 128;
+            mbar_arrive_expect_tx(bar(B_QFULL + s), 2 * kGranule);
+            tma_load_4d(sbase + kOffQ + 2 * s * kGranule, map, bar(B_QFULL + s), 0, row, h, b);
+            tma_load_4d(sbase + kOffQ + (2 * s + 1) * kGranule, map, bar(B_QFULL + s), 64, row, h, b);
+          }
         }
       }
       int n = 0;  // stage counter: ring stage n % kStages, use n / kStages
@@ -181,8 +190,11 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int t = 0; t < 2; ++t) {  // t = 0: V tile of block r-1; t = 1: K tile of block r
               const bool shared = s == 1 && (t == 0 ? r - 1 < nsh : r < nsh);  // slot 0 already loaded this tile
               if ((t == 0 ? (r >= 1 && r <= cnt) : (r < cnt)) && !shared) {
-                const int row = (t == 0 ? (s ? prev1 : prev0) : (s ? cur1 : cur0)) * 128;
-                const void* map = t == 0 ? (const void*)&tmV : (const void*)&tmK;
+                const int blk = t == 0 ? (s ? prev1 : prev0) : (s ? cur1 : cur0);
+                const bool txt = blk >= a.nq_vis;
+                const int row = (txt ? blk - a.nq_vis : blk) * 128;
+                const void* map = t == 0 ? (txt ? (const void*)&tmVt : (const void*)&tmV)
+                                         : (txt ? (const void*)&tmKt : (const void*)&tmK);
                 const int st = n % kStages;
                 const uint32_t dst = sbase + kOffRing + st * 2 * kGranule;
                 mbar_wait(bar(B_KVEMPTY + st), ((n / kStages) & 1) ^ 1);
@@ -292,7 +304,11 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     if (tile < a.nqt) {
       for (int i = 0; i < cnt; ++i) {
         RSA_TRACE(tr, i, 0);
-        const int lim = a.kv_len - (int)list[i] * 128;  // valid keys in this block (the schedule is not ascending)
+        // valid keys in this block (the schedule is not ascending): the end of the valid keys, and the end of the
+        // visual tokens inside the last visual block (zero rows that pad it are never attended)
+        const int blk = (int)list[i];
+        int lim = a.kv_len - blk * 128;
+        if (blk < a.nq_vis) lim = min(lim, a.vis_len - blk * 128);
         mbar_wait(bar(B_SFULL + s), i & 1);
         tc_fence_after();
         RSA_TRACE(tr, i, 1);
@@ -308,7 +324,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tmem_wait_ld();
         tmem_ld32(tS + 64, sr + 64);  // in flight while the first half is reduced
         tmem_ld32(tS + 96, sr + 96);
-        const bool partial = lim < 128;  // keys >= kv_len -> -inf (wan21 :75-87); at most one block of a list
+        const bool partial = lim < 128;  // keys >= kv_len -> -inf (wan21 :75-87); at most two blocks of a list
         if (partial) {
 #pragma unroll
           for (int c = 0; c < 64; ++c)
@@ -410,9 +426,11 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const float R = a.R ? a.R[lrow] : 1.f;
       const float inv = l > 0.f ? R / l : 0.f;
       const float* __restrict__ crow = a.C ? a.C + lrow * 128 : nullptr;
-      const int grow = tile * 128 + row;
-      const bool store = grow < a.seq_q, zero = grow >= a.q_valid;
-      __nv_bfloat16* orow = a.o + b * a.os[0] + h * a.os[1] + (int64_t)grow * a.os[2];
+      const int grow = tile * 128 + row;                            // row in the padded layout
+      const int mrow = tile < a.nq_vis ? grow : grow - a.gap;       // row in memory
+      const bool store = tile < a.nq_vis ? grow < min(a.vis_len, a.seq_q) : mrow < a.seq_q;
+      const bool zero = grow >= a.q_valid;
+      __nv_bfloat16* orow = a.o + b * a.os[0] + h * a.os[1] + (int64_t)mrow * a.os[2];
       if (cnt > 0) {
         mbar_wait(bar(B_OFULL + s), 0);
         tc_fence_after();
@@ -502,16 +520,19 @@ int make_map(CUtensorMap* m, const __nv_bfloat16* base, int batch, int heads, in
   return RSA_OK;
 }
 
+struct Maps {
+  CUtensorMap q, k, v, qt, kt, vt;
+};
+
 template <bool kDebug, int kPolyPairs>
-int launch(dim3 grid, cudaStream_t s, const CUtensorMap& tq, const CUtensorMap& tk, const CUtensorMap& tv,
-           const AttnArgs& a) {
+int launch(dim3 grid, cudaStream_t s, const Maps& m, const AttnArgs& a) {
   static bool configured = false;  // one flag per instantiation
   if (!configured) {
     RSA_CUDA_CHECK(cudaFuncSetAttribute(attn_tc5_kernel<kDebug, kPolyPairs>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
-  attn_tc5_kernel<kDebug, kPolyPairs><<<grid, kThreads, kSmemBytes, s>>>(tq, tk, tv, a);
+  attn_tc5_kernel<kDebug, kPolyPairs><<<grid, kThreads, kSmemBytes, s>>>(m.q, m.k, m.v, m.qt, m.kt, m.vt, a);
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;
 }
@@ -529,19 +550,28 @@ int poly_pairs() {
 
 int launch_attention_tc5(const AttnArgs& a, cudaStream_t s) {
   if (a.nqt == 0) return RSA_OK;
-  CUtensorMap tq, tk, tv;
+  Maps m;
   int rc;
-  if ((rc = make_map(&tq, a.q, a.batch, a.heads, a.seq_q, a.qs)) != RSA_OK) return rc;
-  if ((rc = make_map(&tk, a.k, a.batch, a.heads, a.seq_kv, a.ks)) != RSA_OK) return rc;
-  if ((rc = make_map(&tv, a.v, a.batch, a.heads, a.seq_kv, a.vs)) != RSA_OK) return rc;
+  // visual rows [0, vis) and text rows [vis, seq) of each tensor (RowMap); without a text segment the text maps are
+  // never used and simply repeat the visual ones
+  const int vis_q = a.vis_len < a.seq_q ? a.vis_len : a.seq_q, vis_kv = a.vis_len < a.seq_kv ? a.vis_len : a.seq_kv;
+  if ((rc = make_map(&m.q, a.q, a.batch, a.heads, vis_q, a.qs)) != RSA_OK) return rc;
+  if ((rc = make_map(&m.k, a.k, a.batch, a.heads, vis_kv, a.ks)) != RSA_OK) return rc;
+  if ((rc = make_map(&m.v, a.v, a.batch, a.heads, vis_kv, a.vs)) != RSA_OK) return rc;
+  m.qt = m.q, m.kt = m.k, m.vt = m.v;
+  if (a.seq_q > vis_q && (rc = make_map(&m.qt, a.q + (int64_t)vis_q * a.qs[2], a.batch, a.heads, a.seq_q - vis_q, a.qs)) != RSA_OK) return rc;
+  if (a.seq_kv > vis_kv) {
+    if ((rc = make_map(&m.kt, a.k + (int64_t)vis_kv * a.ks[2], a.batch, a.heads, a.seq_kv - vis_kv, a.ks)) != RSA_OK) return rc;
+    if ((rc = make_map(&m.vt, a.v + (int64_t)vis_kv * a.vs[2], a.batch, a.heads, a.seq_kv - vis_kv, a.vs)) != RSA_OK) return rc;
+  }
   const dim3 grid((a.nqt + 1) / 2, a.batch * a.heads);
-  if (a.dbg) return launch<true, kDefaultPolyPairs>(grid, s, tq, tk, tv, a);
+  if (a.dbg) return launch<true, kDefaultPolyPairs>(grid, s, m, a);
   switch (poly_pairs()) {
-    case 1: return launch<false, 1>(grid, s, tq, tk, tv, a);
-    case 3: return launch<false, 3>(grid, s, tq, tk, tv, a);
-    case 4: return launch<false, 4>(grid, s, tq, tk, tv, a);
-    case 2: return launch<false, 2>(grid, s, tq, tk, tv, a);
-    default: return launch<false, 0>(grid, s, tq, tk, tv, a);
+    case 1: return launch<false, 1>(grid, s, m, a);
+    case 3: return launch<false, 3>(grid, s, m, a);
+    case 4: return launch<false, 4>(grid, s, m, a);
+    case 2: return launch<false, 2>(grid, s, m, a);
+    default: return launch<false, 0>(grid, s, m, a);
   }
 }
 

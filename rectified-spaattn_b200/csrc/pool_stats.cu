@@ -11,6 +11,8 @@
 // it = 0..7, and the eight columns 8*(l&15) .. +7.  Summation order (the oracle replicates it bit for bit):
 //   lane chain over it = 0..7 (sequential fp32) -> half-warp pair (shfl xor 16) -> warps 0..7 (sequential).
 // Rows >= valid_rows contribute zeros; the divisor is always 128 (the reference zero-pads, wan21 :299-302).
+// Rows are counted in the padded layout (rsa_common.cuh RowMap): a visual block reads memory rows below vis_len and
+// zeros above, a text block reads memory rows shifted down by the gap.
 #include "rsa_common.cuh"
 
 namespace rsa {
@@ -21,14 +23,15 @@ constexpr int kThreads = 256;
 struct PoolArgs {
   const __nv_bfloat16* x[3];  // q, k, v
   int64_t stride[3][3];       // (batch, head, token) element strides
-  int valid_rows[3];          // rows >= this are zeros
+  int valid_rows[3];          // padded-layout rows >= this are zeros
+  int vis_len, nq_vis, gap;   // RowMap
   int n_blk[3];               // blocks to pool per tensor (NQ, NQ, NB)
   float* mean[3];             // q_pool, k_cat, v_pool
   float* mad[3];              // q_mad, k_mad, nullptr
   int out_rows[3];            // rows per head of the mean arrays (NQ, NKC, NB)
   int heads;
   // text keys copied as fp32 rows behind the pooled keys
-  int text_keys, text_from;   // a, first text token (= NQ*128)
+  int text_keys, text_from;   // a, memory row of the first text token (= vis_len)
 };
 
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
@@ -57,7 +60,7 @@ __global__ void __launch_bounds__(kThreads) pool_stats_kernel(const PoolArgs a) 
       const __nv_bfloat16* src = a.x[1] + b * a.stride[1][0] + h * a.stride[1][1] + (int64_t)tok * a.stride[1][2];
       float f[8];
       uint4 u = make_uint4(0, 0, 0, 0);
-      if (tok < a.valid_rows[1]) u = *reinterpret_cast<const uint4*>(src + 8 * (tid & 15));
+      if (tok + a.gap < a.valid_rows[1]) u = *reinterpret_cast<const uint4*>(src + 8 * (tid & 15));
       unpack8(u, f);
       float* dst = a.mean[1] + ((int64_t)bh * a.out_rows[1] + a.n_blk[1] + t) * 128 + 8 * (tid & 15);
       reinterpret_cast<float4*>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
@@ -74,14 +77,16 @@ __global__ void __launch_bounds__(kThreads) pool_stats_kernel(const PoolArgs a) 
   const int64_t ts = a.stride[which][2];
   const int col = 8 * (lane & 15);
   const int row0 = blk * 128 + 16 * warp + (lane >> 4);
-  const int valid = a.valid_rows[which];
+  const bool visual = blk < a.nq_vis;
+  const int valid = visual ? min(a.valid_rows[which], a.vis_len) : a.valid_rows[which];
+  const int shift = visual ? 0 : a.gap;  // padded row -> memory row
 
   uint4 raw[8];
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = row0 + 2 * it;
     raw[it] = make_uint4(0, 0, 0, 0);
-    if (r < valid) raw[it] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)r * ts + col));
+    if (r < valid) raw[it] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(r - shift) * ts + col));
   }
 
   float acc[8];
@@ -153,8 +158,13 @@ int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, cons
     a.stride[1][i] = d->k_stride[i];
     a.stride[2][i] = d->v_stride[i];
   }
-  const int kvz = d->kv_zero_from < d->seq ? d->kv_zero_from : d->seq;
-  a.valid_rows[0] = d->seq;
+  const RowMap rm = row_map(d);
+  const int seq_v = d->seq + rm.gap;
+  const int kvz = d->kv_zero_from < seq_v ? d->kv_zero_from : seq_v;
+  a.vis_len = rm.vis_len;
+  a.nq_vis = rm.nq_vis;
+  a.gap = rm.gap;
+  a.valid_rows[0] = seq_v;
   a.valid_rows[1] = kvz;
   a.valid_rows[2] = kvz;
   a.n_blk[0] = L.nq;
@@ -171,7 +181,7 @@ int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, cons
   a.out_rows[2] = L.nb;
   a.heads = d->heads;
   a.text_keys = L.a;
-  a.text_from = L.nq * 128;
+  a.text_from = rm.vis_len;
   const int text_ctas = (L.a + 15) / 16;
   const int gx = L.nb > text_ctas ? L.nb : text_ctas;
   dim3 grid(gx, L.bh, L.a > 0 ? 4 : 3);

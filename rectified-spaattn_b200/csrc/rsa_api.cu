@@ -27,26 +27,33 @@ int validate_desc(const rsa_attn_desc* d) {
   if (d->batch <= 0 || d->heads <= 0 || d->seq <= 0) RSA_FAIL(RSA_ERR_ARG, "batch/heads/seq must be positive");
   if ((int64_t)d->batch * d->heads > 65535) RSA_FAIL(RSA_ERR_UNSUPPORTED, "batch*heads > 65535");
   if (d->family != RSA_FAMILY_WAN && d->family != RSA_FAMILY_JOINT) RSA_FAIL(RSA_ERR_ARG, "unknown family %d", d->family);
-  const int nb = (d->seq + RSA_BLOCK - 1) / RSA_BLOCK;
-  if (d->n_blocks != nb) RSA_FAIL(RSA_ERR_ARG, "n_blocks=%d but ceil(seq/128)=%d", d->n_blocks, nb);
+  if (d->vis_len < 0 || d->vis_len > d->seq) RSA_FAIL(RSA_ERR_ARG, "vis_len=%d out of [0, seq]", d->vis_len);
+  const RowMap rm = row_map(d);
+  const int nb = rm.nq_vis + (d->seq - rm.vis_len + RSA_BLOCK - 1) / RSA_BLOCK;
+  if (d->n_blocks != nb)
+    RSA_FAIL(RSA_ERR_ARG, "n_blocks=%d but the layout has %d (visual %d + text %d)", d->n_blocks, nb, rm.nq_vis, nb - rm.nq_vis);
   if (d->nq_blocks < 0 || d->nq_blocks > nb) RSA_FAIL(RSA_ERR_ARG, "nq_blocks=%d out of [0,%d]", d->nq_blocks, nb);
+  const int seq_v = d->seq + rm.gap;  // length of the padded layout
   if (d->family == RSA_FAMILY_WAN) {
     if (d->nq_blocks != nb || d->text_keys != 0) RSA_FAIL(RSA_ERR_ARG, "WAN family needs nq_blocks == n_blocks and text_keys == 0");
+    if (d->vis_len != 0 && d->vis_len != d->seq) RSA_FAIL(RSA_ERR_ARG, "WAN family: vis_len must be 0 or seq");
   } else {
     if (d->nq_blocks >= nb) RSA_FAIL(RSA_ERR_ARG, "JOINT family needs at least one text block");
-    if (d->text_keys < 1 || (int64_t)d->nq_blocks * RSA_BLOCK + d->text_keys > (int64_t)nb * RSA_BLOCK)
-      RSA_FAIL(RSA_ERR_ARG, "text_keys=%d must be in [1, 128*(n_blocks - nq_blocks)]", d->text_keys);
+    if (d->vis_len != 0 && d->nq_blocks != (d->vis_len + RSA_BLOCK - 1) / RSA_BLOCK)
+      RSA_FAIL(RSA_ERR_ARG, "nq_blocks=%d but ceil(vis_len/128)=%d", d->nq_blocks, (d->vis_len + RSA_BLOCK - 1) / RSA_BLOCK);
+    if (d->text_keys < 1 || d->text_keys > d->seq - rm.vis_len)
+      RSA_FAIL(RSA_ERR_ARG, "text_keys=%d must be in [1, seq - vis_len]", d->text_keys);
   }
   const int n_ent = d->nq_blocks + (d->family == RSA_FAMILY_JOINT ? 1 : 0);
   if (n_ent > RSA_MAX_ENTRIES) RSA_FAIL(RSA_ERR_UNSUPPORTED, "more than %d sortable blocks per row", RSA_MAX_ENTRIES);
   if (nb > 65535) RSA_FAIL(RSA_ERR_UNSUPPORTED, "more than 65535 KV blocks");
-  if (d->kv_len < 1 || d->kv_len > d->seq) RSA_FAIL(RSA_ERR_ARG, "kv_len=%d out of [1, seq]", d->kv_len);
+  if (d->kv_len < 1 || d->kv_len > seq_v) RSA_FAIL(RSA_ERR_ARG, "kv_len=%d out of [1, %d]", d->kv_len, seq_v);
   if (d->kv_zero_from < 0) RSA_FAIL(RSA_ERR_ARG, "kv_zero_from < 0");
   if (d->text_end_block < d->nq_blocks || d->text_end_block > nb) RSA_FAIL(RSA_ERR_ARG, "text_end_block out of range");
   if (d->top_k < 0 || d->first_frame_blocks < 0) RSA_FAIL(RSA_ERR_ARG, "top_k / first_frame_blocks negative");
   if (!(d->p_remain >= 0.f)) RSA_FAIL(RSA_ERR_ARG, "p_remain must be >= 0");
   if (d->text_q_valid < 0 ||
-      (d->family == RSA_FAMILY_JOINT && d->text_q_valid > d->seq - d->nq_blocks * RSA_BLOCK))
+      (d->family == RSA_FAMILY_JOINT && d->text_q_valid > d->seq - rm.vis_len))
     RSA_FAIL(RSA_ERR_ARG, "text_q_valid out of range");
   if ((d->nbr_rows > 0) != (d->nbr_cols > 0) || (d->nbr_rows > 0 && !d->nbr)) RSA_FAIL(RSA_ERR_ARG, "neighbour matrix inconsistent");
   const int64_t* st[4] = {d->q_stride, d->k_stride, d->v_stride, d->o_stride};
@@ -124,8 +131,12 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->seq_q = d->seq;
   a->seq_kv = d->seq;
   a->kv_len = d->kv_len;
+  const RowMap rm = row_map(d);
+  a->vis_len = rm.vis_len;
+  a->nq_vis = rm.nq_vis;
+  a->gap = rm.gap;
   a->q_valid = d->family == RSA_FAMILY_JOINT ? d->nq_blocks * RSA_BLOCK + d->text_q_valid : d->seq;
-  if (a->q_valid > d->seq) a->q_valid = d->seq;
+  if (a->q_valid > d->seq + rm.gap) a->q_valid = d->seq + rm.gap;
   a->nqt = L.nqt;
   a->nb = L.nb;
   a->kept_idx = (const uint16_t*)(ws + L.off_kidx);
@@ -416,6 +427,9 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   a.seq_kv = seq_kv;
   a.kv_len = kv_len;
   a.q_valid = seq_q;
+  a.vis_len = 1 << 30;  // no text segment: every block is "visual", nothing is shifted
+  a.nq_vis = 1 << 20;
+  a.gap = 0;
   a.nqt = n_q_blocks;
   a.nb = n_kv_blocks;
   a.kept_idx = kidx;

@@ -33,6 +33,29 @@ struct WsLayout {
       off_mask, off_kidx, off_kcnt, off_nneed, off_R, off_C, off_sched, off_pshared, total;
 };
 
+// Padded ("virtual") layout <-> memory rows.  Visual token t sits at row t in both; the last visual block is completed
+// with `gap` zero rows that exist nowhere in memory; text token i is memory row vis_len + i and padded row
+// nq_vis*128 + i.  WAN: everything is visual, gap = 0.
+struct RowMap {
+  int vis_len;  // visual tokens in memory
+  int nq_vis;   // visual blocks = ceil(vis_len / 128)
+  int gap;      // nq_vis*128 - vis_len for JOINT (0 when aligned); 0 for WAN (its ragged tail is the end of the tensor)
+};
+inline RowMap row_map(const rsa_attn_desc* d) {
+  RowMap m;
+  if (d->family == RSA_FAMILY_JOINT) {
+    m.vis_len = d->vis_len > 0 ? d->vis_len : d->nq_blocks * RSA_BLOCK;
+    if (m.vis_len > d->seq) m.vis_len = d->seq;
+    m.nq_vis = (m.vis_len + RSA_BLOCK - 1) / RSA_BLOCK;
+    m.gap = m.nq_vis * RSA_BLOCK - m.vis_len;
+  } else {
+    m.vis_len = d->seq;
+    m.nq_vis = (d->seq + RSA_BLOCK - 1) / RSA_BLOCK;
+    m.gap = 0;
+  }
+  return m;
+}
+
 int validate_desc(const rsa_attn_desc* d);
 WsLayout make_layout(const rsa_attn_desc* d);
 int check_ws(const rsa_attn_desc* d, const void* ws, size_t bytes, WsLayout* out);
@@ -54,6 +77,8 @@ struct AttnArgs {
   int seq_kv;               // key rows that exist in memory
   int kv_len;               // keys >= kv_len masked to -inf
   int q_valid;              // query rows >= q_valid are written as zeros
+  int vis_len, nq_vis, gap; // RowMap: blocks/tiles < nq_vis read memory rows [128 i, ..) bounded by vis_len, the others
+                            // read memory rows vis_len + 128 (i - nq_vis); kv_len and q_valid are PADDED-layout rows
   int nqt;                  // query tiles per head
   int nb;                   // kv blocks per head (row length of kept_idx)
   const uint16_t* kept_idx; // [bh, nqt, nb]

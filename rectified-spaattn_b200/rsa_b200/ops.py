@@ -230,6 +230,7 @@ def _fill_desc(desc, shape, strides, geo, top_k, p_remain, nbr_dev, debug_dump_p
     desc.text_end_block, desc.text_q_valid = geo.text_end_block, geo.text_q_valid
     desc.top_k, desc.p_remain = int(top_k), float(p_remain)
     desc.first_frame_blocks = geo.first_frame_blocks
+    desc.vis_len = geo.vis_len
     if nbr_dev is not None:
         desc.nbr_rows, desc.nbr_cols = nbr_dev.shape
         desc.nbr = nbr_dev.data_ptr()

@@ -101,6 +101,7 @@ def _desc(geo, b=1, h=2, top_k=2, p=0.3):
     d.family, d.n_blocks, d.nq_blocks, d.text_keys = geo.family, geo.n_blocks, geo.nq_blocks, geo.text_keys
     d.kv_len, d.kv_zero_from, d.text_end_block = geo.kv_len, geo.kv_zero_from, geo.text_end_block
     d.text_q_valid, d.top_k, d.p_remain, d.first_frame_blocks = geo.text_q_valid, top_k, p, geo.first_frame_blocks
+    d.vis_len = geo.vis_len
     return d
 
 
@@ -125,13 +126,23 @@ def test_product_geometry_matches_oracle():
     pairs = [(G.wan(32760, 12), O.geometry_wan(32760, 64, 0.3, 12)),
              (G.hunyuan(115456, 115400), O.geometry_hunyuan(115456, 115400, 179, 0.3)),
              (G.flux(66048, 512), O.geometry_flux(66048, 512, 51, 0.3)),
-             (G.cogvideo(42466, 226), O.geometry_cogvideo(42466, 226, 49, 0.3))]
+             (G.cogvideo(42466, 226), O.geometry_cogvideo(42466, 226, 49, 0.3)),
+             # HunyuanVideo 129 frames: 118 800 visual tokens = 928 blocks + 16 -> 929 visual blocks, 112 pad rows
+             (G.hunyuan(119056, 119000), O.geometry_hunyuan(119056, 119000, 185, 0.3))]
     for g, o in pairs:
         assert (g.n_blocks, g.nq_blocks, g.text_keys, g.kv_len, g.kv_zero_from, g.text_end_block, g.text_q_valid,
                 g.first_frame_blocks) == (o.n_blocks, o.nq_blocks, o.text_keys, o.kv_len, o.kv_zero_from,
                                           o.text_end_block, o.text_q_valid, o.first_frame_blocks)
-    with pytest.raises(RuntimeError):
-        G.hunyuan(119056, 119000)     # the reference raises on a ragged Hunyuan sequence too
+        assert g.gap == o.gap
+    g = G.hunyuan(119056, 119000)
+    assert (g.n_blocks, g.nq_blocks, g.vis_len, g.gap, g.kv_len) == (931, 929, 118800, 112, 119112)
+    lib = N.lib()
+    d = _desc(g)
+    assert lib.rsa_attn_workspace_bytes(C.byref(d)) > 0, lib.rsa_last_error_string()
+    d.vis_len = 118801                 # nq_blocks no longer equals ceil(vis_len/128)? (still 929) -> n_blocks stays valid
+    assert lib.rsa_attn_workspace_bytes(C.byref(d)) > 0
+    d.vis_len = 118912 + 1             # 930 visual blocks: inconsistent with nq_blocks = 929
+    assert lib.rsa_attn_workspace_bytes(C.byref(d)) == 0
 
 
 def test_hot_path_refuses_cpu_tensors():

@@ -76,8 +76,8 @@ def test_pool_scores_gapr_bit_exact(dev, name):
     geo = case["ogeo"]
     nq, nv = geo.nq_blocks, geo.nq_blocks * 128
     for hi in range(case["heads"]):
-        q, k, v = case["q"][0, hi], case["k"][0, hi], case["v"][0, hi]
-        qp, dq = O.pool_stats(q, geo.seq, nq)
+        q, k, v = O.padded_inputs(case["q"][0, hi], case["k"][0, hi], case["v"][0, hi], geo)
+        qp, dq = O.pool_stats(q, geo.seq + geo.gap, nq)
         kp, dk = O.pool_stats(k, geo.kv_zero_from, nq)
         vp, _ = O.pool_stats(v, geo.kv_zero_from, geo.n_blocks, want_mad=False)
         assert np.array_equal(vw["q_pool"][hi].cpu().numpy(), qp)
@@ -166,6 +166,8 @@ def test_masked_attention_random_mask(dev, impl):
 def test_end_to_end_vs_oracle(dev, name, impl):
     from rsa_b200 import ops
     case = load_case(name)
+    if impl == 1 and case["ogeo"].gap:
+        pytest.skip("the mma.sync cross-check kernel handles block-aligned visual segments only")
     ops.set_attention_impl(impl)
     try:
         plan = _plan(case, dev, dump=False)
@@ -178,7 +180,41 @@ def test_end_to_end_vs_oracle(dev, name, impl):
     assert cos_sim(out, ref) >= COS_OUT
 
 
-@pytest.mark.parametrize("name", ["wan_c1", "hunyuan_mid", "cog_small"])
+@pytest.mark.parametrize("name", [n for n in C.CASES if n not in C.REFERENCE_NEEDS_PADDED_LAYOUT])
+def test_against_unmodified_reference_on_b200(dev, name, gold_dir):
+    """tests/golden/golden_gpu_<case>.npz: output and block mask of the UNMODIFIED reference (bf16 mask arithmetic,
+    Triton JIT kernel, flash-attn text rows) run on a B200 by oracle/ref_on_gpu.py.  The reference's bf16 mask differs
+    from the fp32 one on near-tie entries by construction (iid inputs, whose pooled scores are almost
+    uniform, are the worst case: 93 %), so: the masks must agree on >= 90 % of the entries, and on query blocks whose mask row agrees the outputs must meet the north-star tolerance."""
+    import os
+    case = load_case(name)
+    g = np.load(os.path.join(gold_dir, f"golden_gpu_{name}.npz"))
+    mask_ref = np.unpackbits(g["mask"])[: int(np.prod(g["mask_shape"]))].reshape(g["mask_shape"]).astype(bool)
+    plan = _plan(case, dev, dump=False)
+    out = plan.run().float().cpu().numpy()[0]                         # [S, H, D]
+    ref = g["out"].astype(np.float32).reshape(out.shape)
+    geo = case["ogeo"]
+    nq = geo.nq_blocks
+    mask = plan.dense_mask().cpu().numpy()[:, :nq]
+    agree = (mask == mask_ref)
+    assert agree.mean() >= 0.90, f"{name}: mask agreement {agree.mean():.4f}"
+    rows_ok = agree.all(axis=2)                                       # [H, NQ]
+    assert rows_ok.mean() >= 0.5, f"{name}: only {rows_ok.mean():.2f} of the query blocks comparable"
+    rows = min(nq * 128, geo.seq)
+    keep = np.repeat(rows_ok, 128, axis=1)[:, :rows].T                # [rows, H]
+    d = np.abs(out[:rows] - ref[:rows])[keep]
+    # Measured (tools/ref_gpu_golden_stats.py): six cases max <= 1.2e-2; flux_small / hunyuan_mid have isolated blocks
+    # at 4.7e-2 / 3.1e-2 where the reference's bf16 GAPR test or bf16 R, C differ from fp32 -- the fp32 oracle shows
+    # the same distance to the reference there (4.6e-2 / 3.0e-2), i.e. it is the reference's rounding, not this kernel.
+    assert np.mean(d <= ATOL_OUT) >= 0.999, f"{name}: {np.mean(d <= ATOL_OUT):.5f} of the elements within {ATOL_OUT}"
+    assert d.max() <= 6e-2, f"{name}: max-abs-err {d.max()}"
+    assert cos_sim(out[:rows][keep], ref[:rows][keep]) >= COS_OUT
+    t0, nt = nq * 128, geo.text_q_valid                               # text rows: dense in both implementations
+    if nt:
+        assert np.abs(out[t0: t0 + nt] - ref[t0: t0 + nt]).max() <= ATOL_OUT
+
+
+@pytest.mark.parametrize("name", ["wan_c1", "hunyuan_mid", "cog_small", "hunyuan_ragged"])
 def test_pair_schedule_is_a_permutation_with_common_prefix(dev, name):
     """Kernel 4 walks each kept list as [blocks the tile pair (2p, 2p+1) has in common] + [the rest]; the order of
     blocks does not change the attention result, the common prefix lets one K/V tile serve both tiles."""

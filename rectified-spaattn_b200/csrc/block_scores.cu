@@ -10,7 +10,9 @@
 // operands (55 MB of pooled statistics) are L2-resident.
 //
 // CTA tile 64 (query blocks) x 64 (key entries), 256 threads, 4x4 micro-tile per thread, d staged through
-// shared memory in chunks of 32 with a [d][row] layout so the inner loop is 4 LDS.128 per 48 FMA.
+// shared memory in chunks of 32 with a [d][row] layout so the inner loop is 4 LDS.128 per 48 FMA.  The FMAs are
+// issued as packed fma.rn.f32x2 (two key columns per instruction; each half is an ordinary IEEE fmaf, so the
+// per-element chain and its rounding are unchanged) -- the scalar FFMA issues at half rate on sm_100.
 #include "rsa_common.cuh"
 
 namespace rsa {
@@ -60,11 +62,11 @@ __global__ void __launch_bounds__(kThreads) block_scores_kernel(const ScoreArgs 
   const int rows_j = a.nkc - j0;
   const int rows_jg = a.nq - j0;  // columns that have deviation statistics
 
-  float A[4][4], E1[4][4], E2[4][4];
+  float2 A2[4][2], E12[4][2], E22[4][2];  // [query row u][key-column pair w] = columns (2w, 2w+1)
 #pragma unroll
   for (int u = 0; u < 4; ++u)
 #pragma unroll
-    for (int v = 0; v < 4; ++v) A[u][v] = E1[u][v] = E2[u][v] = 0.f;
+    for (int w = 0; w < 2; ++w) A2[u][w] = E12[u][w] = E22[u][w] = make_float2(0.f, 0.f);
 
   for (int dc = 0; dc < 128; dc += DK) {
     __syncthreads();
@@ -83,15 +85,18 @@ __global__ void __launch_bounds__(kThreads) block_scores_kernel(const ScoreArgs 
         const float4 k4 = *reinterpret_cast<const float4*>(&s_kp[d][4 * tx]);
         const float4 h4 = *reinterpret_cast<const float4*>(&s_dk[d][4 * tx]);
         const float q[4] = {q4.x, q4.y, q4.z, q4.w}, g[4] = {g4.x, g4.y, g4.z, g4.w};
-        const float k[4] = {k4.x, k4.y, k4.z, k4.w}, hh[4] = {h4.x, h4.y, h4.z, h4.w};
+        const float2 k2[2] = {make_float2(k4.x, k4.y), make_float2(k4.z, k4.w)};
+        const float2 h2[2] = {make_float2(h4.x, h4.y), make_float2(h4.z, h4.w)};
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u) {
+          const float2 qq = make_float2(q[u], q[u]), gg = make_float2(g[u], g[u]);
 #pragma unroll
-          for (int v = 0; v < 4; ++v) {
-            A[u][v] = __fmaf_rn(q[u], k[v], A[u][v]);
-            E1[u][v] = __fmaf_rn(g[u], k[v], E1[u][v]);
-            E2[u][v] = __fmaf_rn(q[u], hh[v], E2[u][v]);
+          for (int w = 0; w < 2; ++w) {
+            A2[u][w] = __ffma2_rn(qq, k2[w], A2[u][w]);
+            E12[u][w] = __ffma2_rn(gg, k2[w], E12[u][w]);
+            E22[u][w] = __ffma2_rn(qq, h2[w], E22[u][w]);
           }
+        }
       }
     } else {
 #pragma unroll 8
@@ -99,15 +104,26 @@ __global__ void __launch_bounds__(kThreads) block_scores_kernel(const ScoreArgs 
         const float4 q4 = *reinterpret_cast<const float4*>(&s_qp[d][4 * ty]);
         const float4 k4 = *reinterpret_cast<const float4*>(&s_kp[d][4 * tx]);
         const float q[4] = {q4.x, q4.y, q4.z, q4.w};
-        const float k[4] = {k4.x, k4.y, k4.z, k4.w};
+        const float2 k2[2] = {make_float2(k4.x, k4.y), make_float2(k4.z, k4.w)};
 #pragma unroll
-        for (int u = 0; u < 4; ++u)
+        for (int u = 0; u < 4; ++u) {
+          const float2 qq = make_float2(q[u], q[u]);
 #pragma unroll
-          for (int v = 0; v < 4; ++v) A[u][v] = __fmaf_rn(q[u], k[v], A[u][v]);
+          for (int w = 0; w < 2; ++w) A2[u][w] = __ffma2_rn(qq, k2[w], A2[u][w]);
+        }
       }
     }
   }
 
+  float A[4][4], E1[4][4], E2[4][4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u)
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      A[u][2 * w] = A2[u][w].x, A[u][2 * w + 1] = A2[u][w].y;
+      E1[u][2 * w] = E12[u][w].x, E1[u][2 * w + 1] = E12[u][w].y;
+      E2[u][2 * w] = E22[u][w].x, E2[u][2 * w + 1] = E22[u][w].y;
+    }
 #pragma unroll
   for (int u = 0; u < 4; ++u) {
     const int i = i0 + 4 * ty + u;

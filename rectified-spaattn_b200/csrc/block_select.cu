@@ -121,9 +121,73 @@ __device__ void emit_list(const uint32_t* s_mask, int words, int limit, uint16_t
   }
 }
 
+// Descending bitonic sort of n_sort = kThreads * EPT probabilities, as their bit patterns (p >= +0, so unsigned
+// integer order = float order; one min/max instruction per compare).  Only the sorted VALUES are needed: the
+// cumulative sum runs over them, and the selected set is recovered from the value of the n-th entry (see the kernel).
+// Thread t holds elements [EPT*t, EPT*t + EPT) in registers: partners at distance j < EPT are in the same thread, at
+// distance j < 32*EPT in the same warp (shuffle), and only the few stages with j >= 32*EPT go through shared memory
+// (6 of the 55 stages for 1024 entries).  K and J are template parameters so every x[] index is a compile-time
+// constant and the values stay in registers.
+template <int EPT, int K, int J>
+__device__ __forceinline__ void sort_steps(uint32_t (&x)[EPT], uint32_t* s_val, int tid) {
+  if constexpr (J >= 32 * EPT) {
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) s_val[r * kThreads + tid] = x[r];  // [r][tid]: conflict-free
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+      const int e = tid * EPT + r;
+      const int pt = tid ^ (J / EPT);  // partner element e ^ J = (pt, r)
+      const uint32_t y = s_val[r * kThreads + pt];
+      const bool take_max = ((e & K) == 0) != ((e & J) != 0);
+      x[r] = take_max ? max(x[r], y) : min(x[r], y);
+    }
+  } else if constexpr (J >= EPT) {
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+      const int e = tid * EPT + r;
+      const uint32_t y = __shfl_xor_sync(0xffffffffu, x[r], J / EPT);
+      const bool take_max = ((e & K) == 0) != ((e & J) != 0);
+      x[r] = take_max ? max(x[r], y) : min(x[r], y);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+      if ((r & J) == 0) {  // r is the lower element of the pair (r, r | J)
+        const int e = tid * EPT + r;
+        const bool desc = (e & K) == 0;
+        const uint32_t hi = max(x[r], x[r | J]), lo = min(x[r], x[r | J]);
+        x[r] = desc ? hi : lo;
+        x[r | J] = desc ? lo : hi;
+      }
+    }
+  }
+  if constexpr (J > 1) sort_steps<EPT, K, J / 2>(x, s_val, tid);
+  else if constexpr (K < kThreads * EPT) sort_steps<EPT, 2 * K, K>(x, s_val, tid);
+}
+
+// s_p[0..n_ent) -> s_val[0..kThreads*EPT) sorted descending (entries >= n_ent count as +0)
+template <int EPT>
+__device__ void sort_desc(const float* s_p, int n_ent, uint32_t* s_val, int tid) {
+  uint32_t x[EPT];
+#pragma unroll
+  for (int r = 0; r < EPT; ++r) {
+    const int e = tid * EPT + r;
+    x[r] = e < n_ent ? __float_as_uint(s_p[e]) : 0u;
+  }
+  sort_steps<EPT, 2, 1>(x, s_val, tid);
+  __syncthreads();
+#pragma unroll
+  for (int r = 0; r < EPT; ++r) s_val[tid * EPT + r] = x[r];
+  __syncthreads();
+}
+
 __global__ void __launch_bounds__(kThreads) block_select_kernel(const SelectArgs a) {
   __shared__ float s_p[kMaxEnt + 1];
-  __shared__ unsigned long long s_key[kMaxEnt];
+  __shared__ uint32_t s_val[kMaxEnt];  // sorted probability bit patterns
+  __shared__ uint32_t s_thr;           // bit pattern of the n-th largest probability
+  __shared__ int s_ties_needed, s_ties_total;
   __shared__ uint32_t s_mask[kMaxWords];
   __shared__ int s_scan[kMaxWords];
   __shared__ float s_red[kThreads / 32];
@@ -189,53 +253,78 @@ __global__ void __launch_bounds__(kThreads) block_select_kernel(const SelectArgs
     for (int j = tid; j < n_ent; j += kThreads) prow[j] = s_p[j];
   }
 
-  // ---- sort entries by (probability desc, index asc): bitonic network on 64-bit keys
-  int n_sort = 2;
+  // ---- sort the probabilities (descending); ties are resolved below by index, ascending
+  int n_sort = kThreads;
   while (n_sort < n_ent) n_sort <<= 1;
-  for (int j = tid; j < n_sort; j += kThreads) {
-    unsigned long long key = 0ull;
-    if (j < n_ent) key = ((unsigned long long)__float_as_uint(s_p[j]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)j);
-    s_key[j] = key;
-  }
-  __syncthreads();
-  for (int k = 2; k <= n_sort; k <<= 1) {
-    for (int j = k >> 1; j > 0; j >>= 1) {
-      for (int t = tid; t < (n_sort >> 1); t += kThreads) {
-        const int lo = ((t & ~(j - 1)) << 1) | (t & (j - 1));
-        const int hi = lo | j;
-        const unsigned long long x = s_key[lo], y = s_key[hi];
-        const bool desc = (lo & k) == 0;
-        if (desc ? (x < y) : (x > y)) {
-          s_key[lo] = y;
-          s_key[hi] = x;
-        }
-      }
-      __syncthreads();
-    }
-  }
+  if (n_sort == kThreads) sort_desc<1>(s_p, n_ent, s_val, tid);
+  else if (n_sort == 2 * kThreads) sort_desc<2>(s_p, n_ent, s_val, tid);
+  else if (n_sort == 4 * kThreads) sort_desc<4>(s_p, n_ent, s_val, tid);
+  else sort_desc<8>(s_p, n_ent, s_val, tid);
 
   // ---- sequential fp32 cumulative sum over the sorted probabilities (wan21 :221-229)
   if (tid == 0) {
+    // probabilities are >= 0, so c never decreases: count in chunks of 8 (independent loads, one dependent add
+    // chain) and stop after the first chunk that crosses the threshold
     float c = 0.f;
     int cnt = 0;
-    for (int k = 0; k < n_ent; ++k) {
-      c = __fadd_rn(c, __uint_as_float((uint32_t)(s_key[k] >> 32)));
-      if (c <= a.p_remain) ++cnt; else break;
+    for (int k0 = 0; k0 < n_ent; k0 += 8) {
+      float pk[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) pk[u] = k0 + u < n_ent ? __uint_as_float(s_val[k0 + u]) : INFINITY;
+      int ok = 0;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        c = __fadd_rn(c, pk[u]);
+        ok += (c <= a.p_remain) ? 1 : 0;
+      }
+      cnt += ok;
+      if (ok < 8) break;
     }
     int n = cnt + 1;
     if (n < a.top_k) n = a.top_k;
     if (n > n_ent) n = n_ent;
     s_n = n;
     a.n_needed[(int64_t)bh * nq + i] = n;
+    // The n selected entries in (probability desc, index asc) order are: every entry above the n-th value, plus the
+    // first `ties_needed` entries (by index) equal to it.
+    uint32_t thr = 0u;
+    int above = 0;
+    if (n > 0) {
+      thr = s_val[n - 1];
+      above = n - 1;
+      while (above > 0 && s_val[above - 1] == thr) --above;
+    }
+    s_thr = thr;
+    s_ties_needed = n - above;
+    s_ties_total = 0;
   }
   for (int w = tid; w < words; w += kThreads) s_mask[w] = 0u;
   __syncthreads();
   const int n = s_n;
+  const uint32_t thr = s_thr;
 
   // ---- scatter the n best entries, then the constant unions
-  for (int k = tid; k < n; k += kThreads) {
-    const uint32_t j = 0xffffffffu - (uint32_t)(s_key[k] & 0xffffffffull);
-    atomicOr(&s_mask[j >> 5], 1u << (j & 31));
+  if (n > 0) {
+    int my_ties = 0;
+    for (int j = tid; j < n_ent; j += kThreads) {
+      const uint32_t v = __float_as_uint(s_p[j]);
+      if (v > thr) atomicOr(&s_mask[j >> 5], 1u << (j & 31));
+      my_ties += v == thr ? 1 : 0;
+    }
+    if (my_ties) atomicAdd(&s_ties_total, my_ties);
+    __syncthreads();
+    if (s_ties_total == s_ties_needed) {  // the usual case: one entry holds the n-th value
+      for (int j = tid; j < n_ent; j += kThreads)
+        if (__float_as_uint(s_p[j]) == thr) atomicOr(&s_mask[j >> 5], 1u << (j & 31));
+    } else if (tid == 0) {                // several equal probabilities straddle the cut: lowest indices first
+      int left = s_ties_needed;
+      for (int j = 0; j < n_ent && left > 0; ++j)
+        if (__float_as_uint(s_p[j]) == thr) {
+          s_mask[j >> 5] |= 1u << (j & 31);
+          --left;
+        }
+    }
+    __syncthreads();
   }
   if (a.nbr != nullptr && i < a.nbr_rows) {
     const int cols = a.nbr_cols < nq ? a.nbr_cols : nq;

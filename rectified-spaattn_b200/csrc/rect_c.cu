@@ -19,11 +19,9 @@ __global__ void __launch_bounds__(kThreads) rect_c_kernel(const float* __restric
   __shared__ __align__(16) float s_v[TK][128];
   const int bh = blockIdx.y, i0 = blockIdx.x * TM;
   const int tid = threadIdx.x, tx = tid & 31, ty = tid >> 5;
-  float acc[4][4];
+  float2 acc[4][2];  // packed fma.rn.f32x2: channels (4 tx, 4 tx + 1) and (4 tx + 2, 4 tx + 3)
 #pragma unroll
-  for (int u = 0; u < 4; ++u)
-#pragma unroll
-    for (int v = 0; v < 4; ++v) acc[u][v] = 0.f;
+  for (int u = 0; u < 4; ++u) acc[u][0] = acc[u][1] = make_float2(0.f, 0.f);
   const float* wb = w + ((int64_t)bh * nq + i0) * ent_ld;
   const float* vb = vp + (int64_t)bh * nb * 128;
   for (int j0 = 0; j0 < n_ent; j0 += TK) {
@@ -49,10 +47,9 @@ __global__ void __launch_bounds__(kThreads) rect_c_kernel(const float* __restric
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         const float wv = s_w[4 * ty + u][j];
-        acc[u][0] = fmaf(wv, v4.x, acc[u][0]);
-        acc[u][1] = fmaf(wv, v4.y, acc[u][1]);
-        acc[u][2] = fmaf(wv, v4.z, acc[u][2]);
-        acc[u][3] = fmaf(wv, v4.w, acc[u][3]);
+        const float2 ww = make_float2(wv, wv);
+        acc[u][0] = __ffma2_rn(ww, make_float2(v4.x, v4.y), acc[u][0]);
+        acc[u][1] = __ffma2_rn(ww, make_float2(v4.z, v4.w), acc[u][1]);
       }
     }
   }
@@ -61,7 +58,7 @@ __global__ void __launch_bounds__(kThreads) rect_c_kernel(const float* __restric
     const int i = i0 + 4 * ty + u;
     if (i < nq)
       *reinterpret_cast<float4*>(c + ((int64_t)bh * nqt + i) * 128 + 4 * tx) =
-          make_float4(acc[u][0], acc[u][1], acc[u][2], acc[u][3]);
+          make_float4(acc[u][0].x, acc[u][0].y, acc[u][1].x, acc[u][1].y);
   }
 }
 

@@ -349,3 +349,33 @@ def test_entry_point_accepts_pinned_host_tensors(dev):
     assert got.is_pinned() and torch.equal(got.view(torch.int16), want.view(torch.int16))
     with pytest.raises(RuntimeError):
         hun.rectified_block_sparse_attention(q, k, v, **kw)
+
+
+def test_selection_ties_take_lowest_indices(dev):
+    """Equal probabilities straddling the cut: the kernel sorts values only and recovers the selected set from the
+    n-th value, taking tied entries in ascending index order -- the oracle's stable sort.  Keys are one block repeated
+    (all columns tie) or two alternating blocks (two tie groups)."""
+    from rsa_b200 import geometry as G
+    from rsa_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    nblk = 12
+    for period, top_k, p in ((1, 1, 0.3), (2, 1, 0.55), (3, 5, 0.1), (1, 1, 0.999)):
+        q = torch.randn(1, 2, nblk * 128, 128, generator=g)
+        kb = torch.randn(1, 2, period, 128, 128, generator=g)
+        k = kb.repeat(1, 1, nblk // period, 1, 1).reshape(1, 2, nblk * 128, 128)
+        v = torch.randn(1, 2, nblk * 128, 128, generator=g)
+        q, k, v = (t.to(torch.bfloat16).to(dev) for t in (q, k, v))
+        plan = ops.Plan(q, k, v, G.wan(nblk * 128), top_k, p, None, debug_dump_probs=True)
+        plan.pool_stats()
+        plan.block_scores()
+        plan.block_select()
+        torch.cuda.synchronize()
+        vw = plan.view()
+        geo = O.geometry_wan(nblk * 128, top_k, p, 0)
+        mask = plan.dense_mask().cpu().numpy()
+        for hi in range(2):
+            pg = vw["probs"][hi].cpu().numpy()
+            assert len(np.unique(pg[0])) <= period          # the columns really tie
+            m, n = O.select_blocks(pg, geo, None)
+            assert np.array_equal(vw["n_needed"][hi].cpu().numpy(), n)
+            assert np.array_equal(mask[hi], m)

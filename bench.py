@@ -98,8 +98,9 @@ def ncu_traffic(workload):
     if not os.path.exists(p):
         return None
     k = json.load(open(p))["kernels"].get("attn_tc5_kernel", {})
-    rd, wr = k.get("dram__bytes_read.sum [Gbyte]"), k.get("dram__bytes_write.sum [Mbyte]")
-    return None if rd is None or wr is None else rd * 1e9 + wr * 1e6
+    rd = next((v * (1e9 if "Gbyte" in m else 1e6) for m, v in k.items() if m.startswith("dram__bytes_read.sum")), None)
+    wr = next((v * (1e9 if "Gbyte" in m else 1e6) for m, v in k.items() if m.startswith("dram__bytes_write.sum")), None)
+    return None if rd is None or wr is None else rd + wr
 
 
 def measured_peaks():
@@ -171,8 +172,9 @@ def cpu_sample(wp, regime, budget_s=12.0, threads=None):
     from oracle import rsa_oracle as O
     from rsa_b200 import ops as host_ops  # only the pure-CPU geometry helper (no GPU, no kernels)
 
-    if threads:
-        torch.set_num_threads(threads)
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would silently make this
+    # a single-thread baseline)
+    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
     cores = torch.get_num_threads()
     s = wp["s"]
     q, k, v = O.synth_qkv(1, s, 128, regime, 0)
@@ -226,11 +228,12 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="c3a", choices=list(WORKLOADS))
+    ap.add_argument("--workload", default="c3b", choices=list(WORKLOADS))
     ap.add_argument("--regime", default="walk", choices=["walk", "iid", "cluster"])
     ap.add_argument("--attn-impl", type=int, default=0, help="0 = tcgen05 kernel (product); 1 = mma.sync cross-check")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-permute", action="store_true")
     ap.add_argument("--host-chunk", type=int, default=2, help="heads per chunk of the pipelined host-buffer call")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -325,6 +328,37 @@ def main():
                      ("block_select", plan.block_select), ("rect_c", plan.rect_c),
                      ("sparse_attention", plan.sparse_attention)):
         stages[name] = timed(fn, max(3, args.steps))
+    # kernel 1 (per transformer forward, not per attention call): Gilbert permute of the hidden states [1, Nv, 3072]
+    hbm_kernels = None
+    if rank == 0 and not args.no_permute:
+        peaks_ = measured_peaks()
+        l2h, h2l = ops.gilbert_mapping(t, h, w)
+        chans = 3072 if wp["fam"] != "wan" else (1536 if wp["heads"] == 12 else 5120)
+        x = torch.randn(1, wp["nv"], chans, device=dev).to(torch.bfloat16)
+        xo = torch.empty_like(x)
+        idx = h2l.to(dev)
+        ms_perm = timed(lambda: ops.permute_rows(x, idx, out=xo), max(5, args.steps)) if world == 1 else None
+        if world > 1:   # timed() holds collectives; outside rank 0 nobody joins them, so time locally
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for _ in range(3):
+                ops.permute_rows(x, idx, out=xo)
+            e0.record()
+            for _ in range(10):
+                ops.permute_rows(x, idx, out=xo)
+            e1.record()
+            torch.cuda.synchronize()
+            ms_perm = e0.elapsed_time(e1) / 10
+        b_perm = 2 * x.numel() * 2
+        b_pool = 3 * q.numel() * 2
+        hbm_kernels = [
+            {"kernel": "permute_rows (kernel 1)", "algorithmic_bytes": b_perm, "ms": ms_perm,
+             "achieved_gbs": b_perm / (ms_perm * 1e-3) / 1e9, "peak_gbs": peaks_["hbm"],
+             "frac": b_perm / (ms_perm * 1e-3) / 1e9 / peaks_["hbm"], "shape": [1, wp["nv"], chans]},
+            {"kernel": "pool_stats (kernel 2)", "algorithmic_bytes": b_pool, "ms": stages["pool_stats"],
+             "achieved_gbs": b_pool / (stages["pool_stats"] * 1e-3) / 1e9, "peak_gbs": peaks_["hbm"],
+             "frac": b_pool / (stages["pool_stats"] * 1e-3) / 1e9 / peaks_["hbm"]}]
+        del x, xo
     clocks = sampler.summary() if rank == 0 else None
     vw = plan.view()
     pairs = int(vw["kept_cnt"].sum().item())
@@ -404,6 +438,8 @@ def main():
                          "traffic_note": "DRAM read+write bytes of one launch, ncu --set full, profiles/r01_ncu_summary_*.json"},
             "clocks": clocks,
         }
+        if hbm_kernels:
+            line["hbm_kernels"] = hbm_kernels
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:

@@ -43,7 +43,7 @@ __device__ __forceinline__ void stage(float (*dst)[TI], const float* src, int ro
   }
 }
 
-__global__ void __launch_bounds__(kThreads) block_scores_kernel(const ScoreArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) block_scores_kernel(const ScoreArgs a) {
   __shared__ __align__(16) float s_qp[DK][TI];
   __shared__ __align__(16) float s_dq[DK][TI];
   __shared__ __align__(16) float s_kp[DK][TJ];
@@ -51,7 +51,11 @@ __global__ void __launch_bounds__(kThreads) block_scores_kernel(const ScoreArgs 
 
   const int bh = blockIdx.z;
   const int i0 = blockIdx.y * TI, j0 = blockIdx.x * TJ;
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  // Warp w covers rows [16 (w >> 1), +16) x columns [32 (w & 1), +32) of the tile; inside it lane = 8 * (row group) +
+  // (column group), so one LDS.128 of a warp touches 4 distinct query quads (broadcast) or 8 consecutive key quads
+  // (128 B): 4 shared-memory wavefronts per d step instead of 6 with a 2 x 16 lane layout.
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tx = 8 * (warp & 1) + (lane & 7), ty = 4 * (warp >> 1) + (lane >> 3);
   const bool need_gapr = j0 < a.nq;  // tiles that only hold text-key columns skip the error products
 
   const float* qp = a.qp + ((int64_t)bh * a.nq + i0) * 128;

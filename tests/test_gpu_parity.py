@@ -379,3 +379,60 @@ def test_selection_ties_take_lowest_indices(dev):
             m, n = O.select_blocks(pg, geo, None)
             assert np.array_equal(vw["n_needed"][hi].cpu().numpy(), n)
             assert np.array_equal(mask[hi], m)
+
+
+# ----------------------------------------------------------------- batch > 1, strided views, CUDA-graph capture
+@pytest.mark.parametrize("name", ["hunyuan_small", "wan_ragged"])
+def test_batch_and_strided_views(dev, name):
+    """B = 2 with the two batch entries swapped heads, passed as NON-contiguous [B, H, S, D] views of a [B, S, H, D]
+    buffer (what `unflatten(2, (heads, -1)).transpose(1, 2)` of a projection output is): each (batch, head) must equal
+    the single-batch contiguous result bit for bit."""
+    from rsa_b200 import ops
+    case = load_case(name)
+    geo = product_geometry(case["fam"], case["nv"], case["s"], case["text_len"], case["ntrue_d"], case["grid"][0])
+    nbr = torch.from_numpy(case["nbr"])
+    q, k, v = (torch.from_numpy(case[n]).to(torch.bfloat16).to(dev) for n in ("q", "k", "v"))   # [1, 2, S, D]
+    want = ops.rectified_attention(q, k, v, geo, case["top_k"], case["p"], nbr, shape_xfuse=True)  # [1, S, 2, D]
+
+    def as_view(x):      # [2, 2, S, D] view over [2, S, 2, D]: batch 1 holds the heads in swapped order
+        both = torch.cat([x, x.flip(1)], dim=0)
+        return both.permute(0, 2, 1, 3).contiguous().permute(0, 2, 1, 3)
+
+    qv, kv, vv = as_view(q), as_view(k), as_view(v)
+    assert not qv.is_contiguous()
+    got = ops.rectified_attention(qv, kv, vv, geo, case["top_k"], case["p"], nbr, shape_xfuse=True)  # [2, S, 2, D]
+    assert torch.equal(got[0].view(torch.int16), want[0].view(torch.int16))
+    assert torch.equal(got[1].flip(1).view(torch.int16), want[0].view(torch.int16))
+
+
+def test_call_is_cuda_graph_capturable(dev):
+    """No allocation, no host synchronisation, tensor maps passed by value: the whole call records into a CUDA graph
+    and replays on new input values (the reference has >= 4 host syncs per call and cannot be captured)."""
+    from rsa_b200 import ops
+    case = load_case("hunyuan_mid")
+    geo = product_geometry(case["fam"], case["nv"], case["s"], case["text_len"], case["ntrue_d"], case["grid"][0])
+    nbr = torch.from_numpy(case["nbr"])
+    q, k, v = (torch.from_numpy(case[n]).to(torch.bfloat16).to(dev) for n in ("q", "k", "v"))
+    plan = ops.Plan(q, k, v, geo, case["top_k"], case["p"], nbr)
+    want = plan.run().clone()
+    torch.cuda.synchronize()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(s):
+        plan.run()                                   # warm-up on the capture stream
+        torch.cuda.synchronize()
+        with torch.cuda.graph(graph, stream=s):
+            plan.run()
+    plan.out.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(plan.out.view(torch.int16), want.view(torch.int16))
+    # new values in the captured input buffers -> the replay computes the new result
+    q2 = torch.from_numpy(load_case("hunyuan_mid")["q"]).flip(1).to(torch.bfloat16).to(dev)
+    q.copy_(q2)
+    graph.replay()
+    torch.cuda.synchronize()
+    want2 = ops.Plan(q2, k, v, geo, case["top_k"], case["p"], nbr).run()
+    torch.cuda.synchronize()
+    assert torch.equal(plan.out.view(torch.int16), want2.view(torch.int16))

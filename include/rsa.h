@@ -163,6 +163,47 @@ int rsa_sparse_attention(const rsa_attn_desc* d, const void* q, const void* k, c
 int rsa_rectified_attention(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Kernel 0: what the reference's processors do between the QKV projections and the attention call,
+ * fused into one pass over the projection outputs: head split, per-head QK RMSNorm, rotary embedding, re-layout
+ * [B, rows, H*128] -> [B, H, S, 128], and (pool != 0) kernel 2's block pooling of the rows just produced, so Q, K, V
+ * are written once and never read back before kernel 4.  Replaces rectified_hunyuan_attn.py:448-479 and the same
+ * sequence in rectified_flux_attn.py:
+ *   query.unflatten(2, (heads, -1)).transpose(1, 2)                                   :448-450
+ *   attn.norm_q / attn.norm_k = diffusers RMSNorm(head_dim, eps, elementwise_affine)   :453-456
+ *       (x * rsqrt(mean(x^2) + eps) in fp32, rounded to bf16, times the bf16 weight, rounded to bf16)
+ *   diffusers apply_rotary_emb(x, (cos, sin), use_real=True, use_real_unbind_dim=-1)   :459-478
+ *       (x * cos + rotate_pairs(x) * sin in fp32, rounded to bf16; only the first rope_rows tokens)
+ * diffusers 0.34.0 (requirements.txt:18) is not vendored in the reference; the two functions are restated from its
+ * published source (oracle/prep_oracle.py).
+ * One call handles the `rows` tokens of ONE source: the latent stream (dst_row = 0) or, for a dual-stream block, the
+ * encoder stream (dst_row = visual token count; rope_rows = 0).  Destination tensors, their strides and the block
+ * geometry come from the attention descriptor the rows are produced for.  With pool != 0 the workspace must be that
+ * descriptor's workspace and every visual / text block must be produced by such calls before
+ * rsa_rectified_attention_pooled runs. */
+typedef struct rsa_prep_desc {
+  int32_t rows;             /* tokens in the source tensors                                                   */
+  int32_t dst_row;          /* memory row of the destination the first source token goes to: 0 or the visual  */
+                            /* token count                                                                    */
+  int64_t src_stride[3][2]; /* q, k, v sources [batch, rows, heads*128]: (batch, token) element strides        */
+  int32_t norm;             /* 0 = none, 1 = RMSNorm over head_dim                                             */
+  float eps;
+  const void* q_weight;     /* DEVICE bf16 [128] (norm_q.weight)                                               */
+  const void* k_weight;     /* DEVICE bf16 [128] (norm_k.weight)                                               */
+  int32_t rope_rows;        /* source tokens [0, rope_rows) are rotated; 0 = no rotary embedding               */
+  int32_t reserved;
+  const float* cos;         /* DEVICE fp32 [rope_rows, 128] (diffusers' repeat-interleaved cos table)          */
+  const float* sin;
+} rsa_prep_desc;
+
+int rsa_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* q_src, const void* k_src,
+                 const void* v_src, void* q, void* k, void* v, int pool, void* workspace, size_t workspace_bytes,
+                 void* stream);
+
+/* Kernels 3a, 3b, 3c, 4 on pooled statistics that rsa_qkv_prep(pool = 1) has left in the workspace. */
+int rsa_rectified_attention_pooled(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
+                                   void* workspace, size_t workspace_bytes, void* stream);
+
 /* The whole call on HOST buffers: query/key/value/out are host pointers (page-locked memory gives the full PCIe rate;
  * pageable memory is correct but serialises), described by the same descriptor (strides = the host tensors').  Heads
  * are independent, so the call is cut into chunks of heads_per_chunk heads and pipelined on three streams: H2D of

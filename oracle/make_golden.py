@@ -237,9 +237,51 @@ def make_kernel_fp16():
     print("kernel_fp16 done", float(o.float().abs().mean()), flush=True)
 
 
+# ------------------------------------------------------------------ pre-attention sequence (kernel 0), bf16 CPU
+def prep_inputs(seed=31, rows=390, heads=2, n_rope=300):
+    """Seeded inputs shared with the tests: projection outputs, norm weights, rotary tables."""
+    g = torch.Generator().manual_seed(seed)
+    src = [torch.randn(1, rows, heads * 128, generator=g).mul(1.5).to(torch.bfloat16) for _ in range(3)]
+    wq = (1 + 0.1 * torch.randn(128, generator=g)).to(torch.bfloat16)
+    wk = (1 + 0.1 * torch.randn(128, generator=g)).to(torch.bfloat16)
+    pos = torch.arange(n_rope, dtype=torch.float32)
+    inv = 1.0 / (256.0 ** (torch.arange(0, 128, 2, dtype=torch.float32) / 128))
+    ang = torch.outer(pos, inv)
+    cos, sin = ang.cos().repeat_interleave(2, dim=1), ang.sin().repeat_interleave(2, dim=1)     # [n_rope, 128]
+    return src, wq, wk, cos, sin, n_rope
+
+
+def torch_prep(x, heads, weight, eps, cos, sin, n_rope):
+    """The literal op sequence of rectified_hunyuan_attn.py:448-479 with diffusers' RMSNorm.forward and
+    apply_rotary_emb(use_real=True, use_real_unbind_dim=-1) written out (diffusers is not installed)."""
+    x = x.unflatten(2, (heads, -1)).transpose(1, 2)
+    if weight is not None:
+        variance = x.to(torch.float32).pow(2).mean(-1, keepdim=True)
+        x = x * torch.rsqrt(variance + eps)
+        x = x.to(weight.dtype) * weight
+    if n_rope:
+        xr = x[:, :, :n_rope]
+        c, s_ = cos[None, None], sin[None, None]
+        x_real, x_imag = xr.reshape(*xr.shape[:-1], -1, 2).unbind(-1)
+        x_rot = torch.stack([-x_imag, x_real], dim=-1).flatten(3)
+        xr = (xr.float() * c + x_rot.float() * s_).to(x.dtype)
+        x = torch.cat([xr, x[:, :, n_rope:]], dim=2)
+    return x
+
+
+def make_prep():
+    src, wq, wk, cos, sin, n_rope = prep_inputs()
+    q = torch_prep(src[0], 2, wq, 1e-6, cos, sin, n_rope)
+    k = torch_prep(src[1], 2, wk, 1e-6, cos, sin, n_rope)
+    v = torch_prep(src[2], 2, None, 1e-6, None, None, 0)
+    np.savez_compressed(os.path.join(GOLD, "prep_hunyuan.npz"), q=q.contiguous().view(torch.int16).numpy(),
+                        k=k.contiguous().view(torch.int16).numpy(), v=v.contiguous().view(torch.int16).numpy())
+    print("prep golden", tuple(q.shape), float(q.float().abs().mean()), flush=True)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    what = sys.argv[1:] or ["gilbert", "masks", "kernel"]
+    what = sys.argv[1:] or ["gilbert", "masks", "kernel", "prep"]
     if "gilbert" in what:
         make_gilbert()
     if "masks" in what:
@@ -248,3 +290,5 @@ if __name__ == "__main__":
                 run_reference_case(n)
     if "kernel" in what:
         make_kernel_fp16()
+    if "prep" in what:
+        make_prep()

@@ -13,12 +13,35 @@
 // Rows >= valid_rows contribute zeros; the divisor is always 128 (the reference zero-pads, wan21 :299-302).
 // Rows are counted in the padded layout (rsa_common.cuh RowMap): a visual block reads memory rows below vis_len and
 // zeros above, a text block reads memory rows shifted down by the gap.
+//
+// The same kernel has a second front end ("prep", kernel 0): instead of loading finished Q/K/V rows it builds them from
+// the projection outputs [B, S, H*128] -- per-head RMSNorm, rotary embedding, re-layout to [B, H, S, 128] -- stores
+// them, and pools the values it has just rounded to bf16, so the pooled statistics are bit-identical to pooling the
+// stored rows and Q, K, V are never read back.  Replaces rectified_hunyuan_attn.py:448-479 (and the same sequence
+// in rectified_flux_attn.py): unflatten/transpose, attn.norm_q / attn.norm_k (diffusers RMSNorm(head_dim, eps):
+// x * rsqrt(mean(x^2) + eps) in fp32 -> bf16 -> * weight -> bf16) and diffusers apply_rotary_emb(use_real=True,
+// use_real_unbind_dim=-1): out = x * cos + rotate_pairs(x) * sin in fp32 (two products and a sum, each rounded) -> bf16.
 #include "rsa_common.cuh"
 
 namespace rsa {
 namespace {
 
 constexpr int kThreads = 256;
+
+struct PrepArgs {
+  const __nv_bfloat16* src[3];  // q, k, v projection outputs [B, rows, H*128]
+  int64_t src_stride[3][2];     // (batch, token) element strides
+  __nv_bfloat16* dst[3];        // [B, H, S, 128] views
+  int64_t dst_stride[3][3];     // (batch, head, token)
+  const __nv_bfloat16* w[2];    // RMSNorm weights of q, k (bf16 [128]) or nullptr
+  float eps;
+  const float *cos, *sin;       // fp32 [rope_rows, 128]
+  int rope_rows;                // source rows below this are rotated
+  int rows;                     // source rows
+  int dst_row0;                 // memory row of source row 0 in the destination
+  int blk0;                     // padded-layout block of source row 0
+  int pool;                     // also pool the produced rows
+};
 
 struct PoolArgs {
   const __nv_bfloat16* x[3];  // q, k, v
@@ -44,14 +67,74 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads) pool_stats_kernel(const PoolArgs a) {
+// Kernel 0 front end: rows of one 128-token block of one head, normalised / rotated / rounded to bf16, stored to the
+// destination and returned in the same register layout the pooling sweep uses.
+__device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, int h, int jblk, int warp, int lane,
+                                          uint4 (&raw)[8]) {
+  const int col = 8 * (lane & 15);
+  const __nv_bfloat16* src = p.src[which] + b * p.src_stride[which][0] + (int64_t)h * 128 + col;
+  __nv_bfloat16* dst = p.dst[which] + b * p.dst_stride[which][0] + h * p.dst_stride[which][1] + col;
+  float wgt[8];
+  const bool normed = which < 2 && p.w[which] != nullptr;
+  if (normed) unpack8(__ldg(reinterpret_cast<const uint4*>(p.w[which] + col)), wgt);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = jblk * 128 + 16 * warp + 2 * it + (lane >> 4);  // source row; the 16 lanes of a half-warp share it
+    const bool live = r < p.rows;
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (live) u = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * p.src_stride[which][1]));
+    if (which < 2) {
+      float f[8];
+      unpack8(u, f);
+      if (normed) {
+        // mean(x^2) over the 128 channels of this head: 8 per lane, then a fixed butterfly over the 16 lanes
+        float ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) ss = __fmaf_rn(f[c], f[c], ss);
+#pragma unroll
+        for (int o = 1; o < 16; o <<= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
+        const float rinv = rsqrtf(__fadd_rn(__fmul_rn(ss, 1.0f / 128.0f), p.eps));
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const float xn = __bfloat162float(__float2bfloat16_rn(__fmul_rn(f[c], rinv)));
+          f[c] = __bfloat162float(__float2bfloat16_rn(__fmul_rn(xn, wgt[c])));
+        }
+      }
+      if (live && r < p.rope_rows) {
+        float cs[8], sn[8];
+        const float4* cp = reinterpret_cast<const float4*>(p.cos + (int64_t)r * 128 + col);
+        const float4* sp = reinterpret_cast<const float4*>(p.sin + (int64_t)r * 128 + col);
+        const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
+        cs[0] = c0.x, cs[1] = c0.y, cs[2] = c0.z, cs[3] = c0.w, cs[4] = c1.x, cs[5] = c1.y, cs[6] = c1.z, cs[7] = c1.w;
+        sn[0] = s0.x, sn[1] = s0.y, sn[2] = s0.z, sn[3] = s0.w, sn[4] = s1.x, sn[5] = s1.y, sn[6] = s1.z, sn[7] = s1.w;
+        float g[8];
+#pragma unroll
+        for (int c = 0; c < 8; c += 2) {  // rotate_pairs(x)[2i] = -x[2i+1], [2i+1] = x[2i]
+          g[c] = __fadd_rn(__fmul_rn(f[c], cs[c]), __fmul_rn(-f[c + 1], sn[c]));
+          g[c + 1] = __fadd_rn(__fmul_rn(f[c + 1], cs[c + 1]), __fmul_rn(f[c], sn[c + 1]));
+        }
+#pragma unroll
+        for (int c = 0; c < 8; ++c) f[c] = g[c];
+      }
+      __nv_bfloat162 o2[4];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o2[c] = __floats2bfloat162_rn(f[2 * c], f[2 * c + 1]);
+      u = *reinterpret_cast<const uint4*>(o2);
+    }
+    if (live) *reinterpret_cast<uint4*>(dst + (int64_t)(p.dst_row0 + r) * p.dst_stride[which][2]) = u;
+    raw[it] = live ? u : make_uint4(0, 0, 0, 0);
+  }
+}
+
+template <bool kPrep>
+__global__ void __launch_bounds__(kThreads) pool_stats_kernel(const PoolArgs a, const PrepArgs p) {
   const int which = blockIdx.z;
   const int bh = blockIdx.y;
-  const int blk = blockIdx.x;
+  const int blk = kPrep ? p.blk0 + (int)blockIdx.x : (int)blockIdx.x;
   const int b = bh / a.heads, h = bh % a.heads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (which == 3) {
+  if (!kPrep && which == 3) {
     // text keys -> fp32 rows [NQ, NQ + a) of k_cat; one 16-lane group per row
     const int rows_per_cta = kThreads / 16;
     const int t = blk * rows_per_cta + (tid >> 4);
@@ -68,25 +151,48 @@ __global__ void __launch_bounds__(kThreads) pool_stats_kernel(const PoolArgs a) 
     }
     return;
   }
-  if (blk >= a.n_blk[which]) return;
-
   __shared__ float s_part[8][128];
   __shared__ float s_mean[128];
 
-  const __nv_bfloat16* base = a.x[which] + b * a.stride[which][0] + h * a.stride[which][1];
-  const int64_t ts = a.stride[which][2];
   const int col = 8 * (lane & 15);
   const int row0 = blk * 128 + 16 * warp + (lane >> 4);
   const bool visual = blk < a.nq_vis;
   const int valid = visual ? min(a.valid_rows[which], a.vis_len) : a.valid_rows[which];
-  const int shift = visual ? 0 : a.gap;  // padded row -> memory row
 
   uint4 raw[8];
+  if constexpr (kPrep) {
+    prep_rows(p, which, b, h, blockIdx.x, warp, lane, raw);
+    if (!p.pool) return;
+    // rows the pooling counts as zeros (K, V rows >= kv_zero_from; hunyuan masked_fill_ :307-308) stay stored as they are
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = row0 + 2 * it;
-    raw[it] = make_uint4(0, 0, 0, 0);
-    if (r < valid) raw[it] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(r - shift) * ts + col));
+    for (int it = 0; it < 8; ++it)
+      if (row0 + 2 * it >= valid) raw[it] = make_uint4(0, 0, 0, 0);
+    if (which == 1 && !visual) {
+      // text keys scored as single tokens: fp32 rows [NQ, NQ + a) of k_cat (hunyuan :193-194)
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int t = (blk - a.nq_vis) * 128 + 16 * warp + 2 * it + (lane >> 4);  // text token index
+        if (t < a.text_keys) {
+          float f[8];
+          unpack8(raw[it], f);
+          float* dstk = a.mean[1] + ((int64_t)bh * a.out_rows[1] + a.n_blk[1] + t) * 128 + col;
+          reinterpret_cast<float4*>(dstk)[0] = make_float4(f[0], f[1], f[2], f[3]);
+          reinterpret_cast<float4*>(dstk)[1] = make_float4(f[4], f[5], f[6], f[7]);
+        }
+      }
+    }
+    if (blk >= a.n_blk[which]) return;
+  } else {
+    if (blk >= a.n_blk[which]) return;
+    const __nv_bfloat16* base = a.x[which] + b * a.stride[which][0] + h * a.stride[which][1];
+    const int64_t ts = a.stride[which][2];
+    const int shift = visual ? 0 : a.gap;  // padded row -> memory row
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = row0 + 2 * it;
+      raw[it] = make_uint4(0, 0, 0, 0);
+      if (r < valid) raw[it] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(r - shift) * ts + col));
+    }
   }
 
   float acc[8];
@@ -147,8 +253,8 @@ __global__ void __launch_bounds__(kThreads) pool_stats_kernel(const PoolArgs a) 
 
 }  // namespace
 
-int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, const void* v, char* ws,
-                      const WsLayout& L, cudaStream_t s) {
+static PoolArgs pool_args(const rsa_attn_desc* d, const void* q, const void* k, const void* v, char* ws,
+                          const WsLayout& L) {
   PoolArgs a;
   a.x[0] = (const __nv_bfloat16*)q;
   a.x[1] = (const __nv_bfloat16*)k;
@@ -182,10 +288,59 @@ int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, cons
   a.heads = d->heads;
   a.text_keys = L.a;
   a.text_from = rm.vis_len;
+  return a;
+}
+
+int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, const void* v, char* ws,
+                      const WsLayout& L, cudaStream_t s) {
+  const PoolArgs a = pool_args(d, q, k, v, ws, L);
   const int text_ctas = (L.a + 15) / 16;
   const int gx = L.nb > text_ctas ? L.nb : text_ctas;
   dim3 grid(gx, L.bh, L.a > 0 ? 4 : 3);
-  pool_stats_kernel<<<grid, kThreads, 0, s>>>(a);
+  pool_stats_kernel<false><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
+  RSA_CUDA_CHECK(cudaGetLastError());
+  return RSA_OK;
+}
+
+int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* q_src, const void* k_src,
+                    const void* v_src, void* q, void* k, void* v, char* ws, const WsLayout* L, cudaStream_t s) {
+  const RowMap rm = row_map(d);
+  PrepArgs pa;
+  pa.src[0] = (const __nv_bfloat16*)q_src, pa.src[1] = (const __nv_bfloat16*)k_src, pa.src[2] = (const __nv_bfloat16*)v_src;
+  pa.dst[0] = (__nv_bfloat16*)q, pa.dst[1] = (__nv_bfloat16*)k, pa.dst[2] = (__nv_bfloat16*)v;
+  for (int t = 0; t < 3; ++t) {
+    pa.src_stride[t][0] = p->src_stride[t][0];
+    pa.src_stride[t][1] = p->src_stride[t][1];
+  }
+  for (int i = 0; i < 3; ++i) {
+    pa.dst_stride[0][i] = d->q_stride[i];
+    pa.dst_stride[1][i] = d->k_stride[i];
+    pa.dst_stride[2][i] = d->v_stride[i];
+  }
+  pa.w[0] = p->norm ? (const __nv_bfloat16*)p->q_weight : nullptr;
+  pa.w[1] = p->norm ? (const __nv_bfloat16*)p->k_weight : nullptr;
+  pa.eps = p->eps;
+  pa.cos = p->cos;
+  pa.sin = p->sin;
+  pa.rope_rows = p->rope_rows;
+  pa.rows = p->rows;
+  pa.dst_row0 = p->dst_row;
+  // destination row -> block of the padded layout: visual rows start block 0, text rows start block nq_vis
+  pa.blk0 = p->dst_row == 0 ? 0 : rm.nq_vis;
+  pa.pool = L != nullptr;
+  PoolArgs a;
+  if (L) {
+    a = pool_args(d, q, k, v, ws, *L);
+  } else {
+    a = PoolArgs{};
+    a.heads = d->heads;
+    a.nq_vis = rm.nq_vis;
+    a.vis_len = rm.vis_len;
+    a.gap = rm.gap;
+  }
+  const int blocks = (p->rows + 127) / 128;
+  dim3 grid(blocks, d->batch * d->heads, 3);
+  pool_stats_kernel<true><<<grid, kThreads, 0, s>>>(a, pa);
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;
 }

@@ -380,6 +380,53 @@ extern "C" int rsa_rectified_attention(const rsa_attn_desc* d, const void* q, co
   return launch_attention(a, s);
 }
 
+extern "C" int rsa_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* q_src, const void* k_src,
+                            const void* v_src, void* q, void* k, void* v, int pool, void* workspace, size_t bytes,
+                            void* stream) {
+  int rc = validate_desc(d);
+  if (rc != RSA_OK) return rc;
+  if (!p) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: descriptor is null");
+  if (!q_src || !k_src || !v_src || !q || !k || !v) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: null tensor");
+  const RowMap rm = row_map(d);
+  if (p->rows < 1) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: rows must be positive");
+  if (p->dst_row != 0 && !(d->family == RSA_FAMILY_JOINT && p->dst_row == rm.vis_len))
+    RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: dst_row must be 0 or the visual token count (%d)", rm.vis_len);
+  const int room = p->dst_row == 0 ? (d->family == RSA_FAMILY_JOINT && pool ? rm.vis_len : d->seq) : d->seq - rm.vis_len;
+  if (p->rows > d->seq - p->dst_row) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: %d rows do not fit behind row %d of %d", p->rows, p->dst_row, d->seq);
+  if (pool && p->rows != room && !(p->dst_row == 0 && p->rows == d->seq && rm.gap == 0))
+    RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: pooling needs whole segments (%d rows here, segment has %d)", p->rows, room);
+  if (p->norm != 0 && p->norm != 1) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: norm must be 0 or 1 (RMSNorm over head_dim)");
+  if (p->norm && (!p->q_weight || !p->k_weight)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: norm weights are null");
+  if (p->rope_rows < 0 || p->rope_rows > p->rows) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: rope_rows out of range");
+  if (p->rope_rows > 0 && (!p->cos || !p->sin)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: rotary tables are null");
+  for (int t = 0; t < 3; ++t)
+    for (int i = 0; i < 2; ++i)
+      if (p->src_stride[t][i] < 0 || p->src_stride[t][i] % 8) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: source strides must be multiples of 8 elements");
+  const void* ptrs[8] = {q_src, k_src, v_src, q, k, v, p->q_weight, p->k_weight};
+  for (int i = 0; i < 8; ++i)
+    if ((uintptr_t)ptrs[i] % 16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: tensors must be 16-byte aligned");
+  if (p->rope_rows > 0 && (((uintptr_t)p->cos % 16) || ((uintptr_t)p->sin % 16))) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: rotary tables must be 16-byte aligned");
+  WsLayout L;
+  if (pool && (rc = check_ws(d, workspace, bytes, &L)) != RSA_OK) return rc;
+  return launch_qkv_prep(p, d, q_src, k_src, v_src, q, k, v, (char*)workspace, pool ? &L : nullptr, (cudaStream_t)stream);
+}
+
+extern "C" int rsa_rectified_attention_pooled(const rsa_attn_desc* d, const void* q, const void* k, const void* v,
+                                              void* out, void* workspace, size_t bytes, void* stream) {
+  WsLayout L;
+  int rc = check_ws(d, workspace, bytes, &L);
+  if (rc != RSA_OK) return rc;
+  if (!q || !k || !v || !out) RSA_FAIL(RSA_ERR_ARG, "rsa_rectified_attention_pooled: null tensor");
+  char* ws = (char*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = launch_block_scores(d, ws, L, s)) != RSA_OK) return rc;
+  if ((rc = launch_block_select(d, ws, L, s)) != RSA_OK) return rc;
+  if ((rc = launch_rect_c(d, ws, L, s)) != RSA_OK) return rc;
+  AttnArgs a;
+  fill_attn_args(d, q, k, v, out, ws, L, &a);
+  return launch_attention(a, s);
+}
+
 extern "C" size_t rsa_masked_attention_workspace_bytes(int bh, int nq, int nkv) {
   if (bh <= 0 || nq <= 0 || nkv <= 0) return 0;
   // kept lists + counts + pair schedule + common-prefix lengths

@@ -63,6 +63,8 @@ int check_ws(const rsa_attn_desc* d, const void* ws, size_t bytes, WsLayout* out
 // stage launchers (defined in the .cu files)
 int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, const void* v, char* ws,
                       const WsLayout& L, cudaStream_t s);
+int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* q_src, const void* k_src,
+                    const void* v_src, void* q, void* k, void* v, char* ws, const WsLayout* L, cudaStream_t s);
 int launch_block_scores(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);
 int launch_block_select(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);
 int launch_rect_c(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);

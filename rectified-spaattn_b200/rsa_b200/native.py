@@ -40,13 +40,19 @@ class WsView(C.Structure):
                 ("sched_idx", C.c_void_p), ("pair_shared", C.c_void_p)]
 
 
+class PrepDesc(C.Structure):
+    _fields_ = [("rows", C.c_int32), ("dst_row", C.c_int32), ("src_stride", (C.c_int64 * 2) * 3),
+                ("norm", C.c_int32), ("eps", C.c_float), ("q_weight", C.c_void_p), ("k_weight", C.c_void_p),
+                ("rope_rows", C.c_int32), ("reserved", C.c_int32), ("cos", C.c_void_p), ("sin", C.c_void_p)]
+
+
 EXPORTS = [
     "rsa_last_error_string", "rsa_version", "rsa_device_ok", "rsa_gilbert_map", "rsa_gilbert_block_neighbors",
     "rsa_permute_rows", "rsa_attn_workspace_bytes", "rsa_attn_workspace_view", "rsa_pool_stats",
     "rsa_block_scores", "rsa_block_select", "rsa_rect_c", "rsa_sparse_attention", "rsa_rectified_attention",
     "rsa_masked_attention_workspace_bytes", "rsa_masked_attention", "rsa_set_attention_impl",
     "rsa_debug_set_attention_dump", "rsa_debug_set_attention_flags", "rsa_host_call_scratch_bytes",
-    "rsa_rectified_attention_host",
+    "rsa_rectified_attention_host", "rsa_qkv_prep", "rsa_rectified_attention_pooled",
 ]
 
 _lib = None
@@ -83,6 +89,8 @@ def lib():
     L.rsa_host_call_scratch_bytes.argtypes = [C.POINTER(AttnDesc), i32]
     L.rsa_host_call_scratch_bytes.restype = sz
     L.rsa_rectified_attention_host.argtypes = [C.POINTER(AttnDesc), p, p, p, p, i32, p, sz, p]
+    L.rsa_qkv_prep.argtypes = [C.POINTER(PrepDesc), C.POINTER(AttnDesc), p, p, p, p, p, p, i32, p, sz, p]
+    L.rsa_rectified_attention_pooled.argtypes = [C.POINTER(AttnDesc), p, p, p, p, p, sz, p]
     L.rsa_set_attention_impl.argtypes = [i32]
     L.rsa_debug_set_attention_dump.argtypes = [p]
     L.rsa_debug_set_attention_dump.restype = None

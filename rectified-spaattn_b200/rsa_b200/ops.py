@@ -173,6 +173,54 @@ class Plan:
                    self.out.data_ptr())
         return self.out
 
+    def run_pooled(self):
+        """Kernels 3a-4 on the pooled statistics qkv_prep(..., pool=True) left in this plan's workspace."""
+        self._call("rsa_rectified_attention_pooled", self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(),
+                   self.out.data_ptr())
+        return self.out
+
+    def qkv_prep(self, q_src, k_src, v_src, dst_row=0, q_weight=None, k_weight=None, eps=1e-6, rope=None,
+                 rope_rows=None, pool=True):
+        """Kernel 0: fills rows [dst_row, dst_row + rows) of this plan's q, k, v from projection outputs
+        [B, rows, H*128] (head split, per-head RMSNorm with bf16 weights, rotary embedding on the first `rope_rows`
+        tokens, re-layout) and, with pool=True, the pooled statistics of those blocks."""
+        b, h, s, d = self.shape
+        for t, n in ((q_src, "q_src"), (k_src, "k_src"), (v_src, "v_src")):
+            _need_cuda(t, n)
+            if t.dtype != torch.bfloat16 or t.dim() != 3 or t.shape[0] != b or t.shape[2] != h * d or t.stride(2) != 1:
+                raise RuntimeError(f"{n} must be a bfloat16 [B, rows, H*128] tensor with contiguous channels")
+        rows = q_src.shape[1]
+        if k_src.shape[1] != rows or v_src.shape[1] != rows:
+            raise RuntimeError("q/k/v sources differ in length")
+        p = N.PrepDesc()
+        p.rows, p.dst_row = rows, int(dst_row)
+        for i, t in enumerate((q_src, k_src, v_src)):
+            p.src_stride[i][0], p.src_stride[i][1] = t.stride(0), t.stride(1)
+        keep = []
+        if q_weight is not None or k_weight is not None:
+            if q_weight is None or k_weight is None:
+                raise RuntimeError("both norm weights are needed")
+            ws_ = [w.detach().to(device=self.device, dtype=torch.bfloat16).contiguous() for w in (q_weight, k_weight)]
+            if any(w.numel() != d for w in ws_):
+                raise RuntimeError("RMSNorm weights must have head_dim elements")
+            keep += ws_
+            p.norm, p.eps = 1, float(eps)
+            p.q_weight, p.k_weight = ws_[0].data_ptr(), ws_[1].data_ptr()
+        if rope is not None:
+            cos, sin = (t.detach().to(device=self.device, dtype=torch.float32).contiguous() for t in rope)
+            n_rope = cos.shape[0] if rope_rows is None else int(rope_rows)
+            if cos.shape != sin.shape or cos.dim() != 2 or cos.shape[1] != d or cos.shape[0] < n_rope:
+                raise RuntimeError("rotary tables must be (cos, sin) of shape [rope_rows, head_dim]")
+            keep += [cos, sin]
+            p.rope_rows, p.cos, p.sin = n_rope, cos.data_ptr(), sin.data_ptr()
+        L = N.lib()
+        with torch.cuda.device(self.device):
+            N.check(L.rsa_qkv_prep(C.byref(p), C.byref(self.desc), q_src.data_ptr(), k_src.data_ptr(),
+                                   v_src.data_ptr(), self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(),
+                                   1 if pool else 0, self.ws.data_ptr(), self.ws_bytes, _stream(self.device)),
+                    "rsa_qkv_prep")
+        self._keep = keep   # the kernel reads them asynchronously
+
     # --- workspace views for the parity tests
     def view(self):
         v = N.WsView()

@@ -436,3 +436,87 @@ def test_call_is_cuda_graph_capturable(dev):
     want2 = ops.Plan(q2, k, v, geo, case["top_k"], case["p"], nbr).run()
     torch.cuda.synchronize()
     assert torch.equal(plan.out.view(torch.int16), want2.view(torch.int16))
+
+
+# ------------------------------------------------------------------- kernel 0: fused pre-attention sequence
+def _bf16_ulp_diff(a, b):
+    """|difference| in bf16 ulps between two bf16 tensors of equal sign pattern (int16 bit distance)."""
+    ai = a.contiguous().view(torch.int16).to(torch.int32)
+    bi = b.contiguous().view(torch.int16).to(torch.int32)
+    return (ai - bi).abs(), (ai < 0) == (bi < 0)
+
+
+def test_qkv_prep_against_oracle_and_torch(dev):
+    """Kernel 0 on the golden inputs (390 ragged rows, 2 heads, rotary on the first 300): bit patterns against
+    oracle/prep_oracle.py (which follows the kernel's reduction order; only rsqrt differs) and against the PyTorch op
+    sequence of the reference's processor run on the GPU.  Bar: every element within 1 bf16 ulp, >= 99.9 % identical;
+    V (a pure re-layout) bit-exact."""
+    from oracle import make_golden as MG
+    from oracle import prep_oracle as P
+    from rsa_b200 import geometry as G
+    from rsa_b200 import ops
+    src, wq, wk, cos, sin, n_rope = MG.prep_inputs()
+    rows = src[0].shape[1]
+    q, k, v = (torch.zeros(1, 2, rows, 128, dtype=torch.bfloat16, device=dev) for _ in range(3))
+    plan = ops.Plan(q, k, v, G.wan(rows), 1, 0.3, None)
+    plan.qkv_prep(*(t.to(dev) for t in src), q_weight=wq, k_weight=wk, eps=1e-6, rope=(cos, sin), pool=False)
+    torch.cuda.synchronize()
+    for name, got, x, w, nr in (("q", q, src[0], wq, n_rope), ("k", k, src[1], wk, n_rope), ("v", v, src[2], None, 0)):
+        want = P.prep(x.float().numpy(), 2, None if w is None else w.float().numpy(), 1e-6, cos.numpy(), sin.numpy(), nr)
+        want = torch.from_numpy(want).to(torch.bfloat16)
+        tref = MG.torch_prep(x.to(dev), 2, None if w is None else w.to(dev), 1e-6, cos.to(dev), sin.to(dev), nr).cpu()
+        for ref, what in ((want, "oracle"), (tref, "torch on GPU")):
+            ulp, same = _bf16_ulp_diff(got.cpu(), ref)
+            assert bool((same | (ref.float().abs() < 1e-3)).all()), (name, what)
+            assert int(ulp[same].max()) <= 1, (name, what, int(ulp.max()))
+            assert float((ulp == 0).float().mean()) >= 0.999, (name, what)
+        if name == "v":
+            assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
+
+
+@pytest.mark.parametrize("name,dual", [("hunyuan_small", False), ("hunyuan_small", True), ("hunyuan_ragged", True),
+                                       ("wan_ragged", False)])
+def test_qkv_prep_pooled_path_equals_separate_kernels(dev, name, dual):
+    """qkv_prep(pool=True) + run_pooled() must give exactly what kernel 2 computes from the rows kernel 0 stored, and the
+    same attention output: pooled statistics bit-identical, output bit-identical.  `dual` = latent and encoder streams
+    come from two source tensors (dual-stream block); otherwise one concatenated source (single-stream block)."""
+    from rsa_b200 import ops
+    case = load_case(name)
+    geo = product_geometry(case["fam"], case["nv"], case["s"], case["text_len"], case["ntrue_d"], case["grid"][0])
+    nbr = torch.from_numpy(case["nbr"])
+    heads, s, nv = case["heads"], case["s"], case["nv"]
+    g = torch.Generator().manual_seed(17)
+    # projection outputs whose head split reproduces the case's Q, K, V: [1, S, H*128]
+    src = [torch.from_numpy(case[n]).to(torch.bfloat16)[0].permute(1, 0, 2).reshape(1, s, heads * 128).contiguous().to(dev)
+           for n in ("q", "k", "v")]
+    wq = (1 + 0.1 * torch.randn(128, generator=g)).to(torch.bfloat16)
+    wk = (1 + 0.1 * torch.randn(128, generator=g)).to(torch.bfloat16)
+    ang = torch.outer(torch.arange(nv, dtype=torch.float32), 1.0 / (64.0 ** (torch.arange(0, 128, 2) / 128)))
+    rope = (ang.cos().repeat_interleave(2, 1), ang.sin().repeat_interleave(2, 1))
+    q, k, v = (torch.zeros(1, heads, s, 128, dtype=torch.bfloat16, device=dev) for _ in range(3))
+    plan = ops.Plan(q, k, v, geo, case["top_k"], case["p"], nbr)
+    if dual:
+        plan.qkv_prep(*(t[:, :nv] for t in src), dst_row=0, q_weight=wq, k_weight=wk, rope=rope)
+        plan.qkv_prep(*(t[:, nv:] for t in src), dst_row=nv, q_weight=wq, k_weight=wk)
+    else:
+        plan.qkv_prep(*src, dst_row=0, q_weight=wq, k_weight=wk, rope=rope, rope_rows=nv)
+    torch.cuda.synchronize()
+    vw = plan.view()
+    fused = {n: vw[n].clone() for n in ("q_pool", "q_mad", "k_cat", "k_mad", "v_pool")}
+    out_fused = plan.run_pooled().clone()
+    torch.cuda.synchronize()
+    # the rows kernel 0 stored, through the separate kernels
+    plan2 = ops.Plan(q, k, v, geo, case["top_k"], case["p"], nbr)
+    plan2.pool_stats()
+    torch.cuda.synchronize()
+    vw2 = plan2.view()
+    for n in fused:
+        assert torch.equal(fused[n].view(torch.int32), vw2[n].view(torch.int32)), n
+    out_sep = plan2.run()
+    torch.cuda.synchronize()
+    assert torch.equal(out_fused.view(torch.int16), out_sep.view(torch.int16))
+    # and the stored rows are the PyTorch sequence's (within a bf16 ulp)
+    from oracle import make_golden as MG
+    tq = MG.torch_prep(src[0], heads, wq.to(dev), 1e-6, rope[0].to(dev), rope[1].to(dev), nv)
+    ulp, same = _bf16_ulp_diff(q, tq)
+    assert int(ulp[same].max()) <= 1 and float((ulp == 0).float().mean()) >= 0.999

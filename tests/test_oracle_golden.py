@@ -122,3 +122,27 @@ def test_selection_tie_break_and_threshold():
     assert n.tolist() == [3, 1, 2, 1]
     assert m.tolist() == [[True, True, True, False], [False, True, False, False], [True, True, False, False],
                           [False, False, False, True]]
+
+
+def test_prep_oracle_against_torch_sequence(gold_dir):
+    """oracle/prep_oracle.py (head split, diffusers RMSNorm, diffusers apply_rotary_emb, restated) against the literal
+    PyTorch op sequence run in bf16 (tests/golden/prep_hunyuan.npz).  The reduction order of mean(x^2) and rsqrt differ
+    by fp32 ulps, so a bf16 rounding may flip: every element within 1 bf16 ulp, >= 99.9 % identical."""
+    import torch
+
+    from oracle import make_golden as MG
+    from oracle import prep_oracle as P
+    src, wq, wk, cos, sin, n_rope = MG.prep_inputs()
+    g = np.load(os.path.join(gold_dir, "prep_hunyuan.npz"))
+    for name, x, w, nr in (("q", src[0], wq, n_rope), ("k", src[1], wk, n_rope), ("v", src[2], None, 0)):
+        got = P.prep(x.float().numpy(), 2, None if w is None else w.float().numpy(), 1e-6, cos.numpy(), sin.numpy(), nr)
+        ref = torch.from_numpy(g[name]).view(torch.bfloat16).float().numpy()
+        gb = torch.from_numpy(got).to(torch.bfloat16).view(torch.int16).numpy().astype(np.int32)
+        rb = g[name].astype(np.int32)
+        same_sign = (gb < 0) == (rb < 0)
+        ulp = np.abs(gb - rb)
+        assert np.all(same_sign | (np.abs(got) < 1e-3))
+        assert ulp[same_sign].max() <= 1, (name, ulp.max())
+        assert np.mean(ulp == 0) >= 0.999, (name, np.mean(ulp == 0))
+        if name == "v":
+            assert np.array_equal(got, ref)

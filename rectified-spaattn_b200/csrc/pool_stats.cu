@@ -68,69 +68,100 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
 }
 
 // Kernel 0 front end: rows of one 128-token block of one head, normalised / rotated / rounded to bf16, stored to the
-// destination and returned in the same register layout the pooling sweep uses.
+// destination and returned in the same register layout the pooling sweep uses.  All eight source rows of a thread are
+// requested before the first is used, and the rotary-table row of step it + 1 is requested before step it is
+// computed: the kernel is latency-bound otherwise (first version: 2.1 ms at C3b, 26 % of DRAM throughput).
+struct RopeRow {
+  float4 c0, c1, s0, s1;
+};
+__device__ __forceinline__ RopeRow load_rope(const PrepArgs& p, int r, int col, bool on) {
+  RopeRow t;
+  t.c0 = t.c1 = t.s0 = t.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (on) {
+    const float4* cp = reinterpret_cast<const float4*>(p.cos + (int64_t)r * 128 + col);
+    const float4* sp = reinterpret_cast<const float4*>(p.sin + (int64_t)r * 128 + col);
+    t.c0 = __ldg(cp), t.c1 = __ldg(cp + 1), t.s0 = __ldg(sp), t.s1 = __ldg(sp + 1);
+  }
+  return t;
+}
+
 __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, int h, int jblk, int warp, int lane,
                                           uint4 (&raw)[8]) {
   const int col = 8 * (lane & 15);
   const __nv_bfloat16* src = p.src[which] + b * p.src_stride[which][0] + (int64_t)h * 128 + col;
   __nv_bfloat16* dst = p.dst[which] + b * p.dst_stride[which][0] + h * p.dst_stride[which][1] + col;
-  float wgt[8];
-  const bool normed = which < 2 && p.w[which] != nullptr;
-  if (normed) unpack8(__ldg(reinterpret_cast<const uint4*>(p.w[which] + col)), wgt);
+  const int r0 = jblk * 128 + 16 * warp + (lane >> 4);  // source row of step 0; the 16 lanes of a half-warp share it
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
-    const int r = jblk * 128 + 16 * warp + 2 * it + (lane >> 4);  // source row; the 16 lanes of a half-warp share it
-    const bool live = r < p.rows;
-    uint4 u = make_uint4(0, 0, 0, 0);
-    if (live) u = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * p.src_stride[which][1]));
-    if (which < 2) {
-      float f[8];
-      unpack8(u, f);
-      if (normed) {
-        // mean(x^2) over the 128 channels of this head: 8 per lane, then a fixed butterfly over the 16 lanes
-        float ss = 0.f;
+    const int r = r0 + 2 * it;
+    raw[it] = make_uint4(0, 0, 0, 0);
+    if (r < p.rows) raw[it] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * p.src_stride[which][1]));
+  }
+  if (which == 2) {  // V: re-layout only
 #pragma unroll
-        for (int c = 0; c < 8; ++c) ss = __fmaf_rn(f[c], f[c], ss);
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
-        const float rinv = rsqrtf(__fadd_rn(__fmul_rn(ss, 1.0f / 128.0f), p.eps));
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const float xn = __bfloat162float(__float2bfloat16_rn(__fmul_rn(f[c], rinv)));
-          f[c] = __bfloat162float(__float2bfloat16_rn(__fmul_rn(xn, wgt[c])));
-        }
-      }
-      if (live && r < p.rope_rows) {
-        float cs[8], sn[8];
-        const float4* cp = reinterpret_cast<const float4*>(p.cos + (int64_t)r * 128 + col);
-        const float4* sp = reinterpret_cast<const float4*>(p.sin + (int64_t)r * 128 + col);
-        const float4 c0 = __ldg(cp), c1 = __ldg(cp + 1), s0 = __ldg(sp), s1 = __ldg(sp + 1);
-        cs[0] = c0.x, cs[1] = c0.y, cs[2] = c0.z, cs[3] = c0.w, cs[4] = c1.x, cs[5] = c1.y, cs[6] = c1.z, cs[7] = c1.w;
-        sn[0] = s0.x, sn[1] = s0.y, sn[2] = s0.z, sn[3] = s0.w, sn[4] = s1.x, sn[5] = s1.y, sn[6] = s1.z, sn[7] = s1.w;
-        float g[8];
-#pragma unroll
-        for (int c = 0; c < 8; c += 2) {  // rotate_pairs(x)[2i] = -x[2i+1], [2i+1] = x[2i]
-          g[c] = __fadd_rn(__fmul_rn(f[c], cs[c]), __fmul_rn(-f[c + 1], sn[c]));
-          g[c + 1] = __fadd_rn(__fmul_rn(f[c + 1], cs[c + 1]), __fmul_rn(f[c], sn[c + 1]));
-        }
-#pragma unroll
-        for (int c = 0; c < 8; ++c) f[c] = g[c];
-      }
-      __nv_bfloat162 o2[4];
-#pragma unroll
-      for (int c = 0; c < 4; ++c) o2[c] = __floats2bfloat162_rn(f[2 * c], f[2 * c + 1]);
-      u = *reinterpret_cast<const uint4*>(o2);
+    for (int it = 0; it < 8; ++it) {
+      const int r = r0 + 2 * it;
+      if (r < p.rows) *reinterpret_cast<uint4*>(dst + (int64_t)(p.dst_row0 + r) * p.dst_stride[which][2]) = raw[it];
     }
+    return;
+  }
+  float wgt[8];
+  const bool normed = p.w[which] != nullptr;
+  if (normed) unpack8(__ldg(reinterpret_cast<const uint4*>(p.w[which] + col)), wgt);
+  RopeRow next = load_rope(p, r0, col, r0 < p.rows && r0 < p.rope_rows);
+#pragma unroll
+  for (int it = 0; it < 8; ++it) {
+    const int r = r0 + 2 * it;
+    const bool live = r < p.rows;
+    const bool rot = live && r < p.rope_rows;
+    const RopeRow t = next;
+    if (it < 7) next = load_rope(p, r + 2, col, r + 2 < p.rows && r + 2 < p.rope_rows);
+    float f[8];
+    unpack8(raw[it], f);
+    if (normed) {
+      // mean(x^2) over the 128 channels of this head: 8 per lane, then a fixed butterfly over the 16 lanes
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) ss = __fmaf_rn(f[c], f[c], ss);
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
+      const float rinv = rsqrtf(__fadd_rn(__fmul_rn(ss, 1.0f / 128.0f), p.eps));
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        const float xn = __bfloat162float(__float2bfloat16_rn(__fmul_rn(f[c], rinv)));
+        f[c] = __bfloat162float(__float2bfloat16_rn(__fmul_rn(xn, wgt[c])));
+      }
+    }
+    if (rot) {
+      const float cs[8] = {t.c0.x, t.c0.y, t.c0.z, t.c0.w, t.c1.x, t.c1.y, t.c1.z, t.c1.w};
+      const float sn[8] = {t.s0.x, t.s0.y, t.s0.z, t.s0.w, t.s1.x, t.s1.y, t.s1.z, t.s1.w};
+      float g[8];
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {  // rotate_pairs(x)[2i] = -x[2i+1], [2i+1] = x[2i]
+        g[c] = __fadd_rn(__fmul_rn(f[c], cs[c]), __fmul_rn(-f[c + 1], sn[c]));
+        g[c + 1] = __fadd_rn(__fmul_rn(f[c + 1], cs[c + 1]), __fmul_rn(f[c], sn[c + 1]));
+      }
+#pragma unroll
+      for (int c = 0; c < 8; ++c) f[c] = g[c];
+    }
+    __nv_bfloat162 o2[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) o2[c] = __floats2bfloat162_rn(f[2 * c], f[2 * c + 1]);
+    const uint4 u = *reinterpret_cast<const uint4*>(o2);
     if (live) *reinterpret_cast<uint4*>(dst + (int64_t)(p.dst_row0 + r) * p.dst_stride[which][2]) = u;
     raw[it] = live ? u : make_uint4(0, 0, 0, 0);
   }
 }
 
-template <bool kPrep>
-__global__ void __launch_bounds__(kThreads) pool_stats_kernel(const PoolArgs a, const PrepArgs p) {
-  const int which = blockIdx.z;
-  const int bh = blockIdx.y;
-  const int blk = kPrep ? p.blk0 + (int)blockIdx.x : (int)blockIdx.x;
+template <bool kPrep, int kMinBlocks = 2>
+__global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const PoolArgs a, const PrepArgs p) {
+  // Prep grid: x = (tensor, batch*head) fastest, y = token block -- the CTAs that run together read the same source
+  // rows (all heads of a token are contiguous in the projection output) and the same rotary-table rows, which are as
+  // large as L2 at the HunyuanVideo size (2 x 61 MB) and would otherwise be streamed from HBM once per head.
+  const int which = kPrep ? (int)(blockIdx.x % 3) : (int)blockIdx.z;
+  const int bh = kPrep ? (int)(blockIdx.x / 3) : (int)blockIdx.y;
+  const int jblk = kPrep ? (int)blockIdx.y : (int)blockIdx.x;
+  const int blk = kPrep ? p.blk0 + jblk : jblk;
   const int b = bh / a.heads, h = bh % a.heads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -161,7 +192,7 @@ __global__ void __launch_bounds__(kThreads) pool_stats_kernel(const PoolArgs a, 
 
   uint4 raw[8];
   if constexpr (kPrep) {
-    prep_rows(p, which, b, h, blockIdx.x, warp, lane, raw);
+    prep_rows(p, which, b, h, jblk, warp, lane, raw);
     if (!p.pool) return;
     // rows the pooling counts as zeros (K, V rows >= kv_zero_from; hunyuan masked_fill_ :307-308) stay stored as they are
 #pragma unroll
@@ -297,7 +328,7 @@ int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, cons
   const int text_ctas = (L.a + 15) / 16;
   const int gx = L.nb > text_ctas ? L.nb : text_ctas;
   dim3 grid(gx, L.bh, L.a > 0 ? 4 : 3);
-  pool_stats_kernel<false><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
+  pool_stats_kernel<false, 3><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;
 }
@@ -339,8 +370,9 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
     a.gap = rm.gap;
   }
   const int blocks = (p->rows + 127) / 128;
-  dim3 grid(blocks, d->batch * d->heads, 3);
-  pool_stats_kernel<true><<<grid, kThreads, 0, s>>>(a, pa);
+  dim3 grid(3 * d->batch * d->heads, blocks);
+  // 2 CTAs per SM (about 100 registers): capping at 3 or 4 CTAs spills and is no faster (1.24 / 1.25 / 2.17 ms at C3b)
+  pool_stats_kernel<true, 2><<<grid, kThreads, 0, s>>>(a, pa);
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;
 }

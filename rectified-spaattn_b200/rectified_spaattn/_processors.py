@@ -83,11 +83,86 @@ def dense(fullattn, query, key, value, mode, attention_mask, s_k):
     return out.transpose(1, 2).reshape(b, s_q, -1)
 
 
+def rms_params(mod):
+    """(weight, eps) if `mod` is an RMSNorm over head_dim = 128 with a bf16 weight and no bias -- the form kernel 0
+    fuses (diffusers RMSNorm of HunyuanVideo / Flux `norm_q`, `norm_k`, `norm_added_q`, `norm_added_k`); else None."""
+    w, eps = getattr(mod, "weight", None), getattr(mod, "eps", None)
+    if mod is None or w is None or eps is None or getattr(mod, "bias", None) is not None:
+        return None
+    if "RMSNorm" not in type(mod).__name__ or w.dtype != torch.bfloat16 or w.numel() != 128 or not w.is_cuda:
+        return None
+    return w, float(eps)
+
+
+def rope_tables(emb, n):
+    """(cos, sin) fp32 [>= n, 128] tables as diffusers passes them (`image_rotary_emb`), or None if `emb` has another form."""
+    if not (isinstance(emb, (tuple, list)) and len(emb) == 2):
+        return None
+    cos, sin = emb
+    ok = all(isinstance(t, torch.Tensor) and t.dim() == 2 and t.shape[1] == 128 and t.shape[0] >= n for t in (cos, sin))
+    return (cos, sin) if ok else None
+
+
+def fused_prep_attention(attn, hidden_states, encoder_hidden_states, geo, top_k, p_remain, nbr, image_rotary_emb,
+                         rope_text):
+    """The fused form of a joint-text processor's middle section (kernel 0 + kernels 3a-4): projections ->
+    rsa_qkv_prep (head split, RMSNorm, RoPE, re-layout, pooling) -> rsa_rectified_attention_pooled.  Returns
+    [B, S, H*D], or None when this layer does not have the shape kernel 0 fuses (the caller then runs the op-by-op path).
+    `rope_text`: Flux rotates the text tokens too (their table rows follow the image rows); HunyuanVideo does not."""
+    from rsa_b200 import ops
+    heads = attn.heads
+    if not hidden_states.is_cuda or hidden_states.dtype != torch.bfloat16:
+        return None
+    dual = getattr(attn, "add_q_proj", None) is not None and encoder_hidden_states is not None
+    nq_, nk_ = rms_params(getattr(attn, "norm_q", None)), rms_params(getattr(attn, "norm_k", None))
+    if nq_ is None or nk_ is None or nq_[1] != nk_[1]:
+        return None
+    ne = None
+    if dual:
+        eq_, ek_ = rms_params(getattr(attn, "norm_added_q", None)), rms_params(getattr(attn, "norm_added_k", None))
+        if eq_ is None or ek_ is None or eq_[1] != ek_[1]:
+            return None
+        ne = (eq_[0], ek_[0], eq_[1])
+    b, s = hidden_states.shape[0], geo.seq
+    nv = geo.vis_len or geo.nq_blocks * 128
+    rope = None
+    if image_rotary_emb is not None:
+        rope = rope_tables(image_rotary_emb, s if rope_text else nv)
+        if rope is None:
+            return None
+    lat = [f(hidden_states) for f in (attn.to_q, attn.to_k, attn.to_v)]
+    if lat[0].shape[2] != heads * 128:
+        return None
+    q, k, v = (torch.empty(b, heads, s, 128, dtype=torch.bfloat16, device=hidden_states.device) for _ in range(3))
+    plan = ops.Plan(q, k, v, geo, top_k, p_remain, nbr)
+    cut = lambda r, a, z: None if r is None else (r[0][a:z], r[1][a:z])
+    if dual:
+        enc = [f(encoder_hidden_states) for f in (attn.add_q_proj, attn.add_k_proj, attn.add_v_proj)]
+        if lat[0].shape[1] != nv or enc[0].shape[1] != s - nv:
+            return None
+        plan.qkv_prep(*lat, dst_row=0, q_weight=nq_[0], k_weight=nk_[0], eps=nq_[1], rope=cut(rope, 0, nv))
+        plan.qkv_prep(*enc, dst_row=nv, q_weight=ne[0], k_weight=ne[1], eps=ne[2],
+                      rope=cut(rope, nv, s) if rope_text else None)
+    else:
+        if lat[0].shape[1] != s:
+            return None
+        n_rope = 0 if rope is None else (s if rope_text else nv)
+        if geo.gap:     # ragged visual segment: the two segments are separate block ranges
+            plan.qkv_prep(*(t[:, :nv] for t in lat), dst_row=0, q_weight=nq_[0], k_weight=nk_[0], eps=nq_[1],
+                          rope=cut(rope, 0, nv))
+            plan.qkv_prep(*(t[:, nv:] for t in lat), dst_row=nv, q_weight=nq_[0], k_weight=nk_[0], eps=nq_[1],
+                          rope=cut(rope, nv, s) if rope_text else None)
+        else:
+            plan.qkv_prep(*lat, dst_row=0, q_weight=nq_[0], k_weight=nk_[0], eps=nq_[1], rope=rope, rope_rows=n_rope)
+    return plan.run_pooled().view(b, s, heads * 128)
+
+
 class ProcessorBase:
     """Constructor arguments and mutable per-layer state shared by every reference processor
     (e.g. rectified_wan21_attn.py:390-401)."""
 
     steps_per_cycle = 50  # `current_step` wraps to 0 after this many calls
+    fuse_prep = True      # joint-text processors: run head split / QK norm / RoPE / pooling as kernel 0 when the layer allows
 
     def __init__(self, mode, select_block_num, block_neighbor_list, p_remain_rates, processor_id=0):
         self.mode = mode

@@ -51,6 +51,22 @@ class RectifiedFluxSpaAttnProcessor2_0(_P.ProcessorBase):
         self.text_length = text_length
 
     def __call__(self, attn, hidden_states, encoder_hidden_states=None, attention_mask=None, image_rotary_emb=None):
+        sparse = self.mode == "sparse" and (self.processor_id < 37 or self.processor_id >= 57)
+        if sparse and self.fuse_prep and attention_mask is None:
+            # kernel 0: everything between the projections and the attention in one pass (reference :431-486)
+            s = hidden_states.shape[1] + (encoder_hidden_states.shape[1] if encoder_hidden_states is not None else 0)
+            fused = None
+            if s % 128 == 0 and s > self.text_length:
+                fused = _P.fused_prep_attention(attn, hidden_states, encoder_hidden_states, _G.flux(s, self.text_length),
+                                                self.select_block_num, self.p_remain_rates, self.block_neighbor_list,
+                                                image_rotary_emb, rope_text=True)
+            if fused is not None:
+                self._tick()
+                if encoder_hidden_states is None:
+                    return fused
+                n_txt = encoder_hidden_states.shape[1]
+                hidden_states, encoder_hidden_states = fused[:, :-n_txt], fused[:, -n_txt:]
+                return attn.to_out[1](attn.to_out[0](hidden_states)), attn.to_add_out(encoder_hidden_states)
         query, key, value = (_P.heads_first(f(hidden_states), attn.heads) for f in (attn.to_q, attn.to_k, attn.to_v))
         if getattr(attn, "norm_q", None) is not None:
             query = attn.norm_q(query)

@@ -69,6 +69,23 @@ class RectifiedHunyuanVideoSpaAttnProcessor2_0(_P.ProcessorBase):
         single_stream = getattr(attn, "add_q_proj", None) is None and encoder_hidden_states is not None
         if single_stream:
             hidden_states = torch.cat([hidden_states, encoder_hidden_states], dim=1)
+        if self.mode == "sparse" and self.fuse_prep and encoder_hidden_states is not None:
+            # kernel 0: everything between the projections and the attention in one pass (reference :448-498)
+            s = hidden_states.shape[1] + (0 if single_stream else encoder_hidden_states.shape[1])
+            num_true = self.num_true if self.num_true is not None else _P.kv_valid(attention_mask, s)
+            fused = _P.fused_prep_attention(attn, hidden_states, None if single_stream else encoder_hidden_states,
+                                            _G.hunyuan(s, int(num_true), encoder_hidden_states.shape[1]),
+                                            self.select_block_num, self.p_remain_rates, self.block_neighbor_list,
+                                            image_rotary_emb, rope_text=False)
+            if fused is not None:
+                n_txt = encoder_hidden_states.shape[1]
+                hidden_states, encoder_hidden_states = fused[:, :-n_txt], fused[:, -n_txt:]
+                if getattr(attn, "to_out", None) is not None:
+                    hidden_states = attn.to_out[1](attn.to_out[0](hidden_states))
+                if getattr(attn, "to_add_out", None) is not None:
+                    encoder_hidden_states = attn.to_add_out(encoder_hidden_states)
+                self._tick()
+                return hidden_states, encoder_hidden_states
         query, key, value = (_P.heads_first(f(hidden_states), attn.heads) for f in (attn.to_q, attn.to_k, attn.to_v))
         if getattr(attn, "norm_q", None) is not None:
             query = attn.norm_q(query)

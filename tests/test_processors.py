@@ -150,3 +150,55 @@ def test_joint_text_processors_dense_limit():
     assert h.shape == (1, nv, dim) and e.shape == (1, 226, dim)
     _close(h, hd)
     _close(e, ed)
+
+
+@pytest.mark.gpu
+def test_fused_prep_processors_match_unfused():
+    """HunyuanVideo / Flux processors with kernel 0 (head split + QK RMSNorm + RoPE + pooling fused, the default) against
+    the same processors running those steps op by op (`fuse_prep = False`): dual-stream, single-stream and a ragged
+    visual segment.  (torch.nn.RMSNorm rounds once where diffusers' RMSNorm -- which kernel 0 follows -- rounds twice,
+    so rows differ by at most a bf16 ulp before the attention; the dense limit keeps the block choice out of it.)"""
+    dev = torch.device("cuda:0")
+    dim, heads = 256, 2
+    for nv in (1024, 1000):
+        x = torch.randn(1, nv, dim, device=dev).to(torch.bfloat16)
+        txt = torch.randn(1, 256, dim, device=dev).to(torch.bfloat16)
+        cos, sin, _ = _rope_tables(nv, 128, dev)
+        mask = (torch.arange(nv + 256, device=dev) < nv + 200).view(1, 1, 1, -1)
+        for added in (True, False):                      # dual-stream / single-stream block
+            attn = _mk(dev, dim, heads, added=added)
+            outs = []
+            for fuse in (True, False):
+                if not fuse and nv % 128:
+                    continue                              # the op-by-op path is the reference's: aligned only
+                pr = hun.RectifiedHunyuanVideoSpaAttnProcessor2_0("sparse", 99, None, 0.3)
+                pr.fuse_prep = fuse
+                with torch.no_grad():
+                    outs.append(pr(attn, x, txt, mask, (cos, sin)))
+            if len(outs) == 2:
+                _close(outs[0][0], outs[1][0])
+                _close(outs[0][1][:, :200], outs[1][1][:, :200])
+            else:                                         # ragged: against dense SDPA through the same modules
+                ref = hun.RectifiedHunyuanVideoSpaAttnProcessor2_0("torch", 99, None, 0.3)
+                with torch.no_grad():
+                    hr, er = ref(attn, x, txt, mask.expand(1, 1, nv + 256, nv + 256), (cos, sin))
+                _close(outs[0][0], hr)
+                _close(outs[0][1][:, :200], er[:, :200])
+    # Flux: dual-stream (text appended, rotated) and single-stream (one joint tensor)
+    nv = 1024
+    x = torch.randn(1, nv, dim, device=dev).to(torch.bfloat16)
+    txt = torch.randn(1, 512, dim, device=dev).to(torch.bfloat16)
+    cos2, sin2, _ = _rope_tables(nv + 512, 128, dev)
+    for added, args in ((True, (x, txt)), (False, (torch.cat([x, txt], dim=1), None))):
+        attn = _mk(dev, dim, heads, added=added)
+        outs = []
+        for fuse in (True, False):
+            pr = flux.RectifiedFluxSpaAttnProcessor2_0("sparse", 99, None, 0.3, processor_id=1, text_length=512)
+            pr.fuse_prep = fuse
+            with torch.no_grad():
+                outs.append(pr(attn, args[0], args[1], None, (cos2, sin2)))
+        if added:
+            _close(outs[0][0], outs[1][0])
+            _close(outs[0][1], outs[1][1])
+        else:
+            _close(outs[0], outs[1])

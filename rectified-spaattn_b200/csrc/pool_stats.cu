@@ -127,9 +127,11 @@ __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, i
       for (int o = 1; o < 16; o <<= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
       const float rinv = rsqrtf(__fadd_rn(__fmul_rn(ss, 1.0f / 128.0f), p.eps));
 #pragma unroll
-      for (int c = 0; c < 8; ++c) {
-        const float xn = __bfloat162float(__float2bfloat16_rn(__fmul_rn(f[c], rinv)));
-        f[c] = __bfloat162float(__float2bfloat16_rn(__fmul_rn(xn, wgt[c])));
+      for (int c = 0; c < 8; c += 2) {  // packed conversions: one F2FP per pair, the scalar cvt runs on the XU pipe
+        const float2 xn = __bfloat1622float2(__floats2bfloat162_rn(__fmul_rn(f[c], rinv), __fmul_rn(f[c + 1], rinv)));
+        const float2 y = __bfloat1622float2(__floats2bfloat162_rn(__fmul_rn(xn.x, wgt[c]), __fmul_rn(xn.y, wgt[c + 1])));
+        f[c] = y.x;
+        f[c + 1] = y.y;
       }
     }
     if (rot) {

@@ -174,6 +174,10 @@ int rsa_rectified_attention(const rsa_attn_desc* d, const void* q, const void* k
  *       (x * rsqrt(mean(x^2) + eps) in fp32, rounded to bf16, times the bf16 weight, rounded to bf16)
  *   diffusers apply_rotary_emb(x, (cos, sin), use_real=True, use_real_unbind_dim=-1)   :459-478
  *       (x * cos + rotate_pairs(x) * sin in fp32, rounded to bf16; only the first rope_rows tokens)
+ * and the Wan form of the same steps (rectified_wan21_attn.py:419-441, rectified_wan22_attn.py:44-64): RMSNorm over
+ * all heads*128 channels before the head split (norm = 2), then the rotary embedding -- Wan2.1 multiplies complex pairs
+ * in float64, Wan2.2 uses cos/sin tables; both are the same real arithmetic, done here in fp32 (the bf16 result
+ * differs from the float64 route only when a value sits within 2^-24 of a rounding boundary).
  * diffusers 0.34.0 (requirements.txt:18) is not vendored in the reference; the two functions are restated from its
  * published source (oracle/prep_oracle.py).
  * One call handles the `rows` tokens of ONE source: the latent stream (dst_row = 0) or, for a dual-stream block, the
@@ -186,14 +190,16 @@ typedef struct rsa_prep_desc {
   int32_t dst_row;          /* memory row of the destination the first source token goes to: 0 or the visual  */
                             /* token count                                                                    */
   int64_t src_stride[3][2]; /* q, k, v sources [batch, rows, heads*128]: (batch, token) element strides        */
-  int32_t norm;             /* 0 = none, 1 = RMSNorm over head_dim                                             */
+  int32_t norm;             /* 0 = none, 1 = RMSNorm over head_dim (HunyuanVideo, Flux), 2 = RMSNorm over all  */
+                            /* heads*128 channels of a token (Wan2.1 / Wan2.2, rectified_wan21_attn.py:423-426)*/
   float eps;
-  const void* q_weight;     /* DEVICE bf16 [128] (norm_q.weight)                                               */
-  const void* k_weight;     /* DEVICE bf16 [128] (norm_k.weight)                                               */
+  const void* q_weight;     /* DEVICE bf16 [128] (norm 1) or [heads*128] (norm 2): norm_q.weight               */
+  const void* k_weight;     /* likewise norm_k.weight                                                          */
   int32_t rope_rows;        /* source tokens [0, rope_rows) are rotated; 0 = no rotary embedding               */
   int32_t reserved;
   const float* cos;         /* DEVICE fp32 [rope_rows, 128] (diffusers' repeat-interleaved cos table)          */
   const float* sin;
+  float* row_scratch;       /* norm 2 only: DEVICE scratch of 2*batch*rows floats for the per-token statistics  */
 } rsa_prep_desc;
 
 int rsa_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* q_src, const void* k_src,

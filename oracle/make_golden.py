@@ -269,8 +269,33 @@ def torch_prep(x, heads, weight, eps, cos, sin, n_rope):
     return x
 
 
+def torch_prep_wan(x, heads, weight, eps, freqs):
+    """The literal op sequence of rectified_wan21_attn.py:419-441: RMSNorm over the inner dim (diffusers RMSNorm.forward
+    written out), head split, complex rotary embedding in float64.  freqs: complex [1, 1, S, 64]."""
+    if weight is not None:
+        variance = x.to(torch.float32).pow(2).mean(-1, keepdim=True)
+        x = x * torch.rsqrt(variance + eps)
+        x = x.to(weight.dtype) * weight
+    x = x.unflatten(2, (heads, -1)).transpose(1, 2)
+    if freqs is not None:
+        xr = torch.view_as_complex(x.to(torch.float64).unflatten(3, (-1, 2)))
+        x = torch.view_as_real(xr * freqs).flatten(3, 4).type_as(x)
+    return x
+
+
 def make_prep():
     src, wq, wk, cos, sin, n_rope = prep_inputs()
+    # Wan form on the same sources: weights over the inner dim, rotary embedding on every token (complex, float64)
+    g = torch.Generator().manual_seed(32)
+    rows = src[0].shape[1]
+    wq_in = (1 + 0.1 * torch.randn(256, generator=g)).to(torch.bfloat16)
+    wk_in = (1 + 0.1 * torch.randn(256, generator=g)).to(torch.bfloat16)
+    ang = torch.outer(torch.arange(rows, dtype=torch.float64), 1.0 / (256.0 ** (torch.arange(0, 128, 2, dtype=torch.float64) / 128)))
+    freqs = torch.polar(torch.ones_like(ang), ang)[None, None]
+    qw = torch_prep_wan(src[0], 2, wq_in, 1e-6, freqs)
+    kw = torch_prep_wan(src[1], 2, wk_in, 1e-6, freqs)
+    np.savez_compressed(os.path.join(GOLD, "prep_wan.npz"), q=qw.contiguous().view(torch.int16).numpy(),
+                        k=kw.contiguous().view(torch.int16).numpy())
     q = torch_prep(src[0], 2, wq, 1e-6, cos, sin, n_rope)
     k = torch_prep(src[1], 2, wk, 1e-6, cos, sin, n_rope)
     v = torch_prep(src[2], 2, None, 1e-6, None, None, 0)

@@ -58,6 +58,34 @@ def rms_norm(x, weight, eps):
     return bf16_round((xn * np.asarray(weight, np.float32)).astype(np.float32))
 
 
+def mean_square_row_kernel_order(x):
+    """mean(x^2) over the last axis (heads*128 channels of a token) in row_rms_kernel's order: lane l of 32 runs one fma
+    chain over columns 8(l + 32 j) .. +7 for j = 0, 1, ..; then a butterfly over the lanes (xor 1, 2, 4, 8, 16)."""
+    x = np.asarray(x, dtype=np.float32)
+    inner = x.shape[-1]
+    ss = np.zeros(x.shape[:-1] + (32,), dtype=np.float32)
+    for j in range((inner + 255) // 256):
+        for lane in range(32):
+            c0 = 8 * (lane + 32 * j)
+            if c0 >= inner:
+                continue
+            for c in range(8):
+                ss[..., lane] = _fma32(x[..., c0 + c], x[..., c0 + c], ss[..., lane])
+    for o in (1, 2, 4, 8, 16):
+        idx = np.arange(32) ^ o
+        ss = (ss + ss[..., idx]).astype(np.float32)
+    return (ss[..., 0] / np.float32(inner)).astype(np.float32)
+
+
+def rms_norm_across_heads(x, weight, eps):
+    """Wan: RMSNorm over all heads*128 channels of a token (rectified_wan21_attn.py:423-426; diffusers RMSNorm with
+    dim = inner_dim).  x [..., inner] bf16 values, weight [inner] -> bf16 values."""
+    var = mean_square_row_kernel_order(x)
+    rinv = (1.0 / np.sqrt(var.astype(np.float64) + np.float64(np.float32(eps)))).astype(np.float32)
+    xn = bf16_round((np.asarray(x, np.float32) * rinv[..., None]).astype(np.float32))
+    return bf16_round((xn * np.asarray(weight, np.float32)).astype(np.float32))
+
+
 def rotary(x, cos, sin):
     """x [..., S, 128], cos/sin [S, 128] fp32 -> bf16 values; pairs are (x[2i], x[2i+1])."""
     x = np.asarray(x, np.float32)
@@ -70,10 +98,15 @@ def rotary(x, cos, sin):
 
 
 def prep(src, heads, weight=None, eps=1e-6, cos=None, sin=None, rope_rows=0):
-    """src [B, rows, heads*128] -> [B, heads, rows, 128] after head split, RMSNorm (if weight) and rotary embedding on
-    the first rope_rows tokens."""
+    """src [B, rows, heads*128] -> [B, heads, rows, 128] after head split, RMSNorm (if weight: [128] = per head as in
+    HunyuanVideo / Flux, [heads*128] = across heads as in Wan, applied BEFORE the split) and rotary embedding on the
+    first rope_rows tokens."""
     b, rows, _ = src.shape
-    x = np.asarray(src, np.float32).reshape(b, rows, heads, 128).transpose(0, 2, 1, 3)
+    src = np.asarray(src, np.float32)
+    if weight is not None and np.asarray(weight).size == heads * 128:
+        src = rms_norm_across_heads(src, weight, eps)
+        weight = None
+    x = src.reshape(b, rows, heads, 128).transpose(0, 2, 1, 3)
     if weight is not None:
         x = rms_norm(x, weight, eps)
     if rope_rows:

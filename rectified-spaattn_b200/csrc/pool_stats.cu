@@ -33,7 +33,9 @@ struct PrepArgs {
   int64_t src_stride[3][2];     // (batch, token) element strides
   __nv_bfloat16* dst[3];        // [B, H, S, 128] views
   int64_t dst_stride[3][3];     // (batch, head, token)
-  const __nv_bfloat16* w[2];    // RMSNorm weights of q, k (bf16 [128]) or nullptr
+  const __nv_bfloat16* w[2];    // RMSNorm weights of q, k (bf16 [128], or [H*128] with w_head_stride = 128) or nullptr
+  int w_head_stride;            // 0: one weight vector per tensor (norm over head_dim); 128: norm across heads (Wan)
+  const float* row_rinv[2];     // norm across heads: rsqrt(mean(x^2) + eps) per (batch, source row), from row_rms_kernel
   float eps;
   const float *cos, *sin;       // fp32 [rope_rows, 128]
   int rope_rows;                // source rows below this are rotated
@@ -107,7 +109,8 @@ __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, i
   }
   float wgt[8];
   const bool normed = p.w[which] != nullptr;
-  if (normed) unpack8(__ldg(reinterpret_cast<const uint4*>(p.w[which] + col)), wgt);
+  if (normed) unpack8(__ldg(reinterpret_cast<const uint4*>(p.w[which] + h * p.w_head_stride + col)), wgt);
+  const float* rinv_rows = p.row_rinv[which] ? p.row_rinv[which] + (int64_t)b * p.rows : nullptr;
   RopeRow next = load_rope(p, r0, col, r0 < p.rows && r0 < p.rope_rows);
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
@@ -119,13 +122,18 @@ __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, i
     float f[8];
     unpack8(raw[it], f);
     if (normed) {
-      // mean(x^2) over the 128 channels of this head: 8 per lane, then a fixed butterfly over the 16 lanes
-      float ss = 0.f;
+      float rinv;
+      if (rinv_rows) {  // norm across heads: the row statistic was computed over all H*128 channels beforehand
+        rinv = live ? __ldg(rinv_rows + r) : 0.f;
+      } else {
+        // mean(x^2) over the 128 channels of this head: 8 per lane, then a fixed butterfly over the 16 lanes
+        float ss = 0.f;
 #pragma unroll
-      for (int c = 0; c < 8; ++c) ss = __fmaf_rn(f[c], f[c], ss);
+        for (int c = 0; c < 8; ++c) ss = __fmaf_rn(f[c], f[c], ss);
 #pragma unroll
-      for (int o = 1; o < 16; o <<= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
-      const float rinv = rsqrtf(__fadd_rn(__fmul_rn(ss, 1.0f / 128.0f), p.eps));
+        for (int o = 1; o < 16; o <<= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
+        rinv = rsqrtf(__fadd_rn(__fmul_rn(ss, 1.0f / 128.0f), p.eps));
+      }
 #pragma unroll
       for (int c = 0; c < 8; c += 2) {  // packed conversions: one F2FP per pair, the scalar cvt runs on the XU pipe
         const float2 xn = __bfloat1622float2(__floats2bfloat162_rn(__fmul_rn(f[c], rinv), __fmul_rn(f[c + 1], rinv)));
@@ -153,6 +161,28 @@ __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, i
     if (live) *reinterpret_cast<uint4*>(dst + (int64_t)(p.dst_row0 + r) * p.dst_stride[which][2]) = u;
     raw[it] = live ? u : make_uint4(0, 0, 0, 0);
   }
+}
+
+// RMSNorm across heads (Wan: attn.norm_q / norm_k = RMSNorm(heads*head_dim), rectified_wan21_attn.py:423-426): one warp
+// per source row computes rsqrt(mean(x^2) + eps) over all H*128 channels.  Order (replicated by the oracle): lane l
+// runs one fma chain over its columns 8(l + 32 j) .. +7, j = 0, 1, ..; then a butterfly over the lanes.
+__global__ void __launch_bounds__(256) row_rms_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
+                                                      int64_t qsb, int64_t qst, int64_t ksb, int64_t kst, int rows,
+                                                      int inner, float eps, float* __restrict__ rq, float* __restrict__ rk) {
+  const int row = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  const int b = blockIdx.y, which = blockIdx.z;
+  if (row >= rows) return;
+  const __nv_bfloat16* x = which ? k + b * ksb + (int64_t)row * kst : q + b * qsb + (int64_t)row * qst;
+  float ss = 0.f;
+  for (int c0 = 8 * lane; c0 < inner; c0 += 256) {
+    float f[8];
+    unpack8(__ldg(reinterpret_cast<const uint4*>(x + c0)), f);
+#pragma unroll
+    for (int c = 0; c < 8; ++c) ss = __fmaf_rn(f[c], f[c], ss);
+  }
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
+  if (lane == 0) (which ? rk : rq)[(int64_t)b * rows + row] = rsqrtf(__fadd_rn(__fdiv_rn(ss, (float)inner), eps));
 }
 
 template <bool kPrep, int kMinBlocks = 2>
@@ -352,6 +382,19 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
   }
   pa.w[0] = p->norm ? (const __nv_bfloat16*)p->q_weight : nullptr;
   pa.w[1] = p->norm ? (const __nv_bfloat16*)p->k_weight : nullptr;
+  pa.w_head_stride = p->norm == 2 ? 128 : 0;
+  pa.row_rinv[0] = pa.row_rinv[1] = nullptr;
+  if (p->norm == 2) {
+    float* rq = p->row_scratch;
+    float* rk = rq + (int64_t)d->batch * p->rows;
+    dim3 g((p->rows + 7) / 8, d->batch, 2);
+    row_rms_kernel<<<g, 256, 0, s>>>((const __nv_bfloat16*)q_src, (const __nv_bfloat16*)k_src, p->src_stride[0][0],
+                                     p->src_stride[0][1], p->src_stride[1][0], p->src_stride[1][1], p->rows,
+                                     d->heads * 128, p->eps, rq, rk);
+    RSA_CUDA_CHECK(cudaGetLastError());
+    pa.row_rinv[0] = rq;
+    pa.row_rinv[1] = rk;
+  }
   pa.eps = p->eps;
   pa.cos = p->cos;
   pa.sin = p->sin;

@@ -94,6 +94,41 @@ def rms_params(mod):
     return w, float(eps)
 
 
+def wan_rms_params(mod, heads):
+    """(weight, eps) if `mod` is an RMSNorm over all heads*128 channels with a bf16 weight (Wan norm_q / norm_k)."""
+    w, eps = getattr(mod, "weight", None), getattr(mod, "eps", None)
+    if mod is None or w is None or eps is None or getattr(mod, "bias", None) is not None:
+        return None
+    if "RMSNorm" not in type(mod).__name__ or w.dtype != torch.bfloat16 or w.numel() != heads * 128 or not w.is_cuda:
+        return None
+    return w, float(eps)
+
+
+_wan_rope_cache = {}
+
+
+def wan_rope_tables(emb, n):
+    """fp32 (cos, sin) [n, 128] tables from either Wan rotary form: Wan2.1's complex `freqs` [1, 1, S, 64]
+    (rectified_wan21_attn.py:433-438) or Wan2.2's (freqs_cos, freqs_sin) [1, S, 1, 128] (rectified_wan22_attn.py:52-64,
+    which reads cos[..., 0::2] and sin[..., 1::2]).  Cached per tensor: the tables are constants of a generation."""
+    key = tuple((t.data_ptr(), tuple(t.shape), t._version) for t in (emb if isinstance(emb, (tuple, list)) else (emb,)))
+    hit = _wan_rope_cache.get(key)
+    if hit is not None:
+        return hit
+    if isinstance(emb, torch.Tensor) and emb.is_complex() and emb.shape[-1] == 64 and emb.shape[-2] >= n:
+        f = emb.reshape(-1, 64)[-emb.shape[-2]:][:n]
+        cos, sin = f.real.float().repeat_interleave(2, dim=1), f.imag.float().repeat_interleave(2, dim=1)
+    elif isinstance(emb, (tuple, list)) and len(emb) == 2 and all(t.shape[-1] == 128 and t.numel() >= n * 128 for t in emb):
+        c, s_ = (t.reshape(-1, 128)[:n].float() for t in emb)
+        cos, sin = c[:, 0::2].repeat_interleave(2, dim=1), s_[:, 1::2].repeat_interleave(2, dim=1)
+    else:
+        return None
+    if len(_wan_rope_cache) > 8:
+        _wan_rope_cache.clear()
+    _wan_rope_cache[key] = (cos.contiguous(), sin.contiguous())
+    return _wan_rope_cache[key]
+
+
 def rope_tables(emb, n):
     """(cos, sin) fp32 [>= n, 128] tables as diffusers passes them (`image_rotary_emb`), or None if `emb` has another form."""
     if not (isinstance(emb, (tuple, list)) and len(emb) == 2):
@@ -195,6 +230,36 @@ class WanProcessorBase(ProcessorBase):
     def sparse_now(self) -> bool:
         raise NotImplementedError
 
+    def _fused(self, attn, hidden_states, rotary_emb, enc_img):
+        """Kernel 0 form of the middle section (reference rectified_wan21_attn.py:419-470): projections -> RMSNorm across
+        heads + rotary embedding + head split + pooling in one pass -> kernels 3a-4.  None when the layer does not have
+        the shape kernel 0 fuses."""
+        from rsa_b200 import geometry as G
+        from rsa_b200 import ops
+        heads = attn.heads
+        if not hidden_states.is_cuda or hidden_states.dtype != torch.bfloat16:
+            return None
+        nq_, nk_ = wan_rms_params(getattr(attn, "norm_q", None), heads), wan_rms_params(getattr(attn, "norm_k", None), heads)
+        if nq_ is None or nk_ is None or nq_[1] != nk_[1]:
+            return None
+        b, s, _ = hidden_states.shape
+        rope = None
+        if rotary_emb is not None:
+            rope = wan_rope_tables(rotary_emb, s)
+            if rope is None:
+                return None
+        src = [f(hidden_states) for f in (attn.to_q, attn.to_k, attn.to_v)]
+        if src[0].shape[2] != heads * 128:
+            return None
+        q, k, v = (torch.empty(b, heads, s, 128, dtype=torch.bfloat16, device=hidden_states.device) for _ in range(3))
+        plan = ops.Plan(q, k, v, G.wan(s, self.first_frame_blocks), self.select_block_num, self.p_remain_rates,
+                        self.block_neighbor_list)
+        plan.qkv_prep(*src, dst_row=0, q_weight=nq_[0], k_weight=nk_[0], eps=nq_[1], rope=rope)
+        out = plan.run_pooled().view(b, s, heads * 128)
+        if enc_img is not None:
+            out = out + image_cross_attention(attn, q, enc_img)
+        return out
+
     def __call__(self, attn, hidden_states: torch.Tensor, encoder_hidden_states: Optional[torch.Tensor] = None,
                  attention_mask: Optional[torch.Tensor] = None, rotary_emb=None) -> torch.Tensor:
         from .attn import fullattn
@@ -203,6 +268,11 @@ class WanProcessorBase(ProcessorBase):
         enc_img, encoder_hidden_states = split_wan_context(attn, encoder_hidden_states)
         if encoder_hidden_states is None:
             encoder_hidden_states = hidden_states
+        if self.mode == "sparse" and self.sparse_now() and self.fuse_prep and encoder_hidden_states is hidden_states:
+            fused = self._fused(attn, hidden_states, rotary_emb, enc_img)
+            if fused is not None:
+                self._tick()
+                return attn.to_out[1](attn.to_out[0](fused))
         query = attn.to_q(hidden_states)
         key = attn.to_k(encoder_hidden_states)
         value = attn.to_v(encoder_hidden_states)

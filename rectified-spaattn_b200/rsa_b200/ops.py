@@ -201,10 +201,17 @@ class Plan:
             if q_weight is None or k_weight is None:
                 raise RuntimeError("both norm weights are needed")
             ws_ = [w.detach().to(device=self.device, dtype=torch.bfloat16).contiguous() for w in (q_weight, k_weight)]
-            if any(w.numel() != d for w in ws_):
-                raise RuntimeError("RMSNorm weights must have head_dim elements")
+            if all(w.numel() == d for w in ws_):
+                p.norm = 1                                  # RMSNorm over head_dim
+            elif all(w.numel() == h * d for w in ws_):
+                p.norm = 2                                  # RMSNorm across heads (Wan)
+                scratch = torch.empty(2 * b * rows, dtype=torch.float32, device=self.device)
+                keep.append(scratch)
+                p.row_scratch = scratch.data_ptr()
+            else:
+                raise RuntimeError("RMSNorm weights must have head_dim or heads*head_dim elements")
             keep += ws_
-            p.norm, p.eps = 1, float(eps)
+            p.eps = float(eps)
             p.q_weight, p.k_weight = ws_[0].data_ptr(), ws_[1].data_ptr()
         if rope is not None:
             cos, sin = (t.detach().to(device=self.device, dtype=torch.float32).contiguous() for t in rope)

@@ -222,6 +222,49 @@ size_t rsa_host_call_scratch_bytes(const rsa_attn_desc* d, int heads_per_chunk);
 int rsa_rectified_attention_host(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
                                  int heads_per_chunk, void* device_scratch, size_t scratch_bytes, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------
+ * Peer memory (one process per GPU on one NVSwitch box).  rsa_peer_alloc returns zero-filled device memory that can
+ * be exported to the other ranks (CUDA IPC): rsa_peer_export fills a 64-byte handle to send through any host channel
+ * (torch.distributed.all_gather_object in rsa_b200/parallel.py), rsa_peer_open maps a received handle and returns a
+ * device pointer valid in this process.  Used by the fused Ulysses exchange below; the reference has no counterpart
+ * (it never splits one attention call over GPUs). */
+#define RSA_PEER_HANDLE_BYTES 64
+#define RSA_MAX_PEERS 8
+int rsa_peer_alloc(size_t bytes, void** ptr);
+int rsa_peer_free(void* ptr);
+int rsa_peer_export(const void* ptr, void* handle64);
+int rsa_peer_open(const void* handle64, void** ptr);
+int rsa_peer_close(void* ptr);
+
+/* Fused Ulysses exchange (sequence-parallel host model; SURVEY 8e "fusion target", 8f rank 3).  Every rank owns
+ * rows_per_rank consecutive tokens of all heads_total heads before the attention and must own the same tokens of the
+ * result after it; in between, rank r computes heads [r*H, (r+1)*H) (H = desc->heads) over ALL tokens.  Instead of two
+ * all-to-alls around the call,
+ *   rsa_qkv_prep_gather      kernel 0 reads each token's projection rows straight from the owning rank's peer-mapped
+ *                            buffer over NVLink (head split + norm + rotary embedding + re-layout + pooling as usual),
+ *   rsa_rectified_attention_pooled_scatter   kernel 4's epilogue stores each output row straight into the owning
+ *                            rank's result buffer.
+ * The caller provides the barriers: every rank's sources written before the gather, every rank's scatter finished
+ * before the results are read (a zero-byte collective on the stream; rsa_b200/parallel.py uses an all_reduce of one
+ * element).  Restrictions: seq == n_ranks * rows_per_rank, block-aligned visual segment, prep norm 0 or 1. */
+typedef struct rsa_peer_route {
+  int32_t n_ranks, rank;
+  int32_t rows_per_rank;
+  int32_t heads_total;          /* n_ranks * desc->heads                                                          */
+  const void* const* src_table; /* DEVICE array [3][n_ranks] (q, k, v): every rank's projection output,           */
+                                /* [batch, rows_per_rank, heads_total*128] bf16, as mapped in THIS process          */
+  int64_t src_stride[2];        /* (batch, token) element strides of those buffers                                 */
+  void* const* out_table;       /* DEVICE array [n_ranks]: every rank's result buffer [batch, rows_per_rank,       */
+                                /* heads_total, 128] bf16, as mapped in this process                               */
+  int64_t out_stride[2];        /* (batch, token) element strides of those buffers                                 */
+} rsa_peer_route;
+
+int rsa_qkv_prep_gather(const rsa_prep_desc* p, const rsa_attn_desc* d, const rsa_peer_route* route, void* q, void* k,
+                        void* v, int pool, void* workspace, size_t workspace_bytes, void* stream);
+int rsa_rectified_attention_pooled_scatter(const rsa_attn_desc* d, const void* q, const void* k, const void* v,
+                                           const rsa_peer_route* route, void* workspace, size_t workspace_bytes,
+                                           void* stream);
+
 /* Kernel 4 alone on a caller-supplied dense block mask (bytes, [BH, n_q_blocks, n_kv_blocks]) -- the literal
  * surface of _triton_block_sparse_attention_onehot(q, k, v, seqlens, block_mask, sm_scale) (wan21 :108-117).
  * q/k/v/out are [BH, seq, 128] with the given token strides; R = 1, C = 0.  workspace must hold

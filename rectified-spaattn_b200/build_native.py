@@ -15,7 +15,7 @@ OBJ_DIR = os.path.join(HERE, "build")
 LIB = os.path.join(OUT_DIR, "librsa_b200.so")
 
 SOURCES = ["rsa_api.cu", "gilbert.cc", "permute.cu", "pool_stats.cu", "block_scores.cu", "block_select.cu",
-           "rect_c.cu", "attn_mma.cu", "attn_tc5.cu", "host_call.cu"]
+           "rect_c.cu", "attn_mma.cu", "attn_tc5.cu", "host_call.cu", "peer.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 FLAGS = ARCH + ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "-I", os.path.join(REPO, "include"),

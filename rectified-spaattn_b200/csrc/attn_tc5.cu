@@ -430,7 +430,14 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const int mrow = tile < a.nq_vis ? grow : grow - a.gap;       // row in memory
       const bool store = tile < a.nq_vis ? grow < min(a.vis_len, a.seq_q) : mrow < a.seq_q;
       const bool zero = grow >= a.q_valid;
-      __nv_bfloat16* orow = a.o + b * a.os[0] + h * a.os[1] + (int64_t)mrow * a.os[2];
+      __nv_bfloat16* orow;
+      if (a.o_table == nullptr) {
+        orow = a.o + b * a.os[0] + h * a.os[1] + (int64_t)mrow * a.os[2];
+      } else {  // fused Ulysses scatter: the row belongs to rank mrow / peer_rows; store into its buffer over NVLink
+        const int owner = store ? mrow / a.peer_rows : 0;  // rows that are not stored must not index past the table
+        orow = a.o_table[owner] + b * a.peer_os[0] +
+               (int64_t)(mrow - owner * a.peer_rows) * a.peer_os[1] + (a.peer_head0 + h) * 128;
+      }
       if (cnt > 0) {
         mbar_wait(bar(B_OFULL + s), 0);
         tc_fence_after();

@@ -43,6 +43,9 @@ struct PrepArgs {
   int dst_row0;                 // memory row of source row 0 in the destination
   int blk0;                     // padded-layout block of source row 0
   int pool;                     // also pool the produced rows
+  // fused Ulysses gather: source row r lives on rank r / src_rows (peer-mapped buffers), head h is head src_head0 + h there
+  const __nv_bfloat16* const* src_table;  // device array [3][n_src] or nullptr
+  int n_src, src_rows, src_head0;
 };
 
 struct PoolArgs {
@@ -69,6 +72,12 @@ __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
   }
 }
 
+__device__ __forceinline__ uint4 ld_global_v4(const void* p) {
+  uint4 r;
+  asm volatile("ld.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+  return r;
+}
+
 // Kernel 0 front end: rows of one 128-token block of one head, normalised / rotated / rounded to bf16, stored to the
 // destination and returned in the same register layout the pooling sweep uses.  All eight source rows of a thread are
 // requested before the first is used, and the rotary-table row of step it + 1 is requested before step it is
@@ -93,11 +102,26 @@ __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, i
   const __nv_bfloat16* src = p.src[which] + b * p.src_stride[which][0] + (int64_t)h * 128 + col;
   __nv_bfloat16* dst = p.dst[which] + b * p.dst_stride[which][0] + h * p.dst_stride[which][1] + col;
   const int r0 = jblk * 128 + 16 * warp + (lane >> 4);  // source row of step 0; the 16 lanes of a half-warp share it
+  if (p.src_table == nullptr) {
 #pragma unroll
-  for (int it = 0; it < 8; ++it) {
-    const int r = r0 + 2 * it;
-    raw[it] = make_uint4(0, 0, 0, 0);
-    if (r < p.rows) raw[it] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * p.src_stride[which][1]));
+    for (int it = 0; it < 8; ++it) {
+      const int r = r0 + 2 * it;
+      raw[it] = make_uint4(0, 0, 0, 0);
+      if (r < p.rows) raw[it] = __ldg(reinterpret_cast<const uint4*>(src + (int64_t)r * p.src_stride[which][1]));
+    }
+  } else {
+    // each row comes from the rank that owns it, over NVLink
+    const int64_t off = b * p.src_stride[which][0] + (int64_t)(p.src_head0 + h) * 128 + col;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int r = r0 + 2 * it;
+      raw[it] = make_uint4(0, 0, 0, 0);
+      if (r < p.rows) {
+        const int owner = r / p.src_rows;
+        const __nv_bfloat16* base = p.src_table[which * p.n_src + owner];
+        raw[it] = ld_global_v4(base + off + (int64_t)(r - owner * p.src_rows) * p.src_stride[which][1]);
+      }
+    }
   }
   if (which == 2) {  // V: re-layout only
 #pragma unroll
@@ -366,7 +390,8 @@ int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, cons
 }
 
 int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* q_src, const void* k_src,
-                    const void* v_src, void* q, void* k, void* v, char* ws, const WsLayout* L, cudaStream_t s) {
+                    const void* v_src, const rsa_peer_route* route, void* q, void* k, void* v, char* ws,
+                    const WsLayout* L, cudaStream_t s) {
   const RowMap rm = row_map(d);
   PrepArgs pa;
   pa.src[0] = (const __nv_bfloat16*)q_src, pa.src[1] = (const __nv_bfloat16*)k_src, pa.src[2] = (const __nv_bfloat16*)v_src;
@@ -404,6 +429,18 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
   // destination row -> block of the padded layout: visual rows start block 0, text rows start block nq_vis
   pa.blk0 = p->dst_row == 0 ? 0 : rm.nq_vis;
   pa.pool = L != nullptr;
+  pa.src_table = nullptr;
+  pa.n_src = pa.src_rows = pa.src_head0 = 0;
+  if (route) {
+    pa.src_table = (const __nv_bfloat16* const*)route->src_table;
+    pa.n_src = route->n_ranks;
+    pa.src_rows = route->rows_per_rank;
+    pa.src_head0 = route->rank * d->heads;
+    for (int t = 0; t < 3; ++t) {
+      pa.src_stride[t][0] = route->src_stride[0];
+      pa.src_stride[t][1] = route->src_stride[1];
+    }
+  }
   PoolArgs a;
   if (L) {
     a = pool_args(d, q, k, v, ws, *L);

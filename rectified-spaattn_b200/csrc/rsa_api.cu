@@ -145,6 +145,9 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->pair_shared = (int32_t*)(ws + L.off_pshared);
   a->R = (const float*)(ws + L.off_R);
   a->C = (const float*)(ws + L.off_C);
+  a->o_table = nullptr;
+  a->peer_rows = a->peer_head0 = 0;
+  a->peer_os[0] = a->peer_os[1] = 0;
   a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.4426950408889634);
   a->dbg = g_attention_dbg;
   a->dbg_flags = g_attention_dbg_flags;
@@ -409,7 +412,64 @@ extern "C" int rsa_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, cons
   if (p->rope_rows > 0 && (((uintptr_t)p->cos % 16) || ((uintptr_t)p->sin % 16))) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: rotary tables must be 16-byte aligned");
   WsLayout L;
   if (pool && (rc = check_ws(d, workspace, bytes, &L)) != RSA_OK) return rc;
-  return launch_qkv_prep(p, d, q_src, k_src, v_src, q, k, v, (char*)workspace, pool ? &L : nullptr, (cudaStream_t)stream);
+  return launch_qkv_prep(p, d, q_src, k_src, v_src, nullptr, q, k, v, (char*)workspace, pool ? &L : nullptr,
+                         (cudaStream_t)stream);
+}
+
+static int validate_route(const rsa_attn_desc* d, const rsa_peer_route* r, bool need_src, bool need_out) {
+  if (!r) RSA_FAIL(RSA_ERR_ARG, "peer route is null");
+  if (r->n_ranks < 1 || r->n_ranks > RSA_MAX_PEERS || r->rank < 0 || r->rank >= r->n_ranks)
+    RSA_FAIL(RSA_ERR_ARG, "peer route: rank %d of %d", r->rank, r->n_ranks);
+  if (r->rows_per_rank < 1 || (int64_t)r->rows_per_rank * r->n_ranks != d->seq)
+    RSA_FAIL(RSA_ERR_ARG, "peer route: %d ranks x %d rows != seq %d", r->n_ranks, r->rows_per_rank, d->seq);
+  if (r->heads_total != r->n_ranks * d->heads) RSA_FAIL(RSA_ERR_ARG, "peer route: heads_total != n_ranks * heads");
+  if (row_map(d).gap != 0) RSA_FAIL(RSA_ERR_UNSUPPORTED, "peer route: ragged visual segments are not supported");
+  if (need_src && (!r->src_table || r->src_stride[0] < 0 || r->src_stride[1] < r->heads_total * 128 || r->src_stride[0] % 8 || r->src_stride[1] % 8))
+    RSA_FAIL(RSA_ERR_ARG, "peer route: source table / strides");
+  if (need_out && (!r->out_table || r->out_stride[0] < 0 || r->out_stride[1] < r->heads_total * 128 || r->out_stride[0] % 8 || r->out_stride[1] % 8))
+    RSA_FAIL(RSA_ERR_ARG, "peer route: result table / strides");
+  return RSA_OK;
+}
+
+extern "C" int rsa_qkv_prep_gather(const rsa_prep_desc* p, const rsa_attn_desc* d, const rsa_peer_route* route,
+                                   void* q, void* k, void* v, int pool, void* workspace, size_t bytes, void* stream) {
+  int rc = validate_desc(d);
+  if (rc != RSA_OK) return rc;
+  if ((rc = validate_route(d, route, true, false)) != RSA_OK) return rc;
+  if (!p || !q || !k || !v) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: null pointer");
+  if (p->rows != d->seq || p->dst_row != 0) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rows must be seq and dst_row 0");
+  if (p->norm != 0 && p->norm != 1) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep_gather: norm must be 0 or 1");
+  if (p->norm && (!p->q_weight || !p->k_weight)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: norm weights are null");
+  if (p->rope_rows < 0 || p->rope_rows > p->rows) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rope_rows out of range");
+  if (p->rope_rows > 0 && (!p->cos || !p->sin)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rotary tables are null");
+  WsLayout L;
+  if (pool && (rc = check_ws(d, workspace, bytes, &L)) != RSA_OK) return rc;
+  return launch_qkv_prep(p, d, nullptr, nullptr, nullptr, route, q, k, v, (char*)workspace, pool ? &L : nullptr,
+                         (cudaStream_t)stream);
+}
+
+extern "C" int rsa_rectified_attention_pooled_scatter(const rsa_attn_desc* d, const void* q, const void* k,
+                                                      const void* v, const rsa_peer_route* route, void* workspace,
+                                                      size_t bytes, void* stream) {
+  WsLayout L;
+  int rc = check_ws(d, workspace, bytes, &L);
+  if (rc != RSA_OK) return rc;
+  if ((rc = validate_route(d, route, false, true)) != RSA_OK) return rc;
+  if (!q || !k || !v) RSA_FAIL(RSA_ERR_ARG, "rsa_rectified_attention_pooled_scatter: null tensor");
+  if (g_attention_impl != 0) RSA_FAIL(RSA_ERR_UNSUPPORTED, "the scatter epilogue exists in the tcgen05 kernel only");
+  char* ws = (char*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  if ((rc = launch_block_scores(d, ws, L, s)) != RSA_OK) return rc;
+  if ((rc = launch_block_select(d, ws, L, s)) != RSA_OK) return rc;
+  if ((rc = launch_rect_c(d, ws, L, s)) != RSA_OK) return rc;
+  AttnArgs a;
+  fill_attn_args(d, q, k, v, nullptr, ws, L, &a);
+  a.o_table = (__nv_bfloat16* const*)route->out_table;
+  a.peer_rows = route->rows_per_rank;
+  a.peer_head0 = route->rank * d->heads;
+  a.peer_os[0] = route->out_stride[0];
+  a.peer_os[1] = route->out_stride[1];
+  return launch_attention(a, s);
 }
 
 extern "C" int rsa_rectified_attention_pooled(const rsa_attn_desc* d, const void* q, const void* k, const void* v,
@@ -486,6 +546,9 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   a.pair_shared = pshared;
   a.R = nullptr;
   a.C = nullptr;
+  a.o_table = nullptr;
+  a.peer_rows = a.peer_head0 = 0;
+  a.peer_os[0] = a.peer_os[1] = 0;
   a.scale_log2 = (float)((1.0 / sqrt(128.0)) * 1.4426950408889634);
   a.dbg = g_attention_dbg;
   a.dbg_flags = g_attention_dbg_flags;

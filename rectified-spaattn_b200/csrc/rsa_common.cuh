@@ -64,7 +64,8 @@ int check_ws(const rsa_attn_desc* d, const void* ws, size_t bytes, WsLayout* out
 int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, const void* v, char* ws,
                       const WsLayout& L, cudaStream_t s);
 int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* q_src, const void* k_src,
-                    const void* v_src, void* q, void* k, void* v, char* ws, const WsLayout* L, cudaStream_t s);
+                    const void* v_src, const rsa_peer_route* route, void* q, void* k, void* v, char* ws,
+                    const WsLayout* L, cudaStream_t s);
 int launch_block_scores(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);
 int launch_block_select(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);
 int launch_rect_c(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);
@@ -89,6 +90,9 @@ struct AttnArgs {
   int32_t* pair_shared;     // [bh, ceil(nqt/2)]
   const float* R;           // [bh, nqt]  or nullptr (=1)
   const float* C;           // [bh, nqt, 128] or nullptr (=0)
+  __nv_bfloat16* const* o_table;  // fused Ulysses scatter: result buffer of every rank (device array) or nullptr
+  int peer_rows, peer_head0;      // tokens per rank; first head of this rank inside a token of the result buffers
+  int64_t peer_os[2];             // (batch, token) element strides of the result buffers
   float scale_log2;         // head_dim^-0.5 * log2(e)
   int dbg_flags;            // bring-up ablations (rsa_debug_set_attention_flags), only read by the debug kernel
   float* dbg;               // bring-up dump of tile 0 / bh 0 (rsa_debug_set_attention_dump), normally null

@@ -47,13 +47,21 @@ class PrepDesc(C.Structure):
                 ("row_scratch", C.c_void_p)]
 
 
+class PeerRoute(C.Structure):
+    _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("rows_per_rank", C.c_int32), ("heads_total", C.c_int32),
+                ("src_table", C.c_void_p), ("src_stride", C.c_int64 * 2), ("out_table", C.c_void_p),
+                ("out_stride", C.c_int64 * 2)]
+
+
 EXPORTS = [
     "rsa_last_error_string", "rsa_version", "rsa_device_ok", "rsa_gilbert_map", "rsa_gilbert_block_neighbors",
     "rsa_permute_rows", "rsa_attn_workspace_bytes", "rsa_attn_workspace_view", "rsa_pool_stats",
     "rsa_block_scores", "rsa_block_select", "rsa_rect_c", "rsa_sparse_attention", "rsa_rectified_attention",
     "rsa_masked_attention_workspace_bytes", "rsa_masked_attention", "rsa_set_attention_impl",
     "rsa_debug_set_attention_dump", "rsa_debug_set_attention_flags", "rsa_host_call_scratch_bytes",
-    "rsa_rectified_attention_host", "rsa_qkv_prep", "rsa_rectified_attention_pooled",
+    "rsa_rectified_attention_host", "rsa_qkv_prep", "rsa_rectified_attention_pooled", "rsa_peer_alloc",
+    "rsa_peer_free", "rsa_peer_export", "rsa_peer_open", "rsa_peer_close", "rsa_qkv_prep_gather",
+    "rsa_rectified_attention_pooled_scatter",
 ]
 
 _lib = None
@@ -92,6 +100,14 @@ def lib():
     L.rsa_rectified_attention_host.argtypes = [C.POINTER(AttnDesc), p, p, p, p, i32, p, sz, p]
     L.rsa_qkv_prep.argtypes = [C.POINTER(PrepDesc), C.POINTER(AttnDesc), p, p, p, p, p, p, i32, p, sz, p]
     L.rsa_rectified_attention_pooled.argtypes = [C.POINTER(AttnDesc), p, p, p, p, p, sz, p]
+    L.rsa_qkv_prep_gather.argtypes = [C.POINTER(PrepDesc), C.POINTER(AttnDesc), C.POINTER(PeerRoute), p, p, p, i32, p,
+                                      sz, p]
+    L.rsa_rectified_attention_pooled_scatter.argtypes = [C.POINTER(AttnDesc), p, p, p, C.POINTER(PeerRoute), p, sz, p]
+    L.rsa_peer_alloc.argtypes = [sz, C.POINTER(p)]
+    L.rsa_peer_free.argtypes = [p]
+    L.rsa_peer_export.argtypes = [p, p]
+    L.rsa_peer_open.argtypes = [p, C.POINTER(p)]
+    L.rsa_peer_close.argtypes = [p]
     L.rsa_set_attention_impl.argtypes = [i32]
     L.rsa_debug_set_attention_dump.argtypes = [p]
     L.rsa_debug_set_attention_dump.restype = None

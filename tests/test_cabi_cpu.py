@@ -151,3 +151,24 @@ def test_hot_path_refuses_cpu_tensors():
         ops.Plan(q, q, q, G.wan(1024), 2, 0.3)
     with pytest.raises(RuntimeError):
         ops.permute_rows(torch.zeros(1, 4, 8), torch.arange(4))
+
+
+def test_peer_route_validation():
+    """The gather / scatter entry points check the route before touching the device."""
+    lib = N.lib()
+    d = _desc(G.hunyuan(1280, 1224))
+    r = N.PeerRoute()
+    p = N.PrepDesc()
+    p.rows, p.dst_row = 1280, 0
+    r.n_ranks, r.rank, r.rows_per_rank, r.heads_total = 2, 0, 600, 4            # 2 x 600 != 1280
+    assert lib.rsa_qkv_prep_gather(C.byref(p), C.byref(d), C.byref(r), 16, 16, 16, 0, None, 0, None) == -1
+    assert b"rows" in lib.rsa_last_error_string()
+    r.rows_per_rank = 640
+    r.heads_total = 5                                                             # != n_ranks * heads
+    assert lib.rsa_qkv_prep_gather(C.byref(p), C.byref(d), C.byref(r), 16, 16, 16, 0, None, 0, None) == -1
+    r.heads_total = 4                                                             # tables still null
+    assert lib.rsa_qkv_prep_gather(C.byref(p), C.byref(d), C.byref(r), 16, 16, 16, 0, None, 0, None) == -1
+    assert b"table" in lib.rsa_last_error_string()
+    d2 = _desc(G.hunyuan(1256, 1200))                                             # ragged visual segment: refused
+    r.rows_per_rank = 628
+    assert lib.rsa_qkv_prep_gather(C.byref(p), C.byref(d2), C.byref(r), 16, 16, 16, 0, None, 0, None) in (-1, -2)

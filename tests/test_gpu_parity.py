@@ -546,3 +546,23 @@ def test_qkv_prep_wan_form(dev):
     for n in fused:
         assert torch.equal(fused[n].view(torch.int32), vw2[n].view(torch.int32)), n
     assert torch.equal(out_fused.view(torch.int16), out_sep.view(torch.int16))
+
+
+def test_fused_ulysses_two_gpus(dev):
+    """The fused Ulysses exchange (kernel 0 gathers over peer memory, kernel 4's epilogue scatters) on 2 GPUs of one box,
+    through torchrun: bit-identical to the NCCL all-to-all form on every rank and to the single-GPU call.  Skipped on a
+    single-GPU box (the driver's 1-GPU tier); tools/check_fused_ulysses.py is the same check run by hand on 2-8 GPUs."""
+    import json
+    import os
+    import subprocess
+    import sys
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    repo = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29577",
+                        os.path.join(repo, "tools", "check_fused_ulysses.py"), "c2"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["fused_equals_nccl_form_bitwise_all_ranks"] and line["fused_equals_single_gpu_bitwise_rank0"]

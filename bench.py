@@ -238,6 +238,8 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
+    # stdout carries exactly one JSON line: NCCL's own banner / debug output (it defaults to stdout) goes to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

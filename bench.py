@@ -234,7 +234,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-permute", action="store_true")
-    ap.add_argument("--host-chunk", type=int, default=2, help="heads per chunk of the pipelined host-buffer call")
+    ap.add_argument("--host-chunk", type=int, default=0,
+                    help="heads per chunk of the pipelined host-buffer call (0 = library default: 2, or 1 below 8 heads)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -379,7 +380,8 @@ def main():
     e2e = None
     if not args.no_e2e:
         call = entry_point(wp)
-        ops.HOST_HEADS_PER_CHUNK = args.host_chunk
+        ops.HOST_HEADS_PER_CHUNK = args.host_chunk or None
+        host_chunk = args.host_chunk or (2 if h_loc >= 8 else 1)
         hq, hk, hv = (x.cpu().pin_memory() for x in (q, k, v))
         ho = torch.empty((1, wp["s"], h_loc * 128), dtype=torch.bfloat16).pin_memory()
         dq_, dk_, dv_ = (torch.empty_like(x) for x in (q, k, v))
@@ -414,7 +416,7 @@ def main():
         e2e = {"value": wp["dense_flop_per_head"] * heads / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s",
                "ms_per_step": ms_e2e, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
                "path": f"public per-family entry point on pinned host tensors -> rsa_rectified_attention_host, "
-                       f"{args.host_chunk} head(s) per chunk, H2D | kernels | D2H on three streams",
+                       f"{host_chunk} head(s) per chunk, H2D | kernels | D2H on three streams",
                "ms_per_step_unpipelined": ms_serial,
                "h2d_only_ms": ms_h2d}
 

@@ -294,7 +294,7 @@ def _fill_desc(desc, shape, strides, geo, top_k, p_remain, nbr_dev, debug_dump_p
 
 
 _host_scratch = {}
-HOST_HEADS_PER_CHUNK = 2
+HOST_HEADS_PER_CHUNK = None   # None: 2 heads per chunk from 8 heads up, else 1 (a head-parallel rank may hold only 3)
 
 
 def rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfuse=False, heads_per_chunk=None,
@@ -325,7 +325,7 @@ def rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfus
     nbr_dev = _device_neighbors(nbr, device)
     desc = _fill_desc(N.AttnDesc(), (b, h, s, d), [_strides3(t) for t in (q, k, v, o4)], geo, top_k, p_remain,
                       nbr_dev)
-    hc = int(heads_per_chunk or HOST_HEADS_PER_CHUNK)
+    hc = int(heads_per_chunk or HOST_HEADS_PER_CHUNK or (2 if h >= 8 else 1))
     L = N.lib()
     need = L.rsa_host_call_scratch_bytes(C.byref(desc), hc)
     if need == 0:

@@ -192,6 +192,7 @@ typedef struct rsa_prep_desc {
   int64_t src_stride[3][2]; /* q, k, v sources [batch, rows, heads*128]: (batch, token) element strides        */
   int32_t norm;             /* 0 = none, 1 = RMSNorm over head_dim (HunyuanVideo, Flux), 2 = RMSNorm over all  */
                             /* heads*128 channels of a token (Wan2.1 / Wan2.2, rectified_wan21_attn.py:423-426)*/
+                            /* 3 = LayerNorm over head_dim with weight and bias (CogVideoX, cogvideo :452-455) */
   float eps;
   const void* q_weight;     /* DEVICE bf16 [128] (norm 1) or [heads*128] (norm 2): norm_q.weight               */
   const void* k_weight;     /* likewise norm_k.weight                                                          */
@@ -200,6 +201,8 @@ typedef struct rsa_prep_desc {
   const float* cos;         /* DEVICE fp32 [rope_rows, 128] (diffusers' repeat-interleaved cos table)          */
   const float* sin;
   float* row_scratch;       /* norm 2 only: DEVICE scratch of 2*batch*rows floats for the per-token statistics  */
+  const void* q_bias;       /* norm 3 only: DEVICE bf16 [128] (norm_q.bias)                                     */
+  const void* k_bias;
 } rsa_prep_desc;
 
 int rsa_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* q_src, const void* k_src,

@@ -283,8 +283,27 @@ def torch_prep_wan(x, heads, weight, eps, freqs):
     return x
 
 
+def torch_prep_cog(x, heads, weight, bias, eps, cos, sin, n_rope):
+    """rectified_cogvideo_attn.py:443-469: head split, torch.nn.LayerNorm(head_dim), rotary embedding on the video tokens."""
+    x = x.unflatten(2, (heads, -1)).transpose(1, 2)
+    x = torch.nn.functional.layer_norm(x, (x.shape[-1],), weight, bias, eps)
+    return torch_prep(x.transpose(1, 2).flatten(2), heads, None, eps, cos, sin, n_rope)
+
+
+def cog_prep_params():
+    g = torch.Generator().manual_seed(33)
+    w = [(1 + 0.1 * torch.randn(128, generator=g)).to(torch.bfloat16) for _ in range(2)]
+    b = [(0.05 * torch.randn(128, generator=g)).to(torch.bfloat16) for _ in range(2)]
+    return w, b
+
+
 def make_prep():
     src, wq, wk, cos, sin, n_rope = prep_inputs()
+    cw, cb = cog_prep_params()
+    qc = torch_prep_cog(src[0], 2, cw[0], cb[0], 1e-6, cos, sin, n_rope)
+    kc = torch_prep_cog(src[1], 2, cw[1], cb[1], 1e-6, cos, sin, n_rope)
+    np.savez_compressed(os.path.join(GOLD, "prep_cog.npz"), q=qc.contiguous().view(torch.int16).numpy(),
+                        k=kc.contiguous().view(torch.int16).numpy())
     # Wan form on the same sources: weights over the inner dim, rotary embedding on every token (complex, float64)
     g = torch.Generator().manual_seed(32)
     rows = src[0].shape[1]

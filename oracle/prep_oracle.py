@@ -58,6 +58,31 @@ def rms_norm(x, weight, eps):
     return bf16_round((xn * np.asarray(weight, np.float32)).astype(np.float32))
 
 
+def layer_norm(x, weight, bias, eps):
+    """torch.nn.LayerNorm(128) on bf16 values (CogVideoX norm_q / norm_k, rectified_cogvideo_attn.py:452-455): statistics
+    and affine in fp32, one rounding to bf16.  Kernel order: per lane a sequential sum of its 8 columns, a butterfly over
+    the 16 lanes; two-pass variance (fma chain of the centred values, same butterfly)."""
+    x = np.asarray(x, dtype=np.float32)
+    lanes = x.reshape(*x.shape[:-1], 16, 8)
+    sm = np.zeros(lanes.shape[:-1], dtype=np.float32)
+    for c in range(8):
+        sm = (sm + lanes[..., c]).astype(np.float32)
+    for o in (1, 2, 4, 8):
+        sm = (sm + sm[..., np.arange(16) ^ o]).astype(np.float32)
+    mean = (sm[..., 0] * np.float32(1.0 / 128.0)).astype(np.float32)
+    d = (lanes - mean[..., None, None]).astype(np.float32)
+    ss = np.zeros(lanes.shape[:-1], dtype=np.float32)
+    for c in range(8):
+        ss = _fma32(d[..., c], d[..., c], ss)
+    for o in (1, 2, 4, 8):
+        ss = (ss + ss[..., np.arange(16) ^ o]).astype(np.float32)
+    var = (ss[..., 0] * np.float32(1.0 / 128.0)).astype(np.float32)
+    rstd = (1.0 / np.sqrt(var.astype(np.float64) + np.float64(np.float32(eps)))).astype(np.float32)
+    t = (d.reshape(x.shape) * rstd[..., None]).astype(np.float32)
+    return bf16_round(_fma32(np.broadcast_to(np.asarray(weight, np.float32), x.shape), t,
+                             np.broadcast_to(np.asarray(bias, np.float32), x.shape)))
+
+
 def mean_square_row_kernel_order(x):
     """mean(x^2) over the last axis (heads*128 channels of a token) in row_rms_kernel's order: lane l of 32 runs one fma
     chain over columns 8(l + 32 j) .. +7 for j = 0, 1, ..; then a butterfly over the lanes (xor 1, 2, 4, 8, 16)."""
@@ -97,7 +122,7 @@ def rotary(x, cos, sin):
     return bf16_round((a + b).astype(np.float32))
 
 
-def prep(src, heads, weight=None, eps=1e-6, cos=None, sin=None, rope_rows=0):
+def prep(src, heads, weight=None, eps=1e-6, cos=None, sin=None, rope_rows=0, bias=None):
     """src [B, rows, heads*128] -> [B, heads, rows, 128] after head split, RMSNorm (if weight: [128] = per head as in
     HunyuanVideo / Flux, [heads*128] = across heads as in Wan, applied BEFORE the split) and rotary embedding on the
     first rope_rows tokens."""
@@ -107,7 +132,9 @@ def prep(src, heads, weight=None, eps=1e-6, cos=None, sin=None, rope_rows=0):
         src = rms_norm_across_heads(src, weight, eps)
         weight = None
     x = src.reshape(b, rows, heads, 128).transpose(0, 2, 1, 3)
-    if weight is not None:
+    if weight is not None and bias is not None:
+        x = layer_norm(x, weight, bias, eps)
+    elif weight is not None:
         x = rms_norm(x, weight, eps)
     if rope_rows:
         x = x.copy()

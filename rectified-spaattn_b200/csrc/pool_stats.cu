@@ -34,6 +34,8 @@ struct PrepArgs {
   __nv_bfloat16* dst[3];        // [B, H, S, 128] views
   int64_t dst_stride[3][3];     // (batch, head, token)
   const __nv_bfloat16* w[2];    // RMSNorm weights of q, k (bf16 [128], or [H*128] with w_head_stride = 128) or nullptr
+  const __nv_bfloat16* bias[2]; // LayerNorm biases of q, k (bf16 [128]) -- layer_norm only
+  int layer_norm;               // 1: LayerNorm over head_dim (CogVideoX: mean removed, bias added, one rounding)
   int w_head_stride;            // 0: one weight vector per tensor (norm over head_dim); 128: norm across heads (Wan)
   const float* row_rinv[2];     // norm across heads: rsqrt(mean(x^2) + eps) per (batch, source row), from row_rms_kernel
   float eps;
@@ -135,6 +137,8 @@ __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, i
   const bool normed = p.w[which] != nullptr;
   if (normed) unpack8(__ldg(reinterpret_cast<const uint4*>(p.w[which] + h * p.w_head_stride + col)), wgt);
   const float* rinv_rows = p.row_rinv[which] ? p.row_rinv[which] + (int64_t)b * p.rows : nullptr;
+  float bia[8];
+  if (normed && p.layer_norm) unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias[which] + col)), bia);
   RopeRow next = load_rope(p, r0, col, r0 < p.rows && r0 < p.rope_rows);
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
@@ -145,7 +149,32 @@ __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, i
     if (it < 7) next = load_rope(p, r + 2, col, r + 2 < p.rows && r + 2 < p.rope_rows);
     float f[8];
     unpack8(raw[it], f);
-    if (normed) {
+    if (normed && p.layer_norm) {
+      // torch.nn.LayerNorm(head_dim) on a bf16 tensor: statistics and affine in fp32, ONE rounding to bf16
+      // (cogvideo :452-455; two-pass variance, fixed butterfly order over the 16 lanes that share the row)
+      float sm = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) sm = __fadd_rn(sm, f[c]);
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) sm = __fadd_rn(sm, __shfl_xor_sync(0xffffffffu, sm, o));
+      const float mean = __fmul_rn(sm, 1.0f / 128.0f);
+      float ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 8; ++c) {
+        f[c] = __fsub_rn(f[c], mean);
+        ss = __fmaf_rn(f[c], f[c], ss);
+      }
+#pragma unroll
+      for (int o = 1; o < 16; o <<= 1) ss = __fadd_rn(ss, __shfl_xor_sync(0xffffffffu, ss, o));
+      const float rstd = rsqrtf(__fadd_rn(__fmul_rn(ss, 1.0f / 128.0f), p.eps));
+#pragma unroll
+      for (int c = 0; c < 8; c += 2) {
+        const float2 y = __bfloat1622float2(__floats2bfloat162_rn(__fmaf_rn(wgt[c], __fmul_rn(rstd, f[c]), bia[c]),
+                                                                  __fmaf_rn(wgt[c + 1], __fmul_rn(rstd, f[c + 1]), bia[c + 1])));
+        f[c] = y.x;
+        f[c + 1] = y.y;
+      }
+    } else if (normed) {
       float rinv;
       if (rinv_rows) {  // norm across heads: the row statistic was computed over all H*128 channels beforehand
         rinv = live ? __ldg(rinv_rows + r) : 0.f;
@@ -408,6 +437,9 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
   pa.w[0] = p->norm ? (const __nv_bfloat16*)p->q_weight : nullptr;
   pa.w[1] = p->norm ? (const __nv_bfloat16*)p->k_weight : nullptr;
   pa.w_head_stride = p->norm == 2 ? 128 : 0;
+  pa.layer_norm = p->norm == 3 ? 1 : 0;
+  pa.bias[0] = (const __nv_bfloat16*)p->q_bias;
+  pa.bias[1] = (const __nv_bfloat16*)p->k_bias;
   pa.row_rinv[0] = pa.row_rinv[1] = nullptr;
   if (p->norm == 2) {
     float* rq = p->row_scratch;

@@ -398,7 +398,9 @@ extern "C" int rsa_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, cons
   if (p->rows > d->seq - p->dst_row) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: %d rows do not fit behind row %d of %d", p->rows, p->dst_row, d->seq);
   if (pool && p->rows != room && !(p->dst_row == 0 && p->rows == d->seq && rm.gap == 0))
     RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: pooling needs whole segments (%d rows here, segment has %d)", p->rows, room);
-  if (p->norm < 0 || p->norm > 2) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: norm must be 0, 1 (RMSNorm over head_dim) or 2 (across heads)");
+  if (p->norm < 0 || p->norm > 3) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: norm must be 0, 1 (RMSNorm over head_dim), 2 (across heads) or 3 (LayerNorm)");
+  if (p->norm == 3 && (!p->q_bias || !p->k_bias || (uintptr_t)p->q_bias % 16 || (uintptr_t)p->k_bias % 16))
+    RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: norm 3 needs 16-byte aligned biases");
   if (p->norm == 2 && (!p->row_scratch || (uintptr_t)p->row_scratch % 4)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: norm 2 needs row_scratch (2*batch*rows floats)");
   if (p->norm && (!p->q_weight || !p->k_weight)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: norm weights are null");
   if (p->rope_rows < 0 || p->rope_rows > p->rows) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: rope_rows out of range");

@@ -129,6 +129,20 @@ def wan_rope_tables(emb, n):
     return _wan_rope_cache[key]
 
 
+def head_norm_params(mod):
+    """dict(q_weight-style kwargs) for a per-head norm kernel 0 fuses: RMSNorm(128) (HunyuanVideo / Flux) or
+    LayerNorm(128) with bias (CogVideoX), bf16 parameters; else None.  Returns (weight, bias or None, eps)."""
+    r = rms_params(mod)
+    if r is not None:
+        return r[0], None, r[1]
+    w, b, eps = getattr(mod, "weight", None), getattr(mod, "bias", None), getattr(mod, "eps", None)
+    if mod is None or w is None or b is None or eps is None or "LayerNorm" not in type(mod).__name__:
+        return None
+    if w.dtype != torch.bfloat16 or b.dtype != torch.bfloat16 or w.numel() != 128 or b.numel() != 128 or not w.is_cuda:
+        return None
+    return w, b, float(eps)
+
+
 def rope_tables(emb, n):
     """(cos, sin) fp32 [>= n, 128] tables as diffusers passes them (`image_rotary_emb`), or None if `emb` has another form."""
     if not (isinstance(emb, (tuple, list)) and len(emb) == 2):
@@ -149,15 +163,20 @@ def fused_prep_attention(attn, hidden_states, encoder_hidden_states, geo, top_k,
     if not hidden_states.is_cuda or hidden_states.dtype != torch.bfloat16:
         return None
     dual = getattr(attn, "add_q_proj", None) is not None and encoder_hidden_states is not None
-    nq_, nk_ = rms_params(getattr(attn, "norm_q", None)), rms_params(getattr(attn, "norm_k", None))
-    if nq_ is None or nk_ is None or nq_[1] != nk_[1]:
-        return None
-    ne = None
-    if dual:
-        eq_, ek_ = rms_params(getattr(attn, "norm_added_q", None)), rms_params(getattr(attn, "norm_added_k", None))
-        if eq_ is None or ek_ is None or eq_[1] != ek_[1]:
+    def pair(nq, nk):
+        a, c = head_norm_params(getattr(attn, nq, None)), head_norm_params(getattr(attn, nk, None))
+        if a is None or c is None or a[2] != c[2] or (a[1] is None) != (c[1] is None):
             return None
-        ne = (eq_[0], ek_[0], eq_[1])
+        return dict(q_weight=a[0], k_weight=c[0], q_bias=a[1], k_bias=c[1], eps=a[2])
+
+    lat_norm = pair("norm_q", "norm_k")
+    if lat_norm is None:
+        return None
+    enc_norm = None
+    if dual:
+        enc_norm = pair("norm_added_q", "norm_added_k")
+        if enc_norm is None:
+            return None
     b, s = hidden_states.shape[0], geo.seq
     nv = geo.vis_len or geo.nq_blocks * 128
     rope = None
@@ -175,20 +194,18 @@ def fused_prep_attention(attn, hidden_states, encoder_hidden_states, geo, top_k,
         enc = [f(encoder_hidden_states) for f in (attn.add_q_proj, attn.add_k_proj, attn.add_v_proj)]
         if lat[0].shape[1] != nv or enc[0].shape[1] != s - nv:
             return None
-        plan.qkv_prep(*lat, dst_row=0, q_weight=nq_[0], k_weight=nk_[0], eps=nq_[1], rope=cut(rope, 0, nv))
-        plan.qkv_prep(*enc, dst_row=nv, q_weight=ne[0], k_weight=ne[1], eps=ne[2],
-                      rope=cut(rope, nv, s) if rope_text else None)
+        plan.qkv_prep(*lat, dst_row=0, rope=cut(rope, 0, nv), **lat_norm)
+        plan.qkv_prep(*enc, dst_row=nv, rope=cut(rope, nv, s) if rope_text else None, **enc_norm)
     else:
         if lat[0].shape[1] != s:
             return None
         n_rope = 0 if rope is None else (s if rope_text else nv)
         if geo.gap:     # ragged visual segment: the two segments are separate block ranges
-            plan.qkv_prep(*(t[:, :nv] for t in lat), dst_row=0, q_weight=nq_[0], k_weight=nk_[0], eps=nq_[1],
-                          rope=cut(rope, 0, nv))
-            plan.qkv_prep(*(t[:, nv:] for t in lat), dst_row=nv, q_weight=nq_[0], k_weight=nk_[0], eps=nq_[1],
-                          rope=cut(rope, nv, s) if rope_text else None)
+            plan.qkv_prep(*(t[:, :nv] for t in lat), dst_row=0, rope=cut(rope, 0, nv), **lat_norm)
+            plan.qkv_prep(*(t[:, nv:] for t in lat), dst_row=nv, rope=cut(rope, nv, s) if rope_text else None,
+                          **lat_norm)
         else:
-            plan.qkv_prep(*lat, dst_row=0, q_weight=nq_[0], k_weight=nk_[0], eps=nq_[1], rope=rope, rope_rows=n_rope)
+            plan.qkv_prep(*lat, dst_row=0, rope=rope, rope_rows=n_rope, **lat_norm)
     return plan.run_pooled().view(b, s, heads * 128)
 
 

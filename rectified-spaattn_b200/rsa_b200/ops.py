@@ -180,7 +180,7 @@ class Plan:
         return self.out
 
     def qkv_prep(self, q_src, k_src, v_src, dst_row=0, q_weight=None, k_weight=None, eps=1e-6, rope=None,
-                 rope_rows=None, pool=True):
+                 rope_rows=None, pool=True, q_bias=None, k_bias=None):
         """Kernel 0: fills rows [dst_row, dst_row + rows) of this plan's q, k, v from projection outputs
         [B, rows, H*128] (head split, per-head RMSNorm with bf16 weights, rotary embedding on the first `rope_rows`
         tokens, re-layout) and, with pool=True, the pooled statistics of those blocks."""
@@ -201,7 +201,13 @@ class Plan:
             if q_weight is None or k_weight is None:
                 raise RuntimeError("both norm weights are needed")
             ws_ = [w.detach().to(device=self.device, dtype=torch.bfloat16).contiguous() for w in (q_weight, k_weight)]
-            if all(w.numel() == d for w in ws_):
+            if q_bias is not None or k_bias is not None:    # LayerNorm over head_dim (CogVideoX)
+                bs_ = [x.detach().to(device=self.device, dtype=torch.bfloat16).contiguous() for x in (q_bias, k_bias)]
+                if any(w.numel() != d for w in ws_ + bs_):
+                    raise RuntimeError("LayerNorm weights and biases must have head_dim elements")
+                keep += bs_
+                p.norm, p.q_bias, p.k_bias = 3, bs_[0].data_ptr(), bs_[1].data_ptr()
+            elif all(w.numel() == d for w in ws_):
                 p.norm = 1                                  # RMSNorm over head_dim
             elif all(w.numel() == h * d for w in ws_):
                 p.norm = 2                                  # RMSNorm across heads (Wan)

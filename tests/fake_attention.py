@@ -12,8 +12,14 @@ class FakeAttention(nn.Module):
         self.heads = heads
         self.is_cross_attention = False
         self.to_q, self.to_k, self.to_v = (nn.Linear(dim, inner) for _ in range(3))
-        nd = head_dim if norm == "head" else inner          # Hunyuan/Flux/Cog norm per head; Wan over the inner dim
-        self.norm_q, self.norm_k = nn.RMSNorm(nd, eps=1e-6), nn.RMSNorm(nd, eps=1e-6)
+        nd = inner if norm == "inner" else head_dim         # Hunyuan/Flux/Cog norm per head; Wan over the inner dim
+        if norm == "layer":                                  # CogVideoX: LayerNorm(head_dim) with bias
+            self.norm_q, self.norm_k = nn.LayerNorm(nd, eps=1e-6), nn.LayerNorm(nd, eps=1e-6)
+            for m in (self.norm_q, self.norm_k):
+                nn.init.normal_(m.weight, 1.0, 0.1)
+                nn.init.normal_(m.bias, 0.0, 0.05)
+        else:
+            self.norm_q, self.norm_k = nn.RMSNorm(nd, eps=1e-6), nn.RMSNorm(nd, eps=1e-6)
         self.add_q_proj = self.add_k_proj = self.add_v_proj = None
         self.norm_added_q = self.norm_added_k = None
         self.to_add_out = None

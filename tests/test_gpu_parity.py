@@ -566,3 +566,26 @@ def test_fused_ulysses_two_gpus(dev):
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert line["fused_equals_nccl_form_bitwise_all_ranks"] and line["fused_equals_single_gpu_bitwise_rank0"]
+
+
+def test_qkv_prep_cogvideo_form(dev):
+    """Kernel 0, CogVideoX form: LayerNorm(head_dim) with weight and bias + rotary embedding on the video tokens, against
+    the oracle and torch.nn.functional.layer_norm on the GPU."""
+    from oracle import make_golden as MG
+    from oracle import prep_oracle as P
+    from rsa_b200 import geometry as G
+    from rsa_b200 import ops
+    src, _, _, cos, sin, n_rope = MG.prep_inputs()
+    cw, cb = MG.cog_prep_params()
+    rows = src[0].shape[1]
+    q, k, v = (torch.zeros(1, 2, rows, 128, dtype=torch.bfloat16, device=dev) for _ in range(3))
+    plan = ops.Plan(q, k, v, G.wan(rows), 1, 0.3, None)
+    plan.qkv_prep(*(t.to(dev) for t in src), q_weight=cw[0], k_weight=cw[1], q_bias=cb[0], k_bias=cb[1], eps=1e-6,
+                  rope=(cos, sin), pool=False)
+    torch.cuda.synchronize()
+    for i, (name, got) in enumerate((("q", q), ("k", k))):
+        want = P.prep(src[i].float().numpy(), 2, cw[i].float().numpy(), 1e-6, cos.numpy(), sin.numpy(), n_rope,
+                      bias=cb[i].float().numpy())
+        tref = MG.torch_prep_cog(src[i].to(dev), 2, cw[i].to(dev), cb[i].to(dev), 1e-6, cos.to(dev), sin.to(dev), n_rope)
+        assert_prep_close(got.float().cpu().numpy(), want, f"{name} vs oracle")
+        assert_prep_close(got.float().cpu().numpy(), tref.float().cpu().numpy(), f"{name} vs torch on GPU")

@@ -174,3 +174,20 @@ def test_prep_oracle_wan_form(gold_dir):
         got = P.prep(x.float().numpy(), 2, w.float().numpy(), 1e-6, cos.numpy(), sin.numpy(), x.shape[1])
         ref = torch.from_numpy(g[name]).view(torch.bfloat16).float().numpy()
         assert_prep_close(got, ref, name)
+
+
+def test_prep_oracle_cogvideo_form(gold_dir):
+    """The CogVideoX form (LayerNorm over head_dim with bias, rotary embedding on the video tokens) against
+    torch.nn.functional.layer_norm + the apply_rotary_emb expression in bf16."""
+    import torch
+
+    from oracle import make_golden as MG
+    from oracle import prep_oracle as P
+    src, _, _, cos, sin, n_rope = MG.prep_inputs()
+    cw, cb = MG.cog_prep_params()
+    g = np.load(os.path.join(gold_dir, "prep_cog.npz"))
+    for i, name in enumerate(("q", "k")):
+        got = P.prep(src[i].float().numpy(), 2, cw[i].float().numpy(), 1e-6, cos.numpy(), sin.numpy(), n_rope,
+                     bias=cb[i].float().numpy())
+        ref = torch.from_numpy(g[name]).view(torch.bfloat16).float().numpy()
+        assert_prep_close(got, ref, name)

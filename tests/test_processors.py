@@ -202,3 +202,15 @@ def test_fused_prep_processors_match_unfused():
             _close(outs[0][1], outs[1][1])
         else:
             _close(outs[0], outs[1])
+    # CogVideoX: LayerNorm(head_dim) with bias, 226 text tokens (ragged end), sparse from call 5 on
+    attn = _mk(dev, dim, heads, norm="layer")
+    txt = torch.randn(1, 226, dim, device=dev).to(torch.bfloat16)
+    cos, sin, _ = _rope_tables(nv, 128, dev)
+    outs = []
+    for fuse in (True, False):
+        pr = cog.RectifiedCogVideoXVideoSpaAttnProcessor2_0("sparse", 99, None, 0.3)
+        pr.fuse_prep, pr.current_step = fuse, 5
+        with torch.no_grad():
+            outs.append(pr(attn, x, txt, None, (cos, sin)))
+    _close(outs[0][0], outs[1][0])
+    _close(outs[0][1], outs[1][1])

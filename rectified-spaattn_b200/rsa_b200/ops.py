@@ -116,7 +116,8 @@ def _strides3(t):
 class Plan:
     """One call's descriptor + workspace; build once per (shape, geometry) and reuse across layers/steps."""
 
-    def __init__(self, q, k, v, geo: G.BlockGeometry, top_k, p_remain, nbr=None, debug_dump_probs=False, out=None):
+    def __init__(self, q, k, v, geo: G.BlockGeometry, top_k, p_remain, nbr=None, debug_dump_probs=False, out=None,
+                 private_workspace=False):
         for t, n in ((q, "query"), (k, "key"), (v, "value")):
             _need_cuda(t, n)
             if t.dtype != torch.bfloat16:
@@ -141,7 +142,10 @@ class Plan:
         self.ws_bytes = L.rsa_attn_workspace_bytes(C.byref(desc))
         if self.ws_bytes == 0:
             raise N.RsaError("invalid attention descriptor: " + L.rsa_last_error_string().decode())
-        self.ws = _workspace(q.device, self.ws_bytes)
+        # one workspace per device is shared by short-lived plans (a call's stages run back to back on one stream);
+        # a plan that is kept across other calls (FusedUlysses) owns its own
+        self.ws = (torch.empty(self.ws_bytes, dtype=torch.uint8, device=q.device) if private_workspace
+                   else _workspace(q.device, self.ws_bytes))
         self.q, self.k, self.v = q, k, v
 
     # --- stages (each enqueues on the current stream; no host sync)

@@ -141,7 +141,7 @@ class FusedUlysses:
         self._flag = torch.zeros(1, device=self.device)
         q, k, v = (torch.empty(batch, self.heads, self.seq, 128, dtype=torch.bfloat16, device=self.device)
                    for _ in range(3))
-        self.plan = ops.Plan(q, k, v, geo, top_k, p_remain, nbr)
+        self.plan = ops.Plan(q, k, v, geo, top_k, p_remain, nbr, private_workspace=True)
         route = N.PeerRoute()
         route.n_ranks, route.rank, route.rows_per_rank, route.heads_total = self.world, self.rank, self.rows, heads_total
         route.src_table = self._table[:3].data_ptr()

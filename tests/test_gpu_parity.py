@@ -589,3 +589,24 @@ def test_qkv_prep_cogvideo_form(dev):
         tref = MG.torch_prep_cog(src[i].to(dev), 2, cw[i].to(dev), cb[i].to(dev), 1e-6, cos.to(dev), sin.to(dev), n_rope)
         assert_prep_close(got.float().cpu().numpy(), want, f"{name} vs oracle")
         assert_prep_close(got.float().cpu().numpy(), tref.float().cpu().numpy(), f"{name} vs torch on GPU")
+
+
+def test_peer_buffers_single_process(dev):
+    """CUDA IPC plumbing that does not need a second process: allocate, export a handle, wrap as a tensor, free."""
+    import ctypes as CT
+    from rsa_b200 import native as N
+    from rsa_b200 import parallel
+    L = N.lib()
+    ptr = CT.c_void_p()
+    N.check(L.rsa_peer_alloc(4096, CT.byref(ptr)), "rsa_peer_alloc")
+    h = (CT.c_char * 64)()
+    N.check(L.rsa_peer_export(ptr, h), "rsa_peer_export")
+    assert any(b != 0 for b in bytes(h))
+    t = parallel._peer_tensor(ptr.value, (2, 8, 128))
+    assert t.dtype == torch.bfloat16 and t.data_ptr() == ptr.value and float(t.float().abs().max()) == 0.0   # zero-filled
+    t.fill_(1.5)
+    torch.cuda.synchronize()
+    assert float(t.float().sum()) == 1.5 * 2048
+    del t
+    N.check(L.rsa_peer_free(ptr), "rsa_peer_free")
+    assert L.rsa_peer_alloc(0, CT.byref(ptr)) == -1

@@ -610,3 +610,36 @@ def test_peer_buffers_single_process(dev):
     del t
     N.check(L.rsa_peer_free(ptr), "rsa_peer_free")
     assert L.rsa_peer_alloc(0, CT.byref(ptr)) == -1
+
+
+@pytest.mark.parametrize("s,top_k,p", [(100, 1, 0.3), (128, 0, 0.0), (129, 1, 0.3), (700, 0, 0.0), (700, 2, 1.0),
+                                        (700, 99, 0.3)])
+def test_edge_geometries_wan(dev, s, top_k, p):
+    """Shapes and parameters at the edges of the Wan path against the oracle: a single partial block, exactly one block,
+    one token into the second block, top_k = 0 with p = 0 (one block per row + nothing else), p = 1 (every block by
+    threshold), top_k >= NB; with an all-False neighbour matrix, which must equal passing None (the scripts' commented
+    "linear settings")."""
+    from rsa_b200 import geometry as G
+    from rsa_b200 import ops
+    q, k, v = O.synth_qkv(2, s, 128, "walk", 40 + s)
+    nb = (s + 127) // 128
+    tq, tk, tv = (torch.from_numpy(x).to(dev).to(torch.bfloat16) for x in (q, k, v))
+    out = ops.rectified_attention(tq, tk, tv, G.wan(s), top_k, p, None).float().cpu().numpy()
+    out2 = ops.rectified_attention(tq, tk, tv, G.wan(s), top_k, p, torch.zeros(nb, nb, dtype=torch.bool)).float().cpu().numpy()
+    assert np.array_equal(out, out2)
+    ref = O.forward(q, k, v, O.geometry_wan(s, top_k, p, 0), None)
+    assert np.abs(out - ref).max() <= ATOL_OUT and cos_sim(out, ref) >= COS_OUT
+
+
+def test_edge_geometries_joint(dev):
+    """Joint family edges: a single visual block, one valid text token (a = 1), every text token valid, H = 1."""
+    from rsa_b200 import geometry as G
+    from rsa_b200 import ops
+    for nv, ntrue_d, heads in ((128, 1, 1), (128, 256, 2), (384, 1, 2)):
+        s = nv + 256
+        q, k, v = O.synth_qkv(heads, s, 128, "cluster", 60 + ntrue_d)
+        tq, tk, tv = (torch.from_numpy(x).to(dev).to(torch.bfloat16) for x in (q, k, v))
+        out = ops.rectified_attention(tq, tk, tv, G.hunyuan(s, nv + ntrue_d), 1, 0.3, None).float().cpu().numpy()
+        ref = O.forward(q, k, v, O.geometry_hunyuan(s, nv + ntrue_d, 1, 0.3), None)
+        assert np.abs(out - ref).max() <= ATOL_OUT and cos_sim(out, ref) >= COS_OUT, (nv, ntrue_d, heads)
+        assert np.all(out[0, nv + ntrue_d:] == 0)

@@ -336,6 +336,11 @@ def main():
                      ("block_select", plan.block_select), ("rect_c", plan.rect_c),
                      ("sparse_attention", plan.sparse_attention)):
         stages[name] = timed(fn, max(3, args.steps))
+    # mask re-use (off in the headline): the same call with the selection of the previous call kept
+    reuse = {"keep_lists_ms": timed(lambda: plan.run(native.MASK_KEEP_LISTS), max(3, args.steps // 2)),
+             "keep_all_ms": timed(lambda: plan.run(native.MASK_KEEP_ALL), max(3, args.steps // 2)),
+             "note": "rsa_rectified_attention_reuse on unchanged inputs: RSA_MASK_KEEP_LISTS skips 3b's sort/threshold/"
+                     "scatter and the pair schedule, RSA_MASK_KEEP_ALL runs kernel 4 only; ms_per_step rebuilds every call"}
     # kernel 1 (per transformer forward, not per attention call): Gilbert permute of the hidden states [1, Nv, 3072]
     hbm_kernels = None
     if rank == 0 and not args.no_permute:
@@ -435,6 +440,7 @@ def main():
             "unit": "TFLOP/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config, "ms_per_attn_call": ms_step, "kept_pair_density": density, "stages_ms": stages,
+            "mask_reuse": reuse,
             "attention_impl": "tcgen05" if args.attn_impl == 0 else "mma.sync cross-check",
             "gpu_launches": 6 * args.steps,
             "roofline": {"bound": "tensor", "kernel": "rect_attn (kernel 4)", "achieved": achieved,

@@ -163,6 +163,19 @@ int rsa_sparse_attention(const rsa_attn_desc* d, const void* q, const void* k, c
 int rsa_rectified_attention(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
                             void* workspace, size_t workspace_bytes, void* stream);
 
+/* Mask re-use across calls (the reference rebuilds its mask in every layer of every step,
+ * rectified_hunyuan_attn.py:334-346, although the selections of adjacent denoising steps are highly correlated).  The
+ * workspace of an earlier RSA_MASK_BUILD call on the same descriptor geometry is the cache:
+ *   RSA_MASK_BUILD       same as rsa_rectified_attention (pooled = 0) / rsa_rectified_attention_pooled (pooled = 1)
+ *   RSA_MASK_KEEP_LISTS  kernels 2 (unless pooled), 3a, 3b without its sort / threshold / scatter, 3c, 4: the kept-block
+ *                        lists (and the pair schedule) stay; P, the GAPR test, R and C are recomputed from the CURRENT
+ *                        q, k, v, so the rectification O = Os*R + C is exact for the cached selection
+ *   RSA_MASK_KEEP_ALL    kernel 4 only: lists, R and C of the earlier call are applied to the current q, k, v
+ * The caller decides when a cached selection is still good (same layer, adjacent step); nothing here checks it. */
+enum rsa_mask_mode { RSA_MASK_BUILD = 0, RSA_MASK_KEEP_LISTS = 1, RSA_MASK_KEEP_ALL = 2 };
+int rsa_rectified_attention_reuse(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out,
+                                  void* workspace, size_t workspace_bytes, int mask_mode, int pooled, void* stream);
+
 /* ------------------------------------------------------------------------------------------------------
  * Kernel 0: what the reference's processors do between the QKV projections and the attention call,
  * fused into one pass over the projection outputs: head split, per-head QK RMSNorm, rotary embedding, re-layout

@@ -37,6 +37,8 @@ struct SelectArgs {
   int nbr_rows, nbr_cols;
   int nq, nqt, nb, nkc, score_ld, nogapr_ld, n_ent, ent_ld, mask_words;
   int joint, top_k, first_frame_blocks, text_end_block, kv_blocks_valid;
+  int keep_lists;  // mask re-use: the kept-block bitmask / lists of an earlier call on this workspace stay as they are;
+                   // only P, R and W are recomputed from the current scores and GAPR bytes
   float p_remain, scale;
 };
 
@@ -198,6 +200,7 @@ __global__ void __launch_bounds__(kThreads) block_select_kernel(const SelectArgs
   const int64_t orow = (int64_t)bh * a.nqt + i;
 
   if (i >= a.nq) {
+    if (a.keep_lists) return;  // dense list, R = 1 and C = 0 are already in place
     // text query block: dense row (all valid KV blocks), R = 1, C = 0
     for (int w = tid; w < words; w += kThreads) {
       const int lo = w * 32;
@@ -251,6 +254,25 @@ __global__ void __launch_bounds__(kThreads) block_select_kernel(const SelectArgs
   if (a.probs) {
     float* prow = a.probs + ((int64_t)bh * nq + i) * a.ent_ld;
     for (int j = tid; j < n_ent; j += kThreads) prow[j] = s_p[j];
+  }
+
+  if (a.keep_lists) {
+    // ---- mask re-use: the selection of an earlier call stands; rectify it with the current P
+    for (int w = tid; w < words; w += kThreads) s_mask[w] = a.mask_bits[orow * words + w];
+    __syncthreads();
+    const uint8_t* grow = a.nogapr + ((int64_t)bh * nq + i) * a.nogapr_ld;
+    float* wrow = a.w_skip + ((int64_t)bh * nq + i) * a.ent_ld;
+    float lr = 0.f;
+    for (int j = tid; j < n_ent; j += kThreads) {
+      bool part = (s_mask[j >> 5] >> (j & 31)) & 1u;
+      if (j < nq && grow[j]) part = true;
+      const float p = s_p[j];
+      lr += part ? p : 0.f;
+      wrow[j] = part ? 0.f : p;
+    }
+    const float r = block_sum(lr, s_red);
+    if (tid == 0) a.R[orow] = r;
+    return;
   }
 
   // ---- sort the probabilities (descending); ties are resolved below by index, ascending
@@ -360,8 +382,9 @@ __global__ void __launch_bounds__(kThreads) block_select_kernel(const SelectArgs
 
 }  // namespace
 
-int launch_block_select(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s) {
+int launch_block_select(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s, bool keep_lists) {
   SelectArgs a;
+  a.keep_lists = keep_lists ? 1 : 0;
   a.scores = (const float*)(ws + L.off_scores);
   a.nogapr = (const uint8_t*)(ws + L.off_nogapr);
   a.probs = d->debug_dump_probs ? (float*)(ws + L.off_probs) : nullptr;

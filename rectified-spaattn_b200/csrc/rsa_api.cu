@@ -154,9 +154,11 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   return RSA_OK;
 }
 
-static int launch_attention(const AttnArgs& a, cudaStream_t s) {
+// reschedule = false: the kept lists have not changed since the last launch on this workspace, so neither has the
+// pair schedule kernel 4 walks (mask re-use)
+static int launch_attention(const AttnArgs& a, cudaStream_t s, bool reschedule = true) {
   if (g_attention_impl == 1) return launch_attention_mma(a, s);
-  int rc = launch_pair_schedule(a, s);
+  int rc = reschedule ? launch_pair_schedule(a, s) : RSA_OK;
   return rc != RSA_OK ? rc : launch_attention_tc5(a, s);
 }
 
@@ -488,6 +490,28 @@ extern "C" int rsa_rectified_attention_pooled(const rsa_attn_desc* d, const void
   AttnArgs a;
   fill_attn_args(d, q, k, v, out, ws, L, &a);
   return launch_attention(a, s);
+}
+
+extern "C" int rsa_rectified_attention_reuse(const rsa_attn_desc* d, const void* q, const void* k, const void* v,
+                                             void* out, void* workspace, size_t bytes, int mask_mode, int pooled,
+                                             void* stream) {
+  WsLayout L;
+  int rc = check_ws(d, workspace, bytes, &L);
+  if (rc != RSA_OK) return rc;
+  if (!q || !k || !v || !out) RSA_FAIL(RSA_ERR_ARG, "rsa_rectified_attention_reuse: null tensor");
+  if (mask_mode < RSA_MASK_BUILD || mask_mode > RSA_MASK_KEEP_ALL)
+    RSA_FAIL(RSA_ERR_ARG, "rsa_rectified_attention_reuse: mask_mode %d is not one of rsa_mask_mode", mask_mode);
+  char* ws = (char*)workspace;
+  cudaStream_t s = (cudaStream_t)stream;
+  if (mask_mode != RSA_MASK_KEEP_ALL) {
+    if (!pooled && (rc = launch_pool_stats(d, q, k, v, ws, L, s)) != RSA_OK) return rc;
+    if ((rc = launch_block_scores(d, ws, L, s)) != RSA_OK) return rc;
+    if ((rc = launch_block_select(d, ws, L, s, mask_mode == RSA_MASK_KEEP_LISTS)) != RSA_OK) return rc;
+    if ((rc = launch_rect_c(d, ws, L, s)) != RSA_OK) return rc;
+  }
+  AttnArgs a;
+  fill_attn_args(d, q, k, v, out, ws, L, &a);
+  return launch_attention(a, s, mask_mode == RSA_MASK_BUILD);
 }
 
 extern "C" size_t rsa_masked_attention_workspace_bytes(int bh, int nq, int nkv) {

@@ -67,7 +67,7 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
                     const void* v_src, const rsa_peer_route* route, void* q, void* k, void* v, char* ws,
                     const WsLayout* L, cudaStream_t s);
 int launch_block_scores(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);
-int launch_block_select(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);
+int launch_block_select(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s, bool keep_lists = false);
 int launch_rect_c(const rsa_attn_desc* d, char* ws, const WsLayout& L, cudaStream_t s);
 
 // Attention kernel arguments common to both implementations.  q/k/v/o are addressed as [bh][token][128].

@@ -20,8 +20,9 @@ def host_ints(t):
     return [int(x) for x in t]
 
 
-def run(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse):
-    return ops.rectified_attention(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse)
+def run(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse, mask_cache=None):
+    return ops.rectified_attention(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse,
+                                   mask_cache=mask_cache)
 
 
 def build_index(query, key, geo, top_k, prob_threshold, block_neighbor_list):

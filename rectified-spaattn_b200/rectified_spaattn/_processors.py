@@ -153,7 +153,7 @@ def rope_tables(emb, n):
 
 
 def fused_prep_attention(attn, hidden_states, encoder_hidden_states, geo, top_k, p_remain, nbr, image_rotary_emb,
-                         rope_text):
+                         rope_text, mask_cache=None):
     """The fused form of a joint-text processor's middle section (kernel 0 + kernels 3a-4): projections ->
     rsa_qkv_prep (head split, RMSNorm, RoPE, re-layout, pooling) -> rsa_rectified_attention_pooled.  Returns
     [B, S, H*D], or None when this layer does not have the shape kernel 0 fuses (the caller then runs the op-by-op path).
@@ -188,7 +188,7 @@ def fused_prep_attention(attn, hidden_states, encoder_hidden_states, geo, top_k,
     if lat[0].shape[2] != heads * 128:
         return None
     q, k, v = (torch.empty(b, heads, s, 128, dtype=torch.bfloat16, device=hidden_states.device) for _ in range(3))
-    plan = ops.Plan(q, k, v, geo, top_k, p_remain, nbr)
+    plan = ops.Plan(q, k, v, geo, top_k, p_remain, nbr, mask_cache=mask_cache)
     cut = lambda r, a, z: None if r is None else (r[0][a:z], r[1][a:z])
     if dual:
         enc = [f(encoder_hidden_states) for f in (attn.add_q_proj, attn.add_k_proj, attn.add_v_proj)]
@@ -226,10 +226,29 @@ class ProcessorBase:
         if not hasattr(F, "scaled_dot_product_attention"):
             raise ImportError(f"{type(self).__name__} requires PyTorch 2.0. To use it, please upgrade PyTorch to 2.0.")
 
+    # Extension, off by default: rebuild the block selection only every `mask_refresh_interval`-th
+    # sparse call of this layer and re-use it in between (`mask_keep` = "lists": R and C are still recomputed from the
+    # current tensors; "all": only kernel 4 runs).  1 = the reference's behaviour (a new mask per call).  The cache is
+    # dropped whenever `current_step` wraps, i.e. at the start of every generation.
+    mask_refresh_interval = 1
+    mask_keep = "lists"
+    _cache = None
+
+    def _mask_cache(self):
+        if self.mask_refresh_interval <= 1:
+            return None
+        c = self._cache
+        if c is None or c.refresh_every != self.mask_refresh_interval or c.keep != self.mask_keep:
+            from rsa_b200 import ops
+            c = self._cache = ops.MaskCache(self.mask_refresh_interval, self.mask_keep)
+        return c
+
     def _tick(self):
         self.current_step += 1
         if self.current_step == self.steps_per_cycle:
             self.current_step = 0
+            if self._cache is not None:
+                self._cache.reset()
 
 
 class WanProcessorBase(ProcessorBase):
@@ -270,7 +289,7 @@ class WanProcessorBase(ProcessorBase):
             return None
         q, k, v = (torch.empty(b, heads, s, 128, dtype=torch.bfloat16, device=hidden_states.device) for _ in range(3))
         plan = ops.Plan(q, k, v, G.wan(s, self.first_frame_blocks), self.select_block_num, self.p_remain_rates,
-                        self.block_neighbor_list)
+                        self.block_neighbor_list, mask_cache=self._mask_cache())
         plan.qkv_prep(*src, dst_row=0, q_weight=nq_[0], k_weight=nk_[0], eps=nq_[1], rope=rope)
         out = plan.run_pooled().view(b, s, heads * 128)
         if enc_img is not None:
@@ -313,7 +332,8 @@ class WanProcessorBase(ProcessorBase):
             hidden_states = rectified_block_sparse_attention(
                 query, key, value, attn_mask=attention_mask, top_k=self.select_block_num,
                 max_seqlen_q=query.shape[2], max_seqlen_kv=key.shape[2], block_neighbor_list=self.block_neighbor_list,
-                p_remain_rates=self.p_remain_rates, first_frame_blocks=self.first_frame_blocks)
+                p_remain_rates=self.p_remain_rates, first_frame_blocks=self.first_frame_blocks,
+                mask_cache=self._mask_cache())
         elif self.mode == "sparse":
             hidden_states = dense(fullattn, query, key, value, "flash", attention_mask, s_k)
         elif self.mode in ("flash", "torch", "vanilla"):

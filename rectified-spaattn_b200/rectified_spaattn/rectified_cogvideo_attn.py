@@ -24,19 +24,22 @@ def _build_block_index_with_importance_optimized(query, key, top_k, block_size_M
 
 def block_sparse_attention_combined(query, key, value, attn_mask, top_k, block_size_M=128, block_size_N=128,
                                     cu_seqlens_q=None, cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None,
-                                    prob_threshold=0.5, block_neighbor_list=None, text_length=256, shape_xfuse=False):
+                                    prob_threshold=0.5, block_neighbor_list=None, text_length=256, shape_xfuse=False,
+                                    mask_cache=None):
     _common.check_blocks(block_size_M, block_size_N)
     geo = _G.cogvideo(query.shape[2], int(text_length))
-    return _common.run(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse)
+    return _common.run(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse,
+                       mask_cache)
 
 
 def rectified_block_sparse_attention(query, key, value, attn_mask, top_k, block_size_M=128, block_size_N=128,
                                      cu_seqlens_q=None, cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None,
-                                     block_neighbor_list=None, shape_xfuse=False, p_remain_rates=0.5, text_length=256):
+                                     block_neighbor_list=None, shape_xfuse=False, p_remain_rates=0.5, text_length=256,
+                                     mask_cache=None):
     return block_sparse_attention_combined(
         query, key, value, attn_mask, top_k, block_size_M, block_size_N, cu_seqlens_q, cu_seqlens_kv,
         max_seqlen_q, max_seqlen_kv, block_neighbor_list=block_neighbor_list, shape_xfuse=shape_xfuse,
-        prob_threshold=p_remain_rates, text_length=text_length)
+        prob_threshold=p_remain_rates, text_length=text_length, mask_cache=mask_cache)
 
 
 from . import _processors as _P  # noqa: E402
@@ -59,7 +62,7 @@ class RectifiedCogVideoXVideoSpaAttnProcessor2_0(_P.ProcessorBase):
             # kernel 0: head split + LayerNorm + RoPE + pooling in one pass (reference :443-469), then kernels 3a-4
             fused = _P.fused_prep_attention(attn, hidden_states, None, _G.cogvideo(s, n_txt), self.select_block_num,
                                             self.p_remain_rates, self.block_neighbor_list, image_rotary_emb,
-                                            rope_text=False)
+                                            rope_text=False, mask_cache=self._mask_cache())
             if fused is not None:
                 self._tick()
                 hidden_states = attn.to_out[1](attn.to_out[0](fused))
@@ -80,7 +83,8 @@ class RectifiedCogVideoXVideoSpaAttnProcessor2_0(_P.ProcessorBase):
             hidden_states = rectified_block_sparse_attention(
                 query, key, value, attn_mask=attention_mask, top_k=self.select_block_num, cu_seqlens_q=cu,
                 cu_seqlens_kv=cu, max_seqlen_q=s, max_seqlen_kv=key.shape[2],
-                block_neighbor_list=self.block_neighbor_list, p_remain_rates=self.p_remain_rates, text_length=n_txt)
+                block_neighbor_list=self.block_neighbor_list, p_remain_rates=self.p_remain_rates, text_length=n_txt,
+                mask_cache=self._mask_cache())
         else:
             hidden_states = _P.dense(_fullattn, query, key, value, "flash", attention_mask, s_k)
         hidden_states = hidden_states.to(query.dtype)

@@ -21,21 +21,24 @@ def _build_block_index_with_importance_optimized(query, key, top_k, block_size_M
 
 def block_sparse_attention_combined(query, key, value, attn_mask, top_k, block_size_M=128, block_size_N=128,
                                     cu_seqlens_q=None, cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None,
-                                    prob_threshold=0.5, block_neighbor_list=None, text_length=256, shape_xfuse=False):
+                                    prob_threshold=0.5, block_neighbor_list=None, text_length=256, shape_xfuse=False,
+                                    mask_cache=None):
     _common.check_blocks(block_size_M, block_size_N)
     cu = _common.host_ints(cu_seqlens_kv)
     kv_len = cu[1] if cu is not None else None     # seqlens = cu_seqlens_kv[1:2]  (reference :307)
     geo = _G.flux(query.shape[2], int(text_length), kv_len)
-    return _common.run(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse)
+    return _common.run(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse,
+                       mask_cache)
 
 
 def rectified_block_sparse_attention(query, key, value, attn_mask, top_k, block_size_M=128, block_size_N=128,
                                      cu_seqlens_q=None, cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None,
-                                     block_neighbor_list=None, shape_xfuse=False, p_remain_rates=0.5, text_length=256):
+                                     block_neighbor_list=None, shape_xfuse=False, p_remain_rates=0.5, text_length=256,
+                                     mask_cache=None):
     return block_sparse_attention_combined(
         query, key, value, attn_mask, top_k, block_size_M, block_size_N, cu_seqlens_q, cu_seqlens_kv,
         max_seqlen_q, max_seqlen_kv, block_neighbor_list=block_neighbor_list, shape_xfuse=shape_xfuse,
-        prob_threshold=p_remain_rates, text_length=text_length)
+        prob_threshold=p_remain_rates, text_length=text_length, mask_cache=mask_cache)
 
 
 from . import _processors as _P  # noqa: E402
@@ -59,7 +62,7 @@ class RectifiedFluxSpaAttnProcessor2_0(_P.ProcessorBase):
             if s % 128 == 0 and s > self.text_length:
                 fused = _P.fused_prep_attention(attn, hidden_states, encoder_hidden_states, _G.flux(s, self.text_length),
                                                 self.select_block_num, self.p_remain_rates, self.block_neighbor_list,
-                                                image_rotary_emb, rope_text=True)
+                                                image_rotary_emb, rope_text=True, mask_cache=self._mask_cache())
             if fused is not None:
                 self._tick()
                 if encoder_hidden_states is None:
@@ -90,7 +93,8 @@ class RectifiedFluxSpaAttnProcessor2_0(_P.ProcessorBase):
                 query, key, value, attn_mask=attention_mask, top_k=self.select_block_num, cu_seqlens_q=cu,
                 cu_seqlens_kv=cu, max_seqlen_q=query.shape[2], max_seqlen_kv=key.shape[2],
                 block_neighbor_list=self.block_neighbor_list, p_remain_rates=self.p_remain_rates,
-                text_length=self.text_length)
+                text_length=self.text_length,
+                mask_cache=self._mask_cache())
         else:
             hidden_states = _P.dense(_fullattn, query, key, value, "flash", attention_mask, s_k)
         hidden_states = hidden_states.to(query.dtype)

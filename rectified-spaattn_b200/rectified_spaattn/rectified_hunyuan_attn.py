@@ -38,20 +38,23 @@ def _build_block_index_with_importance_optimized(query, key, top_k, block_size_M
 
 def block_sparse_attention_combined(query, key, value, attn_mask, top_k, block_size_M=128, block_size_N=128,
                                     cu_seqlens_q=None, cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None,
-                                    prob_threshold=0.5, block_neighbor_list=None, shape_xfuse=False, num_true=None):
+                                    prob_threshold=0.5, block_neighbor_list=None, shape_xfuse=False, num_true=None,
+                                    mask_cache=None):
     _common.check_blocks(block_size_M, block_size_N)
     geo = _geometry(query.shape[2], cu_seqlens_q, num_true)
-    return _common.run(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse)
+    return _common.run(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse,
+                       mask_cache)
 
 
 def rectified_block_sparse_attention(query, key, value, attn_mask, top_k, block_size_M=128, block_size_N=128,
                                      cu_seqlens_q=None, cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None,
-                                     block_neighbor_list=None, shape_xfuse=False, p_remain_rates=0.5, num_true=None):
+                                     block_neighbor_list=None, shape_xfuse=False, p_remain_rates=0.5, num_true=None,
+                                     mask_cache=None):
     """`num_true` (host int) is an optional extension: it avoids reading cu_seqlens_q back from the device."""
     return block_sparse_attention_combined(
         query, key, value, attn_mask, top_k, block_size_M, block_size_N, cu_seqlens_q, cu_seqlens_kv,
         max_seqlen_q, max_seqlen_kv, block_neighbor_list=block_neighbor_list, shape_xfuse=shape_xfuse,
-        prob_threshold=p_remain_rates, num_true=num_true)
+        prob_threshold=p_remain_rates, num_true=num_true, mask_cache=mask_cache)
 
 
 from . import _processors as _P  # noqa: E402
@@ -76,7 +79,7 @@ class RectifiedHunyuanVideoSpaAttnProcessor2_0(_P.ProcessorBase):
             fused = _P.fused_prep_attention(attn, hidden_states, None if single_stream else encoder_hidden_states,
                                             _G.hunyuan(s, int(num_true), encoder_hidden_states.shape[1]),
                                             self.select_block_num, self.p_remain_rates, self.block_neighbor_list,
-                                            image_rotary_emb, rope_text=False)
+                                            image_rotary_emb, rope_text=False, mask_cache=self._mask_cache())
             if fused is not None:
                 n_txt = encoder_hidden_states.shape[1]
                 hidden_states, encoder_hidden_states = fused[:, :-n_txt], fused[:, -n_txt:]
@@ -113,7 +116,8 @@ class RectifiedHunyuanVideoSpaAttnProcessor2_0(_P.ProcessorBase):
             hidden_states = rectified_block_sparse_attention(
                 query, key, value, attn_mask=attention_mask, top_k=self.select_block_num, max_seqlen_q=s,
                 max_seqlen_kv=s, block_neighbor_list=self.block_neighbor_list, p_remain_rates=self.p_remain_rates,
-                num_true=num_true)
+                num_true=num_true,
+                mask_cache=self._mask_cache())
         elif self.mode in ("flash", "torch", "vanilla"):
             cu = [0, num_true, s]
             hidden_states = fullattn(query, key, value, mode=self.mode, drop_rate=0.0, attn_mask=attention_mask,

@@ -47,22 +47,25 @@ def _build_block_index_with_importance_optimized(query, key, top_k, block_size_M
 def block_sparse_attention_combined(query, key, value, attn_mask, top_k, block_size_M=128, block_size_N=128,
                                     cu_seqlens_q=None, cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None,
                                     prob_threshold=0.5, block_neighbor_list=None, shape_xfuse=False,
-                                    first_frame_blocks=None):
+                                    first_frame_blocks=None,
+                                    mask_cache=None):
     """[B,H,S,D] -> [B,S,H*D] ([B,S,H,D] if shape_xfuse).  S need not be a multiple of 128: the kernels treat
     the ragged tail as the zero rows the reference pads with (:299-302)."""
     _common.check_blocks(block_size_M, block_size_N)
     geo = _G.wan(query.shape[2], first_frame_blocks or 0)
-    return _common.run(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse)
+    return _common.run(query, key, value, geo, top_k, prob_threshold, block_neighbor_list, shape_xfuse,
+                       mask_cache)
 
 
 def rectified_block_sparse_attention(query, key, value, attn_mask, top_k, block_size_M=128, block_size_N=128,
                                      cu_seqlens_q=None, cu_seqlens_kv=None, max_seqlen_q=None, max_seqlen_kv=None,
                                      block_neighbor_list=None, shape_xfuse=False, p_remain_rates=0.5,
-                                     first_frame_blocks=None):
+                                     first_frame_blocks=None,
+                                     mask_cache=None):
     return block_sparse_attention_combined(
         query, key, value, attn_mask, top_k, block_size_M, block_size_N, cu_seqlens_q, cu_seqlens_kv,
         max_seqlen_q, max_seqlen_kv, block_neighbor_list=block_neighbor_list, shape_xfuse=shape_xfuse,
-        prob_threshold=p_remain_rates, first_frame_blocks=first_frame_blocks)
+        prob_threshold=p_remain_rates, first_frame_blocks=first_frame_blocks, mask_cache=mask_cache)
 
 
 from . import _processors as _P  # noqa: E402

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "librsa_b200.so")
 
 RSA_OK = 0
 FAMILY_WAN, FAMILY_JOINT = 0, 1
+MASK_BUILD, MASK_KEEP_LISTS, MASK_KEEP_ALL = 0, 1, 2   # enum rsa_mask_mode
 BLOCK = 128
 
 
@@ -61,7 +62,7 @@ EXPORTS = [
     "rsa_debug_set_attention_dump", "rsa_debug_set_attention_flags", "rsa_host_call_scratch_bytes",
     "rsa_rectified_attention_host", "rsa_qkv_prep", "rsa_rectified_attention_pooled", "rsa_peer_alloc",
     "rsa_peer_free", "rsa_peer_export", "rsa_peer_open", "rsa_peer_close", "rsa_qkv_prep_gather",
-    "rsa_rectified_attention_pooled_scatter",
+    "rsa_rectified_attention_pooled_scatter", "rsa_rectified_attention_reuse",
 ]
 
 _lib = None
@@ -100,6 +101,7 @@ def lib():
     L.rsa_rectified_attention_host.argtypes = [C.POINTER(AttnDesc), p, p, p, p, i32, p, sz, p]
     L.rsa_qkv_prep.argtypes = [C.POINTER(PrepDesc), C.POINTER(AttnDesc), p, p, p, p, p, p, i32, p, sz, p]
     L.rsa_rectified_attention_pooled.argtypes = [C.POINTER(AttnDesc), p, p, p, p, p, sz, p]
+    L.rsa_rectified_attention_reuse.argtypes = [C.POINTER(AttnDesc), p, p, p, p, p, sz, i32, i32, p]
     L.rsa_qkv_prep_gather.argtypes = [C.POINTER(PrepDesc), C.POINTER(AttnDesc), C.POINTER(PeerRoute), p, p, p, i32, p,
                                       sz, p]
     L.rsa_rectified_attention_pooled_scatter.argtypes = [C.POINTER(AttnDesc), p, p, p, C.POINTER(PeerRoute), p, sz, p]

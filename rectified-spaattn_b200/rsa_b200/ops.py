@@ -117,7 +117,7 @@ class Plan:
     """One call's descriptor + workspace; build once per (shape, geometry) and reuse across layers/steps."""
 
     def __init__(self, q, k, v, geo: G.BlockGeometry, top_k, p_remain, nbr=None, debug_dump_probs=False, out=None,
-                 private_workspace=False):
+                 private_workspace=False, mask_cache=None):
         for t, n in ((q, "query"), (k, "key"), (v, "value")):
             _need_cuda(t, n)
             if t.dtype != torch.bfloat16:
@@ -144,8 +144,15 @@ class Plan:
             raise N.RsaError("invalid attention descriptor: " + L.rsa_last_error_string().decode())
         # one workspace per device is shared by short-lived plans (a call's stages run back to back on one stream);
         # a plan that is kept across other calls (FusedUlysses) owns its own
-        self.ws = (torch.empty(self.ws_bytes, dtype=torch.uint8, device=q.device) if private_workspace
-                   else _workspace(q.device, self.ws_bytes))
+        self.mask_mode = N.MASK_BUILD
+        if mask_cache is not None:    # the cache owns the workspace (it survives this plan) and says what to re-use
+            # the neighbour matrix is a constant of the latent grid: identified by the caller's storage, not its bytes
+            key = (self.shape, geo, int(top_k), float(p_remain),
+                   None if nbr is None else (nbr.data_ptr(), tuple(nbr.shape), nbr._version))
+            self.mask_mode, self.ws = mask_cache.next_mode(key, q.device, self.ws_bytes)
+        else:
+            self.ws = (torch.empty(self.ws_bytes, dtype=torch.uint8, device=q.device) if private_workspace
+                       else _workspace(q.device, self.ws_bytes))
         self.q, self.k, self.v = q, k, v
 
     # --- stages (each enqueues on the current stream; no host sync)
@@ -172,16 +179,35 @@ class Plan:
                    self.out.data_ptr())
         return self.out
 
-    def run(self):
-        self._call("rsa_rectified_attention", self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(),
-                   self.out.data_ptr())
+    def run(self, mask_mode=None):
+        """The whole call.  mask_mode (enum rsa_mask_mode; default: what the plan's MaskCache asked for, else
+        MASK_BUILD): MASK_KEEP_LISTS / MASK_KEEP_ALL re-use the selection an earlier MASK_BUILD run left in this
+        plan's workspace (which must then be private or owned by a MaskCache)."""
+        mask_mode = self.mask_mode if mask_mode is None else mask_mode
+        if mask_mode == N.MASK_BUILD:
+            self._call("rsa_rectified_attention", self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(),
+                       self.out.data_ptr())
+        else:
+            self._reuse(mask_mode, 0)
         return self.out
 
-    def run_pooled(self):
+    def run_pooled(self, mask_mode=None):
         """Kernels 3a-4 on the pooled statistics qkv_prep(..., pool=True) left in this plan's workspace."""
-        self._call("rsa_rectified_attention_pooled", self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(),
-                   self.out.data_ptr())
+        mask_mode = self.mask_mode if mask_mode is None else mask_mode
+        if mask_mode == N.MASK_BUILD:
+            self._call("rsa_rectified_attention_pooled", self.q.data_ptr(), self.k.data_ptr(), self.v.data_ptr(),
+                       self.out.data_ptr())
+        else:
+            self._reuse(mask_mode, 1)
         return self.out
+
+    def _reuse(self, mask_mode, pooled):
+        L = N.lib()
+        with torch.cuda.device(self.device):
+            N.check(L.rsa_rectified_attention_reuse(C.byref(self.desc), self.q.data_ptr(), self.k.data_ptr(),
+                                                    self.v.data_ptr(), self.out.data_ptr(), self.ws.data_ptr(),
+                                                    self.ws_bytes, int(mask_mode), int(pooled), _stream(self.device)),
+                    "rsa_rectified_attention_reuse")
 
     def qkv_prep(self, q_src, k_src, v_src, dst_row=0, q_weight=None, k_weight=None, eps=1e-6, rope=None,
                  rope_rows=None, pool=True, q_bias=None, k_bias=None):
@@ -352,13 +378,52 @@ def rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfus
     return out if shape_xfuse else out.view(b, s, h * d)
 
 
-def rectified_attention(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfuse=False):
+class MaskCache:
+    """Block selection kept across calls: one per attention layer.  The reference rebuilds its
+    mask in every layer of every denoising step (rectified_hunyuan_attn.py:334-346); with a cache the selection is
+    rebuilt every `refresh_every`-th call and re-used in between -- `keep="lists"`: P, the GAPR test, R and C are still
+    recomputed from the current tensors (RSA_MASK_KEEP_LISTS), `keep="all"`: only kernel 4 runs (RSA_MASK_KEEP_ALL).
+    The cache IS the call's workspace (kept lists, pair schedule, R, C), owned here instead of shared per device.
+    refresh_every = 1 is the reference's behaviour."""
+
+    def __init__(self, refresh_every=1, keep="lists"):
+        if keep not in ("lists", "all"):
+            raise ValueError("keep must be 'lists' or 'all'")
+        self.refresh_every = max(1, int(refresh_every))
+        self.keep = keep
+        self.calls = 0
+        self._ws = None
+        self._key = None
+
+    def reset(self):
+        """Forget the cached selection (new prompt / new generation)."""
+        self.calls = 0
+        self._key = None
+
+    def next_mode(self, key, device, ws_bytes):
+        """(mask_mode, workspace) for the next call whose geometry is `key`."""
+        fresh = self._key != key or self._ws is None or self._ws.device != device or self._ws.numel() < ws_bytes
+        if fresh:
+            if self._ws is None or self._ws.device != device or self._ws.numel() < ws_bytes:
+                self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
+            self._key = key
+            self.calls = 0
+        mode = N.MASK_BUILD
+        if self.calls % self.refresh_every != 0:
+            mode = N.MASK_KEEP_LISTS if self.keep == "lists" else N.MASK_KEEP_ALL
+        self.calls += 1
+        return mode, self._ws
+
+
+def rectified_attention(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfuse=False, mask_cache=None):
     """[B,H,S,D] bf16 -> [B,S,H*D] (or [B,S,H,D] with shape_xfuse) -- the reference's return layout
     (rectified_wan21_attn.py:353-357).  Host (pinned) tensors take the pipelined host-buffer entry point and come
-    back as a pinned host tensor; the arithmetic runs on the GPU either way."""
+    back as a pinned host tensor; the arithmetic runs on the GPU either way.  mask_cache: an optional MaskCache."""
     if isinstance(q, torch.Tensor) and not q.is_cuda and torch.cuda.is_available():
+        if mask_cache is not None:
+            raise RuntimeError("mask re-use needs device-resident tensors (the host-buffer call owns no lasting workspace)")
         return rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr, shape_xfuse)
-    out = Plan(q, k, v, geo, top_k, p_remain, nbr).run()
+    out = Plan(q, k, v, geo, top_k, p_remain, nbr, mask_cache=mask_cache).run()
     b, s, h, d = out.shape
     return out if shape_xfuse else out.view(b, s, h * d)
 

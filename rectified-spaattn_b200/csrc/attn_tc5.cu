@@ -236,7 +236,9 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (s == 0) st_v0 = st, par_v0 = par;
             const bool release = !(s == 0 && r - 1 < nsh);  // the last user frees the stage
             const uint64_t vd = smem_desc_sw128(sbase + kOffRing + st * 2 * kGranule, kGranule);
+            RSA_TRACE(dbg && s == 0 && leader, r - 1, 10);
             mbar_wait(bar(B_KVFULL + st), par);
+            RSA_TRACE(dbg && s == 0 && leader, r - 1, 13);
             mbar_wait(bar(B_PHALF + 2 * s), (r - 1) & 1);
             tc_fence_after();
             RSA_TRACE(dbg && s == 0 && leader, r - 1, 9);
@@ -266,6 +268,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const uint64_t kd = smem_desc_sw128(sbase + kOffRing + st * 2 * kGranule);
             const uint64_t qd = smem_desc_sw128(sbase + kOffQ + 2 * s * kGranule);
             if (r == 0) mbar_wait(bar(B_QFULL + s), 0);
+            RSA_TRACE(dbg && s == 0 && leader, r, 14);
             mbar_wait(bar(B_KVFULL + st), par);
             tc_fence_after();
             RSA_TRACE(dbg && s == 0 && leader, r, 12);

@@ -643,3 +643,28 @@ def test_edge_geometries_joint(dev):
         ref = O.forward(q, k, v, O.geometry_hunyuan(s, nv + ntrue_d, 1, 0.3), None)
         assert np.abs(out - ref).max() <= ATOL_OUT and cos_sim(out, ref) >= COS_OUT, (nv, ntrue_d, heads)
         assert np.all(out[0, nv + ntrue_d:] == 0)
+
+
+# ------------------------------------------------ kernel 4: scores far above the running maximum
+@pytest.mark.parametrize("gain", [3.0, 12.0], ids=["2^49", "beyond_2^128"])
+def test_scores_far_above_running_maximum(dev, gain):
+    """Kernel 4 rescales O and l lazily (only when a block's row maximum exceeds the reference maximum by more than
+    2^8) and per warp.  Keys that match their query `gain` times over in a LATER block put that block's scores 2^49
+    (gain 3) or more than 2^128 (gain 12: the rescale factor underflows to zero) above everything accumulated so far,
+    for half of the rows of a warp's tile only -- the result must still be exact."""
+    from rsa_b200 import ops
+    g = torch.Generator().manual_seed(21)
+    s = 640
+    q = torch.randn(1, 2, s, 128, generator=g)
+    k = 0.05 * torch.randn(1, 2, s, 128, generator=g)
+    v = torch.randn(1, 2, s, 128, generator=g)
+    k[:, :, 256:384] = 3.0 * q[:, :, 0:128]          # block 2 matches query tile 0 ...
+    k[:, :, 384:512] = gain * q[:, :, 0:128]         # ... block 3 matches it `gain` times over
+    k[:, :, 512:640] = gain * q[:, :, 128:256]       # and block 4 matches query tile 1
+    q, k, v = (t.to(torch.bfloat16).to(dev) for t in (q, k, v))
+    mask = torch.ones(1, 2, 5, 5, dtype=torch.bool, device=dev)
+    out = ops.masked_attention(q, k, v, mask, s).float()
+    ref = torch.nn.functional.scaled_dot_product_attention(q.float(), k.float(), v.float())
+    assert torch.isfinite(out).all()
+    assert (out - ref).abs().max().item() <= ATOL_OUT
+    assert cos_sim(out.cpu().numpy(), ref.cpu().numpy()) >= COS_OUT

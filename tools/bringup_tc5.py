@@ -146,7 +146,7 @@ def trace(h=8, s=16384, dens=0.25, flags=0):
           f"({int(mask.sum()) * 8388608 / (e0.elapsed_time(e1) / 5) / 1e9:.0f} TFLOP/s-equivalent)")
     t = dbg[33024:].view(64, 16).cpu().double()
     names = ["sm:wait_s", "sm:got_s", "sm:ld_done", "sm:max_done", "sm:half0", "sm:done", "", "", "mma:qk_issued",
-             "mma:got_p0", "", "mma:pv_issued", "mma:k_in"]
+             "mma:got_p0", "mma:pv_enter", "mma:pv_issued", "mma:k_in", "mma:v_in", "mma:qk_enter"]
     print("  step " + " ".join(f"{n:>13}" for n in names if n))
     for i in range(4, 16):
         print(f"  {i:4d} " + " ".join(f"{int(t[i, j]):13d}" for j, n in enumerate(names) if n))

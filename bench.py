@@ -426,7 +426,7 @@ def main():
         e2e = {"value": wp["dense_flop_per_head"] * heads / (ms_e2e * 1e-3) / 1e12, "unit": "TFLOP/s",
                "ms_per_step": ms_e2e, "h2d_bytes_per_step": bi, "d2h_bytes_per_step": bo,
                "path": f"public per-family entry point on pinned host tensors -> rsa_rectified_attention_host, "
-                       f"{host_chunk} head(s) per chunk, H2D | kernels | D2H on three streams",
+                       f"{host_chunk} head(s) per chunk (the last {host_chunk} heads one per chunk), H2D | kernels | D2H on three streams",
                "ms_per_step_unpipelined": ms_serial,
                "h2d_only_ms": ms_h2d}
 

@@ -48,6 +48,8 @@ int lanes_for_current_device(DeviceLanes** out) {
 struct HostPlan {
   int hc;             // heads per chunk
   int n_chunks;
+  int body_heads;     // heads [0, body_heads) go in chunks of hc; the rest one head per chunk (see make_host_plan)
+  int body_chunks;
   bool out_token_major;  // host out has heads adjacent inside a token ([B,S,H,D]): stage as [B,S,hc,D]
   size_t tensor_bytes;   // one staged chunk of q / k / v / out
   size_t ws_bytes;       // attention workspace of one chunk
@@ -73,7 +75,12 @@ int make_host_plan(const rsa_attn_desc* d, int heads_per_chunk, HostPlan* p) {
   if (rc != RSA_OK) return rc;
   if (heads_per_chunk < 1) RSA_FAIL(RSA_ERR_ARG, "heads_per_chunk must be >= 1");
   p->hc = heads_per_chunk < d->heads ? heads_per_chunk : d->heads;
-  p->n_chunks = (d->heads + p->hc - 1) / p->hc;
+  // The input copies are the bottleneck of the pipeline (PCIe), so its length is (all copies in) + (kernels and copy
+  // out of the LAST chunk): the last hc heads are issued one per chunk to keep that tail short.
+  const int tail = (p->hc > 1 && d->heads >= 3 * p->hc) ? p->hc : 0;
+  p->body_heads = d->heads - tail;
+  p->body_chunks = (p->body_heads + p->hc - 1) / p->hc;
+  p->n_chunks = p->body_chunks + tail;
   p->out_token_major = d->o_stride[1] == RSA_HEAD_DIM;
   p->tensor_bytes = align_up((size_t)d->batch * p->hc * d->seq * RSA_HEAD_DIM * 2, 256);
   const rsa_attn_desc c = chunk_desc(d, p->hc, p->out_token_major);
@@ -169,8 +176,9 @@ extern "C" int rsa_rectified_attention_host(const rsa_attn_desc* d, const void* 
 
   for (int c = 0; c < p.n_chunks; ++c) {
     const int slot = c & 1;
-    const int h0 = c * p.hc;
-    const int n = d->heads - h0 < p.hc ? d->heads - h0 : p.hc;
+    const bool body = c < p.body_chunks;
+    const int h0 = body ? c * p.hc : p.body_heads + (c - p.body_chunks);
+    const int n = !body ? 1 : (p.body_heads - h0 < p.hc ? p.body_heads - h0 : p.hc);
     // H2D lane: the slot's input staging is free once chunk c-2 has been computed
     if (c >= 2) RSA_CUDA_CHECK(cudaStreamWaitEvent(lanes->h2d, lanes->computed[slot], 0));
     for (int t = 0; t < 3; ++t)

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(kThreads, 1) attn_mma_kernel(const AttnArgs a)
   __nv_bfloat16* ob = a.o + b * a.os[0] + h * a.os[1];
 
   const int64_t lrow = (int64_t)bh * a.nqt + tile;
-  const int cnt = a.kept_cnt[lrow];
+  const int cnt = min(max(a.kept_cnt[lrow], 0), a.nb);
   const uint16_t* list = a.kept_idx + lrow * a.nb;
   const int row0 = tile * 128;
 

@@ -107,13 +107,15 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int b = bh / a.heads, h = bh % a.heads;
   const int tile0 = 2 * pair, tile1 = 2 * pair + 1;
   const int64_t lrow0 = (int64_t)bh * a.nqt + tile0;
-  const int cnt0 = a.kept_cnt[lrow0];
-  const int cnt1 = tile1 < a.nqt ? a.kept_cnt[lrow0 + 1] : 0;
+  // counts and prefix length are clamped so that a workspace that never saw a build (mask re-use misused) yields
+  // garbage values, not an unbounded walk; out-of-range block numbers read as zero tiles through TMA
+  const int cnt0 = min(max(a.kept_cnt[lrow0], 0), a.nb);
+  const int cnt1 = tile1 < a.nqt ? min(max(a.kept_cnt[lrow0 + 1], 0), a.nb) : 0;
   // the pair schedule (rsa_api.cu: pair_schedule_kernel): both lists start with the nsh blocks the two tiles have in
   // common, in the same order, so over rounds [0, nsh) one K tile and one V tile serve both slots
   const uint16_t* __restrict__ list0 = a.sched_idx + lrow0 * a.nb;
   const uint16_t* __restrict__ list1 = list0 + a.nb;
-  const int nsh = a.pair_shared[(int64_t)bh * gridDim.x + pair];
+  const int nsh = min(max(a.pair_shared[(int64_t)bh * gridDim.x + pair], 0), min(cnt0, cnt1));
   const int rounds = max(cnt0, cnt1);
 
   const long long t0 = kDebug ? clock64() : 0;

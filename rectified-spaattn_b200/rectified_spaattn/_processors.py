@@ -187,18 +187,21 @@ def fused_prep_attention(attn, hidden_states, encoder_hidden_states, geo, top_k,
     lat = [f(hidden_states) for f in (attn.to_q, attn.to_k, attn.to_v)]
     if lat[0].shape[2] != heads * 128:
         return None
-    q, k, v = (torch.empty(b, heads, s, 128, dtype=torch.bfloat16, device=hidden_states.device) for _ in range(3))
-    plan = ops.Plan(q, k, v, geo, top_k, p_remain, nbr, mask_cache=mask_cache)
-    cut = lambda r, a, z: None if r is None else (r[0][a:z], r[1][a:z])
+    enc = None
     if dual:
         enc = [f(encoder_hidden_states) for f in (attn.add_q_proj, attn.add_k_proj, attn.add_v_proj)]
         if lat[0].shape[1] != nv or enc[0].shape[1] != s - nv:
             return None
+    elif lat[0].shape[1] != s:
+        return None
+    # every "this layer does not fit" exit is above: from here on the call is made
+    q, k, v = (torch.empty(b, heads, s, 128, dtype=torch.bfloat16, device=hidden_states.device) for _ in range(3))
+    plan = ops.Plan(q, k, v, geo, top_k, p_remain, nbr, mask_cache=mask_cache)
+    cut = lambda r, a, z: None if r is None else (r[0][a:z], r[1][a:z])
+    if dual:
         plan.qkv_prep(*lat, dst_row=0, rope=cut(rope, 0, nv), **lat_norm)
         plan.qkv_prep(*enc, dst_row=nv, rope=cut(rope, nv, s) if rope_text else None, **enc_norm)
     else:
-        if lat[0].shape[1] != s:
-            return None
         n_rope = 0 if rope is None else (s if rope_text else nv)
         if geo.gap:     # ragged visual segment: the two segments are separate block ranges
             plan.qkv_prep(*(t[:, :nv] for t in lat), dst_row=0, rope=cut(rope, 0, nv), **lat_norm)

@@ -145,6 +145,7 @@ class Plan:
         # one workspace per device is shared by short-lived plans (a call's stages run back to back on one stream);
         # a plan that is kept across other calls (FusedUlysses) owns its own
         self.mask_mode = N.MASK_BUILD
+        self.mask_cache = mask_cache
         if mask_cache is not None:    # the cache owns the workspace (it survives this plan) and says what to re-use
             # the neighbour matrix is a constant of the latent grid: identified by the caller's storage, not its bytes
             key = (self.shape, geo, int(top_k), float(p_remain),
@@ -189,6 +190,8 @@ class Plan:
                        self.out.data_ptr())
         else:
             self._reuse(mask_mode, 0)
+        if self.mask_cache is not None:
+            self.mask_cache.ran(mask_mode)
         return self.out
 
     def run_pooled(self, mask_mode=None):
@@ -199,6 +202,8 @@ class Plan:
                        self.out.data_ptr())
         else:
             self._reuse(mask_mode, 1)
+        if self.mask_cache is not None:
+            self.mask_cache.ran(mask_mode)
         return self.out
 
     def _reuse(self, mask_mode, pooled):
@@ -392,6 +397,7 @@ class MaskCache:
         self.refresh_every = max(1, int(refresh_every))
         self.keep = keep
         self.calls = 0
+        self.valid = False      # the workspace holds a selection built by an earlier call
         self._ws = None
         self._key = None
 
@@ -399,20 +405,27 @@ class MaskCache:
         """Forget the cached selection (new prompt / new generation)."""
         self.calls = 0
         self._key = None
+        self.valid = False
 
     def next_mode(self, key, device, ws_bytes):
-        """(mask_mode, workspace) for the next call whose geometry is `key`."""
-        fresh = self._key != key or self._ws is None or self._ws.device != device or self._ws.numel() < ws_bytes
-        if fresh:
+        """(mask_mode, workspace) for the next call whose geometry is `key`.  A query: the schedule only advances when
+        a call has actually been enqueued (`ran`), so a plan that is built and then abandoned changes nothing."""
+        if self._key != key or self._ws is None or self._ws.device != device or self._ws.numel() < ws_bytes:
             if self._ws is None or self._ws.device != device or self._ws.numel() < ws_bytes:
                 self._ws = torch.empty(ws_bytes, dtype=torch.uint8, device=device)
             self._key = key
             self.calls = 0
+            self.valid = False
         mode = N.MASK_BUILD
-        if self.calls % self.refresh_every != 0:
+        if self.valid and self.calls % self.refresh_every != 0:
             mode = N.MASK_KEEP_LISTS if self.keep == "lists" else N.MASK_KEEP_ALL
-        self.calls += 1
         return mode, self._ws
+
+    def ran(self, mode):
+        """A call in `mode` has been enqueued on this cache's workspace."""
+        if mode == N.MASK_BUILD:
+            self.valid = True
+        self.calls += 1
 
 
 def rectified_attention(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfuse=False, mask_cache=None):

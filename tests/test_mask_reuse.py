@@ -17,21 +17,30 @@ ATOL_OUT, COS_OUT = 2e-2, 0.999
 def test_mask_cache_schedule():
     from rsa_b200 import native as N
     from rsa_b200 import ops
-    c = ops.MaskCache(refresh_every=3, keep="lists")
     dev = torch.device("cpu")
-    modes = [c.next_mode("k", dev, 64)[0] for _ in range(7)]
-    assert modes == [N.MASK_BUILD, N.MASK_KEEP_LISTS, N.MASK_KEEP_LISTS] * 2 + [N.MASK_BUILD]
-    ws = c.next_mode("k", dev, 64)[1]
-    assert c.next_mode("k", dev, 64)[1] is ws                       # the workspace IS the cache: it must persist
-    assert c.next_mode("other geometry", dev, 64)[0] == N.MASK_BUILD  # a different call shape invalidates it
-    assert c.next_mode("other geometry", dev, 64)[0] == N.MASK_KEEP_LISTS
-    assert c.next_mode("other geometry", dev, 4096)[0] == N.MASK_BUILD  # a workspace that has to grow is empty
+
+    def call(c, key="k", nbytes=64):
+        mode, ws = c.next_mode(key, dev, nbytes)
+        c.ran(mode)
+        return mode, ws
+
+    c = ops.MaskCache(refresh_every=3, keep="lists")
+    assert [call(c)[0] for _ in range(7)] == [N.MASK_BUILD, N.MASK_KEEP_LISTS, N.MASK_KEEP_LISTS] * 2 + [N.MASK_BUILD]
+    ws = call(c)[1]
+    assert call(c)[1] is ws                                          # the workspace IS the cache: it must persist
+    # a plan that is built but never run must not advance the schedule or validate the workspace
+    d = ops.MaskCache(refresh_every=2)
+    assert [d.next_mode("k", dev, 64)[0] for _ in range(3)] == [N.MASK_BUILD] * 3
+    assert [call(d)[0] for _ in range(3)] == [N.MASK_BUILD, N.MASK_KEEP_LISTS, N.MASK_BUILD]
+    assert call(c, "other geometry")[0] == N.MASK_BUILD              # a different call shape invalidates it
+    assert call(c, "other geometry")[0] == N.MASK_KEEP_LISTS
+    assert call(c, "other geometry", 4096)[0] == N.MASK_BUILD        # a workspace that has to grow is empty
     c.reset()
-    assert c.next_mode("other geometry", dev, 64)[0] == N.MASK_BUILD
+    assert call(c, "other geometry")[0] == N.MASK_BUILD
     a = ops.MaskCache(refresh_every=2, keep="all")
-    assert [a.next_mode(1, dev, 8)[0] for _ in range(4)] == [N.MASK_BUILD, N.MASK_KEEP_ALL] * 2
+    assert [call(a, 1, 8)[0] for _ in range(4)] == [N.MASK_BUILD, N.MASK_KEEP_ALL] * 2
     one = ops.MaskCache(refresh_every=1)
-    assert [one.next_mode(1, dev, 8)[0] for _ in range(3)] == [N.MASK_BUILD] * 3
+    assert [call(one, 1, 8)[0] for _ in range(3)] == [N.MASK_BUILD] * 3
     with pytest.raises(ValueError):
         ops.MaskCache(keep="nothing")
 
@@ -46,10 +55,10 @@ def test_processor_cache_follows_its_attributes():
     p.mask_keep = "all"
     assert p._mask_cache() is not c and p._mask_cache().keep == "all"
     c2 = p._mask_cache()
-    c2.calls, c2._key = 3, "x"
+    c2.calls, c2._key, c2.valid = 3, "x", True
     p.current_step = p.steps_per_cycle - 1
     p._tick()                                                        # a new generation starts: selection forgotten
-    assert p.current_step == 0 and c2.calls == 0 and c2._key is None
+    assert p.current_step == 0 and c2.calls == 0 and c2._key is None and not c2.valid
 
 
 # ----------------------------------------------------------------------------------------------------- GPU parity
@@ -160,7 +169,7 @@ def test_reuse_through_the_family_entry_point_and_bad_mode(dev):
     cache = ops.MaskCache(refresh_every=3)
     outs = [rectified_block_sparse_attention(q, k, v, mask_cache=cache, **kw).clone() for _ in range(3)]
     torch.cuda.synchronize()
-    assert cache.calls == 3 and all(torch.equal(o, plain) for o in outs)
+    assert cache.calls == 3 and cache.valid and all(torch.equal(o, plain) for o in outs)
     plan = ops.Plan(q, k, v, product_geometry("wan", case["nv"], case["s"], 0, 0, case["grid"][0]), case["top_k"],
                     case["p"], nbr, private_workspace=True)
     rc = N.lib().rsa_rectified_attention_reuse(C.byref(plan.desc), q.data_ptr(), k.data_ptr(), v.data_ptr(),

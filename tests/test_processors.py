@@ -214,3 +214,62 @@ def test_fused_prep_processors_match_unfused():
             outs.append(pr(attn, x, txt, None, (cos, sin)))
     _close(outs[0][0], outs[1][0])
     _close(outs[0][1], outs[1][1])
+
+
+@pytest.mark.gpu
+def test_whole_layer_records_into_a_cuda_graph():
+    """SURVEY 8f rank 3, last clause: with the host synchronisations gone (the caller supplies `num_true`), a whole
+    attention layer through the processor protocol -- projections, kernel 0, kernels 3a-4, output projections --
+    records into one CUDA graph and replays on new inputs with the eager result, bit for bit."""
+    dev = torch.device("cuda:0")
+    dim, heads, nv = 256, 2, 1024
+    attn = _mk(dev, dim, heads, added=True)
+    cos, sin, _ = _rope_tables(nv, 128, dev)
+    pr = hun.RectifiedHunyuanVideoSpaAttnProcessor2_0("sparse", 2, None, 0.3)
+    pr.num_true = nv + 200
+    g = torch.Generator(device=dev).manual_seed(3)
+    xs = [torch.randn(1, nv, dim, device=dev, generator=g).to(torch.bfloat16) for _ in range(2)]
+    ts = [torch.randn(1, 256, dim, device=dev, generator=g).to(torch.bfloat16) for _ in range(2)]
+    with torch.no_grad():
+        eager = [pr(attn, x, t, None, (cos, sin)) for x, t in zip(xs, ts)]      # also warms up every lazy allocation
+        x_in, t_in = xs[0].clone(), ts[0].clone()
+        stream = torch.cuda.Stream()
+        stream.wait_stream(torch.cuda.current_stream())
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(stream):
+            pr(attn, x_in, t_in, None, (cos, sin))
+            stream.synchronize()
+            with torch.cuda.graph(graph, stream=stream):
+                h_out, e_out = pr(attn, x_in, t_in, None, (cos, sin))
+        for x, t, ref in zip(xs, ts, eager):
+            x_in.copy_(x)
+            t_in.copy_(t)
+            graph.replay()
+            torch.cuda.synchronize()
+            assert torch.equal(h_out, ref[0]) and torch.equal(e_out, ref[1])
+
+
+@pytest.mark.gpu
+def test_processor_mask_refresh_interval():
+    """`mask_refresh_interval = 2`: the second call of a layer keeps the first call's block selection (fused and
+    op-by-op paths); on unchanged inputs that is bit-identical to rebuilding, and the third call rebuilds."""
+    dev = torch.device("cuda:0")
+    dim, heads, nv = 256, 2, 2048
+    attn = _mk(dev, dim, heads, added=True)
+    cos, sin, _ = _rope_tables(nv, 128, dev)
+    x = torch.randn(1, nv, dim, device=dev).to(torch.bfloat16)
+    txt = torch.randn(1, 256, dim, device=dev).to(torch.bfloat16)
+    for fuse in (True, False):
+        plain = hun.RectifiedHunyuanVideoSpaAttnProcessor2_0("sparse", 2, None, 0.3)
+        cached = hun.RectifiedHunyuanVideoSpaAttnProcessor2_0("sparse", 2, None, 0.3)
+        plain.fuse_prep = cached.fuse_prep = fuse
+        plain.num_true = cached.num_true = nv + 200
+        cached.mask_refresh_interval = 2
+        with torch.no_grad():
+            ref = plain(attn, x, txt, None, (cos, sin))
+            outs = [cached(attn, x, txt, None, (cos, sin)) for _ in range(3)]
+        torch.cuda.synchronize()
+        c = cached._mask_cache()
+        assert c.calls == 3 and c.valid
+        for o in outs:
+            assert torch.equal(o[0], ref[0]) and torch.equal(o[1], ref[1])

@@ -210,7 +210,11 @@ typedef struct rsa_prep_desc {
   const void* q_weight;     /* DEVICE bf16 [128] (norm 1) or [heads*128] (norm 2): norm_q.weight               */
   const void* k_weight;     /* likewise norm_k.weight                                                          */
   int32_t rope_rows;        /* source tokens [0, rope_rows) are rotated; 0 = no rotary embedding               */
-  int32_t reserved;
+  int32_t rope_compact;     /* 0: cos and sin are two tables.  1: `cos` is ONE table [rope_rows, 64] of          */
+                            /* (cos_i, sin_i) pairs and `sin` is ignored -- diffusers' tables repeat every value  */
+                            /* for the two elements of a pair (repeat_interleave(2)), so this holds the same      */
+                            /* numbers in half the bytes; the caller vouches for cos[2i] == cos[2i+1] and         */
+                            /* sin[2i] == sin[2i+1] (rsa_b200/ops.py checks once per table).  Same arithmetic.    */
   const float* cos;         /* DEVICE fp32 [rope_rows, 128] (diffusers' repeat-interleaved cos table)          */
   const float* sin;
   float* row_scratch;       /* norm 2 only: DEVICE scratch of 2*batch*rows floats for the per-token statistics  */

@@ -40,6 +40,7 @@ struct PrepArgs {
   const float* row_rinv[2];     // norm across heads: rsqrt(mean(x^2) + eps) per (batch, source row), from row_rms_kernel
   float eps;
   const float *cos, *sin;       // fp32 [rope_rows, 128]
+  int rope_compact;             // cos = [rope_rows, 64] pairs (cos_i, sin_i), sin unused: half the table bytes per row
   int rope_rows;                // source rows below this are rotated
   int rows;                     // source rows
   int dst_row0;                 // memory row of source row 0 in the destination
@@ -87,24 +88,36 @@ __device__ __forceinline__ uint4 ld_global_v4(const void* p) {
 struct RopeRow {
   float4 c0, c1, s0, s1;
 };
+template <bool kCompact>
 __device__ __forceinline__ RopeRow load_rope(const PrepArgs& p, int r, int col, bool on) {
   RopeRow t;
   t.c0 = t.c1 = t.s0 = t.s1 = make_float4(0.f, 0.f, 0.f, 0.f);
   if (on) {
     const float4* cp = reinterpret_cast<const float4*>(p.cos + (int64_t)r * 128 + col);
-    const float4* sp = reinterpret_cast<const float4*>(p.sin + (int64_t)r * 128 + col);
-    t.c0 = __ldg(cp), t.c1 = __ldg(cp + 1), t.s0 = __ldg(sp), t.s1 = __ldg(sp + 1);
+    if constexpr (kCompact) {
+      // the thread's 8 columns are 4 pairs: (cos, sin) x 4 = 8 floats at the same offset of the 128-float row
+      const float4 a = __ldg(cp), b = __ldg(cp + 1);
+      t.c0 = make_float4(a.x, a.x, a.z, a.z), t.c1 = make_float4(b.x, b.x, b.z, b.z);
+      t.s0 = make_float4(a.y, a.y, a.w, a.w), t.s1 = make_float4(b.y, b.y, b.w, b.w);
+    } else {
+      const float4* sp = reinterpret_cast<const float4*>(p.sin + (int64_t)r * 128 + col);
+      t.c0 = __ldg(cp), t.c1 = __ldg(cp + 1), t.s0 = __ldg(sp), t.s1 = __ldg(sp + 1);
+    }
   }
   return t;
 }
 
+// kNorm: 0 none, 1 RMSNorm over head_dim, 2 RMSNorm across heads (row statistic precomputed), 3 LayerNorm over head_dim.
+// kGather: rows come from peer-mapped buffers.  kCompact: one (cos, sin)-pair table.  Compile-time so that each form
+// carries only its own code and registers (with all of them behind run-time flags the HunyuanVideo form lost 40 %).
+template <int kNorm, bool kGather, bool kCompact>
 __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, int h, int jblk, int warp, int lane,
                                           uint4 (&raw)[8]) {
   const int col = 8 * (lane & 15);
   const __nv_bfloat16* src = p.src[which] + b * p.src_stride[which][0] + (int64_t)h * 128 + col;
   __nv_bfloat16* dst = p.dst[which] + b * p.dst_stride[which][0] + h * p.dst_stride[which][1] + col;
   const int r0 = jblk * 128 + 16 * warp + (lane >> 4);  // source row of step 0; the 16 lanes of a half-warp share it
-  if (p.src_table == nullptr) {
+  if constexpr (!kGather) {
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
       const int r = r0 + 2 * it;
@@ -134,22 +147,21 @@ __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, i
     return;
   }
   float wgt[8];
-  const bool normed = p.w[which] != nullptr;
-  if (normed) unpack8(__ldg(reinterpret_cast<const uint4*>(p.w[which] + h * p.w_head_stride + col)), wgt);
-  const float* rinv_rows = p.row_rinv[which] ? p.row_rinv[which] + (int64_t)b * p.rows : nullptr;
+  if constexpr (kNorm != 0) unpack8(__ldg(reinterpret_cast<const uint4*>(p.w[which] + h * p.w_head_stride + col)), wgt);
+  const float* rinv_rows = kNorm == 2 ? p.row_rinv[which] + (int64_t)b * p.rows : nullptr;
   float bia[8];
-  if (normed && p.layer_norm) unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias[which] + col)), bia);
-  RopeRow next = load_rope(p, r0, col, r0 < p.rows && r0 < p.rope_rows);
+  if constexpr (kNorm == 3) unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias[which] + col)), bia);
+  RopeRow next = load_rope<kCompact>(p, r0, col, r0 < p.rows && r0 < p.rope_rows);
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     const int r = r0 + 2 * it;
     const bool live = r < p.rows;
     const bool rot = live && r < p.rope_rows;
     const RopeRow t = next;
-    if (it < 7) next = load_rope(p, r + 2, col, r + 2 < p.rows && r + 2 < p.rope_rows);
+    if (it < 7) next = load_rope<kCompact>(p, r + 2, col, r + 2 < p.rows && r + 2 < p.rope_rows);
     float f[8];
     unpack8(raw[it], f);
-    if (normed && p.layer_norm) {
+    if constexpr (kNorm == 3) {
       // torch.nn.LayerNorm(head_dim) on a bf16 tensor: statistics and affine in fp32, ONE rounding to bf16
       // (cogvideo :452-455; two-pass variance, fixed butterfly order over the 16 lanes that share the row)
       float sm = 0.f;
@@ -174,9 +186,9 @@ __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, i
         f[c] = y.x;
         f[c + 1] = y.y;
       }
-    } else if (normed) {
+    } else if constexpr (kNorm != 0) {
       float rinv;
-      if (rinv_rows) {  // norm across heads: the row statistic was computed over all H*128 channels beforehand
+      if constexpr (kNorm == 2) {  // norm across heads: the row statistic was computed over all H*128 channels beforehand
         rinv = live ? __ldg(rinv_rows + r) : 0.f;
       } else {
         // mean(x^2) over the 128 channels of this head: 8 per lane, then a fixed butterfly over the 16 lanes
@@ -238,7 +250,7 @@ __global__ void __launch_bounds__(256) row_rms_kernel(const __nv_bfloat16* __res
   if (lane == 0) (which ? rk : rq)[(int64_t)b * rows + row] = rsqrtf(__fadd_rn(__fdiv_rn(ss, (float)inner), eps));
 }
 
-template <bool kPrep, int kMinBlocks = 2>
+template <bool kPrep, int kMinBlocks = 2, int kNorm = 0, bool kGather = false, bool kCompact = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const PoolArgs a, const PrepArgs p) {
   // Prep grid: x = (tensor, batch*head) fastest, y = token block -- the CTAs that run together read the same source
   // rows (all heads of a token are contiguous in the projection output) and the same rotary-table rows, which are as
@@ -277,7 +289,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const 
 
   uint4 raw[8];
   if constexpr (kPrep) {
-    prep_rows(p, which, b, h, jblk, warp, lane, raw);
+    prep_rows<kNorm, kGather, kCompact>(p, which, b, h, jblk, warp, lane, raw);
     if (!p.pool) return;
     // rows the pooling counts as zeros (K, V rows >= kv_zero_from; hunyuan masked_fill_ :307-308) stay stored as they are
 #pragma unroll
@@ -455,6 +467,7 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
   pa.eps = p->eps;
   pa.cos = p->cos;
   pa.sin = p->sin;
+  pa.rope_compact = p->rope_compact != 0;
   pa.rope_rows = p->rope_rows;
   pa.rows = p->rows;
   pa.dst_row0 = p->dst_row;
@@ -486,7 +499,24 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
   const int blocks = (p->rows + 127) / 128;
   dim3 grid(3 * d->batch * d->heads, blocks);
   // 2 CTAs per SM (about 100 registers): capping at 3 or 4 CTAs spills and is no faster (1.24 / 1.25 / 2.17 ms at C3b)
-  pool_stats_kernel<true, 2><<<grid, kThreads, 0, s>>>(a, pa);
+  const bool compact = pa.rope_compact && pa.rope_rows > 0;
+#define RSA_PREP_LAUNCH(NORM, GATHER)                                                               \
+  do {                                                                                              \
+    if (compact) pool_stats_kernel<true, 2, NORM, GATHER, true><<<grid, kThreads, 0, s>>>(a, pa);   \
+    else pool_stats_kernel<true, 2, NORM, GATHER, false><<<grid, kThreads, 0, s>>>(a, pa);          \
+  } while (0)
+  if (route) {
+    if (p->norm == 1) RSA_PREP_LAUNCH(1, true);
+    else RSA_PREP_LAUNCH(0, true);
+  } else {
+    switch (p->norm) {
+      case 1: RSA_PREP_LAUNCH(1, false); break;
+      case 2: RSA_PREP_LAUNCH(2, false); break;
+      case 3: RSA_PREP_LAUNCH(3, false); break;
+      default: RSA_PREP_LAUNCH(0, false); break;
+    }
+  }
+#undef RSA_PREP_LAUNCH
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;
 }

@@ -406,14 +406,14 @@ extern "C" int rsa_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, cons
   if (p->norm == 2 && (!p->row_scratch || (uintptr_t)p->row_scratch % 4)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: norm 2 needs row_scratch (2*batch*rows floats)");
   if (p->norm && (!p->q_weight || !p->k_weight)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: norm weights are null");
   if (p->rope_rows < 0 || p->rope_rows > p->rows) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: rope_rows out of range");
-  if (p->rope_rows > 0 && (!p->cos || !p->sin)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: rotary tables are null");
+  if (p->rope_rows > 0 && (!p->cos || (!p->sin && !p->rope_compact))) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: rotary tables are null");
   for (int t = 0; t < 3; ++t)
     for (int i = 0; i < 2; ++i)
       if (p->src_stride[t][i] < 0 || p->src_stride[t][i] % 8) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: source strides must be multiples of 8 elements");
   const void* ptrs[8] = {q_src, k_src, v_src, q, k, v, p->q_weight, p->k_weight};
   for (int i = 0; i < 8; ++i)
     if ((uintptr_t)ptrs[i] % 16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: tensors must be 16-byte aligned");
-  if (p->rope_rows > 0 && (((uintptr_t)p->cos % 16) || ((uintptr_t)p->sin % 16))) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: rotary tables must be 16-byte aligned");
+  if (p->rope_rows > 0 && (((uintptr_t)p->cos % 16) || (!p->rope_compact && (uintptr_t)p->sin % 16))) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: rotary tables must be 16-byte aligned");
   WsLayout L;
   if (pool && (rc = check_ws(d, workspace, bytes, &L)) != RSA_OK) return rc;
   return launch_qkv_prep(p, d, q_src, k_src, v_src, nullptr, q, k, v, (char*)workspace, pool ? &L : nullptr,
@@ -445,7 +445,7 @@ extern "C" int rsa_qkv_prep_gather(const rsa_prep_desc* p, const rsa_attn_desc* 
   if (p->norm != 0 && p->norm != 1) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep_gather: norm must be 0 or 1");
   if (p->norm && (!p->q_weight || !p->k_weight)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: norm weights are null");
   if (p->rope_rows < 0 || p->rope_rows > p->rows) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rope_rows out of range");
-  if (p->rope_rows > 0 && (!p->cos || !p->sin)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rotary tables are null");
+  if (p->rope_rows > 0 && (!p->cos || (!p->sin && !p->rope_compact))) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rotary tables are null");
   WsLayout L;
   if (pool && (rc = check_ws(d, workspace, bytes, &L)) != RSA_OK) return rc;
   return launch_qkv_prep(p, d, nullptr, nullptr, nullptr, route, q, k, v, (char*)workspace, pool ? &L : nullptr,

@@ -44,7 +44,7 @@ class WsView(C.Structure):
 class PrepDesc(C.Structure):
     _fields_ = [("rows", C.c_int32), ("dst_row", C.c_int32), ("src_stride", (C.c_int64 * 2) * 3),
                 ("norm", C.c_int32), ("eps", C.c_float), ("q_weight", C.c_void_p), ("k_weight", C.c_void_p),
-                ("rope_rows", C.c_int32), ("reserved", C.c_int32), ("cos", C.c_void_p), ("sin", C.c_void_p),
+                ("rope_rows", C.c_int32), ("rope_compact", C.c_int32), ("cos", C.c_void_p), ("sin", C.c_void_p),
                 ("row_scratch", C.c_void_p), ("q_bias", C.c_void_p), ("k_bias", C.c_void_p)]
 
 

@@ -6,6 +6,7 @@ from __future__ import annotations
 
 import ctypes as C
 import math
+import os
 
 import torch
 
@@ -111,6 +112,34 @@ def _strides3(t):
     if t.stride(3) != 1:
         raise RuntimeError("head_dim must be the contiguous dimension")
     return (t.stride(0), t.stride(1), t.stride(2))
+
+
+_rope_cache = {}
+COMPACT_ROPE = os.environ.get("RSA_COMPACT_ROPE", "1") != "0"     # tests switch this off to compare the two table layouts
+
+
+def _compact_rope(cos_in, sin_in, cos, sin):
+    """diffusers builds its real rotary tables with repeat_interleave(2): both elements of a pair see the same cos and
+    the same sin.  When that holds (checked ONCE per table pair -- one host sync -- and remembered; the tables are
+    constants of a generation) the kernel is given one [rows, 64] table of (cos_i, sin_i) pairs instead of two
+    [rows, 128] tables.  Returns None for tables of any other form."""
+    if not COMPACT_ROPE:
+        return None
+    # Keyed by storage, offset and version, and the entry keeps the caller's tensors (hence their storage) alive, so
+    # a pointer can never come back as a different table; per-call slices of one table hit the same entry.
+    key = (cos_in.untyped_storage().data_ptr(), cos_in.storage_offset(), sin_in.untyped_storage().data_ptr(),
+           sin_in.storage_offset(), tuple(cos_in.shape), tuple(cos_in.stride()), cos_in._version, sin_in._version,
+           str(cos.device))
+    hit = _rope_cache.get(key)
+    if hit is not None:
+        return hit[2]
+    packed = None
+    if bool((cos[:, 0::2] == cos[:, 1::2]).all() & (sin[:, 0::2] == sin[:, 1::2]).all()):
+        packed = torch.stack([cos[:, 0::2], sin[:, 0::2]], dim=-1).reshape(cos.shape[0], cos.shape[1]).contiguous()
+    if len(_rope_cache) > 8:
+        _rope_cache.clear()
+    _rope_cache[key] = (cos_in, sin_in, packed)
+    return packed
 
 
 class Plan:
@@ -259,8 +288,13 @@ class Plan:
             n_rope = cos.shape[0] if rope_rows is None else int(rope_rows)
             if cos.shape != sin.shape or cos.dim() != 2 or cos.shape[1] != d or cos.shape[0] < n_rope:
                 raise RuntimeError("rotary tables must be (cos, sin) of shape [rope_rows, head_dim]")
-            keep += [cos, sin]
-            p.rope_rows, p.cos, p.sin = n_rope, cos.data_ptr(), sin.data_ptr()
+            packed = _compact_rope(rope[0], rope[1], cos, sin)
+            if packed is not None:      # one [rows, 64] table of (cos_i, sin_i) pairs: half the bytes per row
+                keep.append(packed)
+                p.rope_rows, p.rope_compact, p.cos = n_rope, 1, packed.data_ptr()
+            else:
+                keep += [cos, sin]
+                p.rope_rows, p.cos, p.sin = n_rope, cos.data_ptr(), sin.data_ptr()
         L = N.lib()
         with torch.cuda.device(self.device):
             N.check(L.rsa_qkv_prep(C.byref(p), C.byref(self.desc), q_src.data_ptr(), k_src.data_ptr(),

@@ -464,6 +464,36 @@ def test_qkv_prep_against_oracle_and_torch(dev):
             assert torch.equal(got.cpu().view(torch.int16), want.view(torch.int16))
 
 
+def test_qkv_prep_compact_rotary_table_is_bit_identical(dev):
+    """diffusers' rotary tables repeat every cos / sin for the two elements of a pair; the host layer then hands kernel
+    0 ONE [rows, 64] table of (cos_i, sin_i) pairs (rsa_prep_desc.rope_compact) -- the same numbers, half the bytes.
+    Both layouts must give the same bits; a table that is not pair-repeated must take the two-table path."""
+    from oracle import make_golden as MG
+    from rsa_b200 import geometry as G
+    from rsa_b200 import ops
+    src, wq, wk, cos, sin, n_rope = MG.prep_inputs()
+    rows = src[0].shape[1]
+    cos, sin = cos.to(dev), sin.to(dev)
+    assert bool((cos[:, 0::2] == cos[:, 1::2]).all()) and ops._compact_rope(cos, sin, cos, sin) is not None
+    outs = []
+    for compact in (True, False):
+        ops.COMPACT_ROPE = compact
+        try:
+            q, k, v = (torch.zeros(1, 2, rows, 128, dtype=torch.bfloat16, device=dev) for _ in range(3))
+            plan = ops.Plan(q, k, v, G.wan(rows), 1, 0.3, None)
+            plan.qkv_prep(*(t.to(dev) for t in src), q_weight=wq, k_weight=wk, eps=1e-6, rope=(cos, sin), pool=True)
+            torch.cuda.synchronize()
+            outs.append((q, k, plan.view()["q_pool"].clone(), plan.view()["k_cat"].clone()))
+        finally:
+            ops.COMPACT_ROPE = True
+    for a, b in zip(*outs):
+        assert torch.equal(a.view(torch.int16) if a.dtype == torch.bfloat16 else a,
+                           b.view(torch.int16) if b.dtype == torch.bfloat16 else b)
+    odd = cos.clone()
+    odd[:, 1] += 0.25                                   # no longer pair-repeated
+    assert ops._compact_rope(odd, sin, odd, sin) is None
+
+
 @pytest.mark.parametrize("name,dual", [("hunyuan_small", False), ("hunyuan_small", True), ("hunyuan_ragged", True),
                                        ("wan_ragged", False)])
 def test_qkv_prep_pooled_path_equals_separate_kernels(dev, name, dual):

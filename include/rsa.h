@@ -8,7 +8,8 @@
  * (rectified-spaattn_b200/rectified_spaattn/*.py) binds these with ctypes; INTEGRATION.md shows the stub a
  * maintainer of the reference would add.
  *
- * Conventions: all tensors are bf16 unless stated, head_dim == 128, block size == 128 tokens.
+ * Conventions: all tensors are bf16 unless stated (query/key/value/out may be fp16: rsa_attn_desc.dtype), head_dim ==
+ * 128, block size == 128 tokens.
  * "BH" = batch * heads (heads are independent end to end).  Strides are in ELEMENTS of the tensor's dtype.
  */
 #ifndef RSA_H_
@@ -21,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RSA_VERSION 100
+#define RSA_VERSION 101
 #define RSA_BLOCK 128
 #define RSA_HEAD_DIM 128
 #define RSA_MAX_ENTRIES 2048 /* max sortable entries per query block: NQ (+1 for the text aggregate) */
@@ -32,6 +33,11 @@ enum rsa_status {
   RSA_ERR_UNSUPPORTED = -2, /* head_dim != 128, too many blocks, misaligned strides */
   RSA_ERR_CUDA = -3,        /* a CUDA runtime/driver call failed; see rsa_last_error_string() */
   RSA_ERR_WORKSPACE = -4    /* workspace pointer null or smaller than rsa_attn_workspace_bytes() */
+};
+
+enum rsa_dtype {
+  RSA_DTYPE_BF16 = 0, /* every reference script runs its transformer in bf16 */
+  RSA_DTYPE_F16 = 1   /* the reference kernel is dtype-generic (p.to(q.dtype), rectified_wan21_attn.py:97): fp16 too */
 };
 
 enum rsa_family {
@@ -104,6 +110,9 @@ typedef struct rsa_attn_desc {
                                        /* kv_zero_from, text_end_block refer to that PADDED layout (visual  */
                                        /* token t at t, text token i at nq_blocks*128 + i).  seq and the    */
                                        /* strides always describe the tensors as they lie in memory.        */
+  int32_t dtype;                       /* enum rsa_dtype of query / key / value / out (kernels 2 and 4; pooled   */
+                                       /* statistics, scores and selection are fp32 either way).  Kernel 0       */
+                                       /* (rsa_qkv_prep*) follows diffusers' bf16 rounding points: bf16 only.    */
 } rsa_attn_desc;
 
 /* Pointers into the caller's workspace (all device memory, fp32 unless noted). */
@@ -293,7 +302,8 @@ size_t rsa_masked_attention_workspace_bytes(int bh, int n_q_blocks, int n_kv_blo
 int rsa_masked_attention(const void* q, const void* k, const void* v, void* out, int bh, int seq_q, int seq_kv,
                          int kv_len, const int64_t q_stride[2], const int64_t k_stride[2],
                          const int64_t v_stride[2], const int64_t o_stride[2], const uint8_t* block_mask,
-                         int n_q_blocks, int n_kv_blocks, void* workspace, size_t workspace_bytes, void* stream);
+                         int n_q_blocks, int n_kv_blocks, void* workspace, size_t workspace_bytes, void* stream,
+                         int dtype /* enum rsa_dtype */);
 
 /* Selects the attention kernel implementation for this process: 0 = tcgen05/TMEM/TMA (product path),
  * 1 = mma.sync cross-check kernel (tests only).  Returns the previous value. */

@@ -61,6 +61,8 @@ static_assert(kSmemBytes <= 232448, "shared memory per CTA");
 
 constexpr uint32_t kIdescQK = umma_idesc_bf16(128, 128, false);
 constexpr uint32_t kIdescPV = umma_idesc_bf16(128, 128, true);
+constexpr uint32_t kIdescQKh = umma_idesc_f16(128, 128, false);  // fp16 operands (rsa_attn_desc.dtype)
+constexpr uint32_t kIdescPVh = umma_idesc_f16(128, 128, true);
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
@@ -92,7 +94,7 @@ constexpr int kTraceBase = 33024, kTraceSteps = 64, kTraceSlots = 16;
       a.dbg[kTraceBase + (step) * kTraceSlots + (slot)] = (float)(clock64() - t0);                     \
   } while (0)
 
-template <bool kDebug, int kPolyPairs>
+template <bool kDebug, int kPolyPairs, bool kF16 = false>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQt,
@@ -247,13 +249,13 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (leader) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)  // 16 keys = 16 rows of 128 B; P: 16 bf16 = 8 TMEM columns
-                umma_ts(tO, tS + ks * 8, vd + 128 * ks, kIdescPV, (r > 1 || ks > 0) ? 1u : 0u);
+                umma_ts(tO, tS + ks * 8, vd + 128 * ks, kF16 ? kIdescPVh : kIdescPV, (r > 1 || ks > 0) ? 1u : 0u);
             }
             mbar_wait(bar(B_PHALF + 2 * s + 1), (r - 1) & 1);
             tc_fence_after();
             if (leader) {
 #pragma unroll
-              for (int ks = 4; ks < 8; ++ks) umma_ts(tO, tS + ks * 8, vd + 128 * ks, kIdescPV, 1u);
+              for (int ks = 4; ks < 8; ++ks) umma_ts(tO, tS + ks * 8, vd + 128 * ks, kF16 ? kIdescPVh : kIdescPV, 1u);
               if (release) umma_commit(bar(B_KVEMPTY + st));
               if (r == cnt) umma_commit(bar(B_OFULL + s));
             }
@@ -278,7 +280,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
 #pragma unroll
               for (int ks = 0; ks < 8; ++ks) {  // 16 head_dim elements = 32 bytes inside the swizzle atom
                 const uint32_t off = (ks >> 2) * (kGranule >> 4) + 2 * (ks & 3);
-                umma_ss(tS, qd + off, kd + off, kIdescQK, ks != 0);
+                umma_ss(tS, qd + off, kd + off, kF16 ? kIdescQKh : kIdescQK, ks != 0);
               }
               if (release) umma_commit(bar(B_KVEMPTY + st));
               umma_commit(bar(B_SFULL + s));
@@ -412,7 +414,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             la = __fadd2_rn(la, __fadd2_rn(x[0], x[1]));
             lb = __fadd2_rn(lb, __fadd2_rn(x[2], x[3]));
 #pragma unroll
-            for (int e = 0; e < 4; ++e) pk[j / 2 + e] = pack_bf16x2(x[e].x, x[e].y);
+            for (int e = 0; e < 4; ++e) pk[j / 2 + e] = pack_x2<kF16>(x[e].x, x[e].y);
           }
           tmem_st16(tS + c16 * 16, pk);
           if (c16 & 1) {  // 64 keys done: hand this half of P to the MMA thread
@@ -473,7 +475,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             for (int e = 0; e < 4; ++e) {
               const int c = c4 * 32 + j + 2 * e;
               const float c0 = crow ? crow[c] : 0.f, c1 = crow ? crow[c + 1] : 0.f;
-              w[e] = zero ? 0u : pack_bf16x2(fmaf(u2f(o[j + 2 * e]), inv, c0), fmaf(u2f(o[j + 2 * e + 1]), inv, c1));
+              w[e] = zero ? 0u : pack_x2<kF16>(fmaf(u2f(o[j + 2 * e]), inv, c0), fmaf(u2f(o[j + 2 * e + 1]), inv, c1));
             }
             *reinterpret_cast<uint4*>(orow + c4 * 32 + j) = make_uint4(w[0], w[1], w[2], w[3]);
           }
@@ -512,7 +514,7 @@ EncodeTiledFn encode_fn() {
 // [batch, heads, rows, 128] bf16 view with element strides st = (batch, head, row) -> 4-D tensor map whose box is
 // one granule: 64 head_dim elements x 128 rows, 128-byte swizzle; rows past the end read as zeros (the
 // reference zero-pads to a multiple of 128, rectified_wan21_attn.py:299-302).
-int make_map(CUtensorMap* m, const __nv_bfloat16* base, int batch, int heads, int rows, const int64_t* st) {
+int make_map(CUtensorMap* m, const __nv_bfloat16* base, int batch, int heads, int rows, const int64_t* st, bool f16) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) RSA_FAIL(RSA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   if ((uintptr_t)base % 16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "q/k/v must be 16-byte aligned");
@@ -525,7 +527,7 @@ int make_map(CUtensorMap* m, const __nv_bfloat16* base, int batch, int heads, in
   cuuint64_t strides[3] = {(cuuint64_t)sr * 2, (cuuint64_t)sh * 2, (cuuint64_t)sb * 2};
   cuuint32_t box[4] = {64, 128, 1, 1};
   cuuint32_t estr[4] = {1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
+  CUresult r = fn(m, f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, (void*)base, dims, strides, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) RSA_FAIL(RSA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -536,15 +538,15 @@ struct Maps {
   CUtensorMap q, k, v, qt, kt, vt;
 };
 
-template <bool kDebug, int kPolyPairs>
+template <bool kDebug, int kPolyPairs, bool kF16 = false>
 int launch(dim3 grid, cudaStream_t s, const Maps& m, const AttnArgs& a) {
   static bool configured = false;  // one flag per instantiation
   if (!configured) {
-    RSA_CUDA_CHECK(cudaFuncSetAttribute(attn_tc5_kernel<kDebug, kPolyPairs>,
+    RSA_CUDA_CHECK(cudaFuncSetAttribute(attn_tc5_kernel<kDebug, kPolyPairs, kF16>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
-  attn_tc5_kernel<kDebug, kPolyPairs><<<grid, kThreads, kSmemBytes, s>>>(m.q, m.k, m.v, m.qt, m.kt, m.vt, a);
+  attn_tc5_kernel<kDebug, kPolyPairs, kF16><<<grid, kThreads, kSmemBytes, s>>>(m.q, m.k, m.v, m.qt, m.kt, m.vt, a);
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;
 }
@@ -567,16 +569,17 @@ int launch_attention_tc5(const AttnArgs& a, cudaStream_t s) {
   // visual rows [0, vis) and text rows [vis, seq) of each tensor (RowMap); without a text segment the text maps are
   // never used and simply repeat the visual ones
   const int vis_q = a.vis_len < a.seq_q ? a.vis_len : a.seq_q, vis_kv = a.vis_len < a.seq_kv ? a.vis_len : a.seq_kv;
-  if ((rc = make_map(&m.q, a.q, a.batch, a.heads, vis_q, a.qs)) != RSA_OK) return rc;
-  if ((rc = make_map(&m.k, a.k, a.batch, a.heads, vis_kv, a.ks)) != RSA_OK) return rc;
-  if ((rc = make_map(&m.v, a.v, a.batch, a.heads, vis_kv, a.vs)) != RSA_OK) return rc;
+  if ((rc = make_map(&m.q, a.q, a.batch, a.heads, vis_q, a.qs, a.f16 != 0)) != RSA_OK) return rc;
+  if ((rc = make_map(&m.k, a.k, a.batch, a.heads, vis_kv, a.ks, a.f16 != 0)) != RSA_OK) return rc;
+  if ((rc = make_map(&m.v, a.v, a.batch, a.heads, vis_kv, a.vs, a.f16 != 0)) != RSA_OK) return rc;
   m.qt = m.q, m.kt = m.k, m.vt = m.v;
-  if (a.seq_q > vis_q && (rc = make_map(&m.qt, a.q + (int64_t)vis_q * a.qs[2], a.batch, a.heads, a.seq_q - vis_q, a.qs)) != RSA_OK) return rc;
+  if (a.seq_q > vis_q && (rc = make_map(&m.qt, a.q + (int64_t)vis_q * a.qs[2], a.batch, a.heads, a.seq_q - vis_q, a.qs, a.f16 != 0)) != RSA_OK) return rc;
   if (a.seq_kv > vis_kv) {
-    if ((rc = make_map(&m.kt, a.k + (int64_t)vis_kv * a.ks[2], a.batch, a.heads, a.seq_kv - vis_kv, a.ks)) != RSA_OK) return rc;
-    if ((rc = make_map(&m.vt, a.v + (int64_t)vis_kv * a.vs[2], a.batch, a.heads, a.seq_kv - vis_kv, a.vs)) != RSA_OK) return rc;
+    if ((rc = make_map(&m.kt, a.k + (int64_t)vis_kv * a.ks[2], a.batch, a.heads, a.seq_kv - vis_kv, a.ks, a.f16 != 0)) != RSA_OK) return rc;
+    if ((rc = make_map(&m.vt, a.v + (int64_t)vis_kv * a.vs[2], a.batch, a.heads, a.seq_kv - vis_kv, a.vs, a.f16 != 0)) != RSA_OK) return rc;
   }
   const dim3 grid((a.nqt + 1) / 2, a.batch * a.heads);
+  if (a.f16) return a.dbg ? launch<true, kDefaultPolyPairs, true>(grid, s, m, a) : launch<false, kDefaultPolyPairs, true>(grid, s, m, a);
   if (a.dbg) return launch<true, kDefaultPolyPairs>(grid, s, m, a);
   switch (poly_pairs()) {
     case 1: return launch<false, 1>(grid, s, m, a);

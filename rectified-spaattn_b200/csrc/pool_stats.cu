@@ -21,6 +21,8 @@
 // in rectified_flux_attn.py): unflatten/transpose, attn.norm_q / attn.norm_k (diffusers RMSNorm(head_dim, eps):
 // x * rsqrt(mean(x^2) + eps) in fp32 -> bf16 -> * weight -> bf16) and diffusers apply_rotary_emb(use_real=True,
 // use_real_unbind_dim=-1): out = x * cos + rotate_pairs(x) * sin in fp32 (two products and a sum, each rounded) -> bf16.
+#include <cuda_fp16.h>
+
 #include "rsa_common.cuh"
 
 namespace rsa {
@@ -65,11 +67,13 @@ struct PoolArgs {
   int text_keys, text_from;   // a, memory row of the first text token (= vis_len)
 };
 
+template <bool kF16 = false>
 __device__ __forceinline__ void unpack8(const uint4& u, float* f) {
-  const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(&u);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 t = __bfloat1622float2(p[i]);
+    float2 t;
+    if constexpr (kF16) t = __half22float2(reinterpret_cast<const __half2*>(&u)[i]);
+    else t = __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(&u)[i]);
     f[2 * i] = t.x;
     f[2 * i + 1] = t.y;
   }
@@ -250,7 +254,7 @@ __global__ void __launch_bounds__(256) row_rms_kernel(const __nv_bfloat16* __res
   if (lane == 0) (which ? rk : rq)[(int64_t)b * rows + row] = rsqrtf(__fadd_rn(__fdiv_rn(ss, (float)inner), eps));
 }
 
-template <bool kPrep, int kMinBlocks = 2, int kNorm = 0, bool kGather = false, bool kCompact = false>
+template <bool kPrep, int kMinBlocks = 2, int kNorm = 0, bool kGather = false, bool kCompact = false, bool kF16 = false>
 __global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const PoolArgs a, const PrepArgs p) {
   // Prep grid: x = (tensor, batch*head) fastest, y = token block -- the CTAs that run together read the same source
   // rows (all heads of a token are contiguous in the projection output) and the same rotary-table rows, which are as
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const 
       float f[8];
       uint4 u = make_uint4(0, 0, 0, 0);
       if (tok + a.gap < a.valid_rows[1]) u = *reinterpret_cast<const uint4*>(src + 8 * (tid & 15));
-      unpack8(u, f);
+      unpack8<kF16>(u, f);
       float* dst = a.mean[1] + ((int64_t)bh * a.out_rows[1] + a.n_blk[1] + t) * 128 + 8 * (tid & 15);
       reinterpret_cast<float4*>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
       reinterpret_cast<float4*>(dst)[1] = make_float4(f[4], f[5], f[6], f[7]);
@@ -302,7 +306,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const 
         const int t = (blk - a.nq_vis) * 128 + 16 * warp + 2 * it + (lane >> 4);  // text token index
         if (t < a.text_keys) {
           float f[8];
-          unpack8(raw[it], f);
+          unpack8<kF16>(raw[it], f);
           float* dstk = a.mean[1] + ((int64_t)bh * a.out_rows[1] + a.n_blk[1] + t) * 128 + col;
           reinterpret_cast<float4*>(dstk)[0] = make_float4(f[0], f[1], f[2], f[3]);
           reinterpret_cast<float4*>(dstk)[1] = make_float4(f[4], f[5], f[6], f[7]);
@@ -329,7 +333,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const 
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     float f[8];
-    unpack8(raw[it], f);
+    unpack8<kF16>(raw[it], f);
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = __fadd_rn(acc[c], f[c]);
   }
@@ -359,7 +363,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const 
 #pragma unroll
   for (int it = 0; it < 8; ++it) {
     float f[8];
-    unpack8(raw[it], f);
+    unpack8<kF16>(raw[it], f);
 #pragma unroll
     for (int c = 0; c < 8; ++c) acc[c] = __fadd_rn(acc[c], fabsf(__fsub_rn(f[c], mean[c])));
   }
@@ -425,7 +429,8 @@ int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, cons
   const int text_ctas = (L.a + 15) / 16;
   const int gx = L.nb > text_ctas ? L.nb : text_ctas;
   dim3 grid(gx, L.bh, L.a > 0 ? 4 : 3);
-  pool_stats_kernel<false, 3><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
+  if (d->dtype == RSA_DTYPE_F16) pool_stats_kernel<false, 3, 0, false, false, true><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
+  else pool_stats_kernel<false, 3><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;
 }

@@ -131,6 +131,10 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n, bool b_mn_m
   return (1u << 4) | (1u << 7) | (1u << 10) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) |
          ((uint32_t)(m >> 4) << 24);
 }
+// the same with fp16 operands (a/b format F16 = 0)
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, bool b_mn_major) {
+  return (1u << 4) | ((b_mn_major ? 1u : 0u) << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
 
 #define RSA_R8(r, o) "=r"(r[o + 0]), "=r"(r[o + 1]), "=r"(r[o + 2]), "=r"(r[o + 3]), "=r"(r[o + 4]), "=r"(r[o + 5]), "=r"(r[o + 6]), "=r"(r[o + 7])
 #define RSA_W8(r, o) "r"(r[o + 0]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]), "r"(r[o + 7])
@@ -179,6 +183,18 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   uint32_t d;
   asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
   return d;
+}
+
+// {hi, lo} -> packed f16x2 with lo in bits [0,16)
+__device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
+  uint32_t d;
+  asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+template <bool kF16>
+__device__ __forceinline__ uint32_t pack_x2(float lo, float hi) {
+  if constexpr (kF16) return pack_f16x2(lo, hi);
+  else return pack_bf16x2(lo, hi);
 }
 
 }  // namespace ptx

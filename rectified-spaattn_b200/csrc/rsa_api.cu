@@ -25,6 +25,7 @@ int validate_desc(const rsa_attn_desc* d) {
   if (d->head_dim != RSA_HEAD_DIM)
     RSA_FAIL(RSA_ERR_UNSUPPORTED, "head_dim must be 128 (got %d); the reference asserts Lk in {16,32,64,128}", d->head_dim);
   if (d->batch <= 0 || d->heads <= 0 || d->seq <= 0) RSA_FAIL(RSA_ERR_ARG, "batch/heads/seq must be positive");
+  if (d->dtype != RSA_DTYPE_BF16 && d->dtype != RSA_DTYPE_F16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "dtype %d is not one of rsa_dtype (bf16, fp16)", d->dtype);
   if ((int64_t)d->batch * d->heads > 65535) RSA_FAIL(RSA_ERR_UNSUPPORTED, "batch*heads > 65535");
   if (d->family != RSA_FAMILY_WAN && d->family != RSA_FAMILY_JOINT) RSA_FAIL(RSA_ERR_ARG, "unknown family %d", d->family);
   if (d->vis_len < 0 || d->vis_len > d->seq) RSA_FAIL(RSA_ERR_ARG, "vis_len=%d out of [0, seq]", d->vis_len);
@@ -149,6 +150,7 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->peer_rows = a->peer_head0 = 0;
   a->peer_os[0] = a->peer_os[1] = 0;
   a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.4426950408889634);
+  a->f16 = d->dtype == RSA_DTYPE_F16;
   a->dbg = g_attention_dbg;
   a->dbg_flags = g_attention_dbg_flags;
   return RSA_OK;
@@ -157,7 +159,10 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
 // reschedule = false: the kept lists have not changed since the last launch on this workspace, so neither has the
 // pair schedule kernel 4 walks (mask re-use)
 static int launch_attention(const AttnArgs& a, cudaStream_t s, bool reschedule = true) {
-  if (g_attention_impl == 1) return launch_attention_mma(a, s);
+  if (g_attention_impl == 1) {
+    if (a.f16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "the mma.sync cross-check kernel is bf16 only");
+    return launch_attention_mma(a, s);
+  }
   int rc = reschedule ? launch_pair_schedule(a, s) : RSA_OK;
   return rc != RSA_OK ? rc : launch_attention_tc5(a, s);
 }
@@ -391,6 +396,7 @@ extern "C" int rsa_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, cons
   int rc = validate_desc(d);
   if (rc != RSA_OK) return rc;
   if (!p) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: descriptor is null");
+  if (d->dtype != RSA_DTYPE_BF16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep follows diffusers' bf16 rounding points: bf16 only");
   if (!q_src || !k_src || !v_src || !q || !k || !v) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: null tensor");
   const RowMap rm = row_map(d);
   if (p->rows < 1) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: rows must be positive");
@@ -441,6 +447,7 @@ extern "C" int rsa_qkv_prep_gather(const rsa_prep_desc* p, const rsa_attn_desc* 
   if (rc != RSA_OK) return rc;
   if ((rc = validate_route(d, route, true, false)) != RSA_OK) return rc;
   if (!p || !q || !k || !v) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: null pointer");
+  if (d->dtype != RSA_DTYPE_BF16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep_gather: bf16 only");
   if (p->rows != d->seq || p->dst_row != 0) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rows must be seq and dst_row 0");
   if (p->norm != 0 && p->norm != 1) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep_gather: norm must be 0 or 1");
   if (p->norm && (!p->q_weight || !p->k_weight)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: norm weights are null");
@@ -524,8 +531,10 @@ extern "C" size_t rsa_masked_attention_workspace_bytes(int bh, int nq, int nkv) 
 extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v, void* out, int bh, int seq_q,
                                     int seq_kv, int kv_len, const int64_t q_stride[2], const int64_t k_stride[2],
                                     const int64_t v_stride[2], const int64_t o_stride[2], const uint8_t* block_mask,
-                                    int n_q_blocks, int n_kv_blocks, void* workspace, size_t bytes, void* stream) {
+                                    int n_q_blocks, int n_kv_blocks, void* workspace, size_t bytes, void* stream,
+                                    int dtype) {
   if (!q || !k || !v || !out || !block_mask) RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: null pointer");
+  if (dtype != RSA_DTYPE_BF16 && dtype != RSA_DTYPE_F16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_masked_attention: dtype %d", dtype);
   if (bh <= 0 || bh > 65535 || seq_q <= 0 || seq_kv <= 0 || kv_len < 1 || kv_len > seq_kv)
     RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: bad sizes");
   if (n_q_blocks != (seq_q + 127) / 128 || n_kv_blocks != (seq_kv + 127) / 128)
@@ -576,6 +585,7 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   a.peer_rows = a.peer_head0 = 0;
   a.peer_os[0] = a.peer_os[1] = 0;
   a.scale_log2 = (float)((1.0 / sqrt(128.0)) * 1.4426950408889634);
+  a.f16 = dtype == RSA_DTYPE_F16;
   a.dbg = g_attention_dbg;
   a.dbg_flags = g_attention_dbg_flags;
   return launch_attention(a, s);

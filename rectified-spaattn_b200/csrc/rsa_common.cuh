@@ -94,6 +94,7 @@ struct AttnArgs {
   int peer_rows, peer_head0;      // tokens per rank; first head of this rank inside a token of the result buffers
   int64_t peer_os[2];             // (batch, token) element strides of the result buffers
   float scale_log2;         // head_dim^-0.5 * log2(e)
+  int f16;                  // q/k/v/o hold fp16 instead of bf16 (the pointer types above are nominal: 2-byte elements)
   int dbg_flags;            // bring-up ablations (rsa_debug_set_attention_flags), only read by the debug kernel
   float* dbg;               // bring-up dump of tile 0 / bh 0 (rsa_debug_set_attention_dump), normally null
 };

@@ -149,8 +149,8 @@ class Plan:
                  private_workspace=False, mask_cache=None):
         for t, n in ((q, "query"), (k, "key"), (v, "value")):
             _need_cuda(t, n)
-            if t.dtype != torch.bfloat16:
-                raise RuntimeError(f"{n} must be bfloat16 (got {t.dtype})")
+            if t.dtype not in (torch.bfloat16, torch.float16) or t.dtype != q.dtype:
+                raise RuntimeError(f"{n} must be bfloat16 or float16 like the query (got {t.dtype})")
         b, h, s, d = q.shape
         if k.shape != q.shape or v.shape != q.shape:
             raise RuntimeError("query/key/value shapes differ")
@@ -161,11 +161,14 @@ class Plan:
             raise ValueError("geometry was built for a different sequence length")
         self.device = q.device
         self.shape = (b, h, s, d)
-        self.out = out if out is not None else torch.empty((b, s, h, d), dtype=torch.bfloat16, device=q.device)
+        self.out = out if out is not None else torch.empty((b, s, h, d), dtype=q.dtype, device=q.device)
+        if self.out.dtype != q.dtype:
+            raise RuntimeError("out must have the dtype of query/key/value")
         o4 = self.out.view(b, s, h, d).permute(0, 2, 1, 3)
         self.nbr_dev = _device_neighbors(nbr, q.device)
         desc = _fill_desc(N.AttnDesc(), (b, h, s, d), [_strides3(t) for t in (q, k, v, o4)], geo, top_k, p_remain,
                           self.nbr_dev, debug_dump_probs)
+        desc.dtype = N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16
         self.desc = desc
         L = N.lib()
         self.ws_bytes = L.rsa_attn_workspace_bytes(C.byref(desc))
@@ -249,6 +252,8 @@ class Plan:
         [B, rows, H*128] (head split, per-head RMSNorm with bf16 weights, rotary embedding on the first `rope_rows`
         tokens, re-layout) and, with pool=True, the pooled statistics of those blocks."""
         b, h, s, d = self.shape
+        if self.q.dtype != torch.bfloat16:
+            raise RuntimeError("kernel 0 follows diffusers' bf16 rounding points: bfloat16 only")
         for t, n in ((q_src, "q_src"), (k_src, "k_src"), (v_src, "v_src")):
             _need_cuda(t, n)
             if t.dtype != torch.bfloat16 or t.dim() != 3 or t.shape[0] != b or t.shape[2] != h * d or t.stride(2) != 1:
@@ -381,8 +386,8 @@ def rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfus
         raise RuntimeError("no CUDA device: this path has no CPU implementation")
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     for t, n in ((q, "query"), (k, "key"), (v, "value")):
-        if t.is_cuda or t.dtype != torch.bfloat16:
-            raise RuntimeError(f"{n} must be a bfloat16 host tensor")
+        if t.is_cuda or t.dtype not in (torch.bfloat16, torch.float16) or t.dtype != q.dtype:
+            raise RuntimeError(f"{n} must be a bfloat16 (or float16) host tensor")
         if not t.is_pinned():
             raise RuntimeError(f"{n} must be page-locked (tensor.pin_memory()): the copies run asynchronously")
     b, h, s, d = q.shape
@@ -393,13 +398,14 @@ def rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfus
     if s != geo.seq:
         raise ValueError("geometry was built for a different sequence length")
     if out is None:
-        out = torch.empty((b, s, h, d), dtype=torch.bfloat16, pin_memory=True)
-    elif out.is_cuda or not out.is_pinned() or out.numel() != b * s * h * d or out.dtype != torch.bfloat16:
-        raise RuntimeError("out must be a pinned bfloat16 host tensor of B*S*H*D elements")
+        out = torch.empty((b, s, h, d), dtype=q.dtype, pin_memory=True)
+    elif out.is_cuda or not out.is_pinned() or out.numel() != b * s * h * d or out.dtype != q.dtype:
+        raise RuntimeError("out must be a pinned host tensor of B*S*H*D elements with the inputs' dtype")
     o4 = out.view(b, s, h, d).permute(0, 2, 1, 3)
     nbr_dev = _device_neighbors(nbr, device)
     desc = _fill_desc(N.AttnDesc(), (b, h, s, d), [_strides3(t) for t in (q, k, v, o4)], geo, top_k, p_remain,
                       nbr_dev)
+    desc.dtype = N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16
     hc = int(heads_per_chunk or HOST_HEADS_PER_CHUNK or (2 if h >= 8 else 1))
     L = N.lib()
     need = L.rsa_host_call_scratch_bytes(C.byref(desc), hc)
@@ -481,6 +487,8 @@ def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None):
     _need_cuda(q, "q")
     b, h, s, d = q.shape
     assert d in (128,), "head_dim must be 128"
+    if q.dtype not in (torch.bfloat16, torch.float16) or k.dtype != q.dtype or v.dtype != q.dtype:
+        raise RuntimeError("q, k, v must all be bfloat16 or all float16")
     if sm_scale is not None and abs(sm_scale - d ** -0.5) > 1e-7:
         raise ValueError("only sm_scale = head_dim ** -0.5 is supported")
     q3, k3, v3 = (t.reshape(b * h, t.shape[2], d).contiguous() for t in (q, k, v))
@@ -497,7 +505,8 @@ def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None):
     with torch.cuda.device(q.device):
         N.check(L.rsa_masked_attention(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o.data_ptr(), b * h, s, skv,
                                        int(kv_len), mk(q3), mk(k3), mk(v3), mk(o), m.data_ptr(), nqb, nkb,
-                                       ws.data_ptr(), nbytes, _stream(q.device)), "rsa_masked_attention")
+                                       ws.data_ptr(), nbytes, _stream(q.device),
+                                       N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16), "rsa_masked_attention")
     return o.view(b, h, s, d)
 
 

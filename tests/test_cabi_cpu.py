@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in rsa.h but not exported"
     assert declared == set(N.EXPORTS)
-    assert lib.rsa_version() == 100
+    assert lib.rsa_version() == 101
 
 
 def test_struct_layout_matches_header():
@@ -116,6 +116,11 @@ def test_descriptor_validation_and_workspace_size():
     d = _desc(G.wan(1000))
     d.n_blocks = 7
     assert lib.rsa_attn_workspace_bytes(C.byref(d)) == 0
+    d = _desc(G.wan(1000))
+    d.dtype = N.DTYPE_F16                                   # fp16 tensors: same workspace (fp32 statistics)
+    assert lib.rsa_attn_workspace_bytes(C.byref(d)) == lib.rsa_attn_workspace_bytes(C.byref(_desc(G.wan(1000))))
+    d.dtype = 7
+    assert lib.rsa_attn_workspace_bytes(C.byref(d)) == 0 and b"dtype" in lib.rsa_last_error_string()
     # stage calls refuse a null / short workspace before touching the device
     d = _desc(G.wan(1024))
     assert lib.rsa_block_scores(C.byref(d), None, 0, None) == -4

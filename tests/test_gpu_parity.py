@@ -698,3 +698,48 @@ def test_scores_far_above_running_maximum(dev, gain):
     assert torch.isfinite(out).all()
     assert (out - ref).abs().max().item() <= ATOL_OUT
     assert cos_sim(out.cpu().numpy(), ref.cpu().numpy()) >= COS_OUT
+
+
+# ------------------------------------------------------------------------------------------ fp16 tensors
+def test_kernel4_fp16_against_the_literal_reference_kernel(dev, gold_dir):
+    """tests/golden/kernel_fp16.npz holds the output of the reference's OWN Triton kernel
+    (_triton_block_sparse_attention_onehot, rectified_wan21_attn.py:108-168) run under TRITON_INTERPRET=1 in fp16 --
+    the one dtype the interpreter and this library share.  Kernel 4 on the same q, k, v, block mask and seqlen must
+    reproduce it to fp16 rounding of P and of the output (the accumulation order inside a block differs)."""
+    import os
+    from rsa_b200 import ops
+    g = np.load(os.path.join(gold_dir, "kernel_fp16.npz"))
+    seqlen = int(g["seqlen"])
+    q, k, v = (torch.from_numpy(g[n]).to(dev) for n in ("q", "k", "v"))
+    assert q.dtype == torch.float16
+    out = ops.masked_attention(q, k, v, torch.from_numpy(g["mask"]).to(dev), seqlen)
+    assert out.dtype == torch.float16
+    got, ref = out.float().cpu().numpy(), g["out"].astype(np.float32)
+    assert np.abs(got[:, :, :seqlen] - ref[:, :, :seqlen]).max() <= 3e-3
+    assert cos_sim(got[:, :, :seqlen], ref[:, :, :seqlen]) >= 0.99999
+
+
+@pytest.mark.parametrize("name", ["wan_ragged", "hunyuan_small", "flux_small", "hunyuan_ragged"])
+def test_end_to_end_fp16_vs_oracle(dev, name):
+    """The whole call on fp16 tensors (rsa_attn_desc.dtype = RSA_DTYPE_F16; kernels 2 and 4 read and write fp16, the
+    pooled statistics / scores / selection are fp32 either way) against the oracle on the same fp16-rounded values."""
+    from rsa_b200 import ops
+    case = load_case(name)
+    q, k, v = (torch.from_numpy(case[n]).to(torch.float16) for n in ("q", "k", "v"))
+    geo = product_geometry(case["fam"], case["nv"], case["s"], case["text_len"], case["ntrue_d"], case["grid"][0])
+    plan = ops.Plan(q.to(dev), k.to(dev), v.to(dev), geo, case["top_k"], case["p"], torch.from_numpy(case["nbr"]))
+    out = plan.run()
+    assert out.dtype == torch.float16
+    out = out.float().cpu().numpy()
+    ref = O.forward(q.float().numpy(), k.float().numpy(), v.float().numpy(), case["ogeo"], case["nbr"]).reshape(out.shape)
+    assert np.abs(out - ref).max() <= ATOL_OUT and cos_sim(out, ref) >= COS_OUT
+    # pooled statistics of the fp16 rows: bit-exact like the bf16 ones
+    vw = plan.view()
+    ogeo = case["ogeo"]
+    qh, kh, vh = O.padded_inputs(q[0, 0].float().numpy(), k[0, 0].float().numpy(), v[0, 0].float().numpy(), ogeo)
+    qp, dq = O.pool_stats(qh, ogeo.seq + ogeo.gap, ogeo.nq_blocks)
+    assert np.array_equal(vw["q_pool"][0].cpu().numpy(), qp) and np.array_equal(vw["q_mad"][0].cpu().numpy(), dq)
+    with pytest.raises(RuntimeError):                     # kernel 0 is bf16 only
+        plan.qkv_prep(*(torch.zeros(1, case["s"], case["heads"] * 128, dtype=torch.float16, device=dev) for _ in range(3)))
+    with pytest.raises(RuntimeError):                     # mixed dtypes
+        ops.Plan(q.to(dev), k.to(dev).to(torch.bfloat16), v.to(dev), geo, case["top_k"], case["p"], None)

@@ -580,7 +580,7 @@ int launch_attention_tc5(const AttnArgs& a, cudaStream_t s) {
   }
   const dim3 grid((a.nqt + 1) / 2, a.batch * a.heads);
   if (a.f16) return a.dbg ? launch<true, kDefaultPolyPairs, true>(grid, s, m, a) : launch<false, kDefaultPolyPairs, true>(grid, s, m, a);
-  if (a.dbg) return launch<true, kDefaultPolyPairs>(grid, s, m, a);
+  if (a.dbg) return poly_pairs() == 1 ? launch<true, 1>(grid, s, m, a) : poly_pairs() == 2 ? launch<true, 2>(grid, s, m, a) : launch<true, kDefaultPolyPairs>(grid, s, m, a);
   switch (poly_pairs()) {
     case 1: return launch<false, 1>(grid, s, m, a);
     case 3: return launch<false, 3>(grid, s, m, a);

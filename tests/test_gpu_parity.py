@@ -381,6 +381,23 @@ def test_selection_ties_take_lowest_indices(dev):
             assert np.array_equal(mask[hi], m)
 
 
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "fp16"])
+def test_host_buffer_call_tapered_tail(dev, dtype):
+    """With heads >= 3 * heads_per_chunk the last heads_per_chunk heads go one per chunk (the pipeline's tail is the
+    last chunk's kernels + copy-out): 7 heads in chunks of 2 = chunks of 2, 2, 1 (body) + 1, 1 (tail).  Bit-identical
+    to the device-resident call, in both dtypes."""
+    from rsa_b200 import ops
+    case = load_case("hunyuan_small")
+    q, k, v = (torch.from_numpy(np.concatenate([case[n]] * 4, axis=1)[:, :7]).to(dtype) for n in ("q", "k", "v"))
+    geo = product_geometry(case["fam"], case["nv"], case["s"], case["text_len"], case["ntrue_d"], case["grid"][0])
+    nbr = torch.from_numpy(case["nbr"])
+    want = ops.rectified_attention(q.to(dev), k.to(dev), v.to(dev), geo, case["top_k"], case["p"], nbr).cpu()
+    got = ops.rectified_attention_host(*(t.pin_memory() for t in (q, k, v)), geo, case["top_k"], case["p"], nbr,
+                                       heads_per_chunk=2)
+    torch.cuda.synchronize()
+    assert got.dtype == dtype and torch.equal(got.view(torch.int16), want.view(torch.int16))
+
+
 # ----------------------------------------------------------------- batch > 1, strided views, CUDA-graph capture
 @pytest.mark.parametrize("name", ["hunyuan_small", "wan_ragged"])
 def test_batch_and_strided_views(dev, name):

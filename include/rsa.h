@@ -113,6 +113,11 @@ typedef struct rsa_attn_desc {
   int32_t dtype;                       /* enum rsa_dtype of query / key / value / out (kernels 2 and 4; pooled   */
                                        /* statistics, scores and selection are fp32 either way).  Kernel 0       */
                                        /* (rsa_qkv_prep*) follows diffusers' bf16 rounding points: bf16 only.    */
+  int32_t scale_dim;                   /* 0 = head_dim.  Otherwise the softmax scale is scale_dim^-1/2 (block    */
+                                       /* scoring and kernel 4): the tensors are a model's head_dim-scale_dim    */
+                                       /* heads (CogVideoX: 64) zero-padded to 128 columns by the caller -- zero  */
+                                       /* columns change neither q.k, the pooled statistics nor the GAPR test,    */
+                                       /* and the padded output columns are zero.  1 <= scale_dim <= 128.         */
 } rsa_attn_desc;
 
 /* Pointers into the caller's workspace (all device memory, fp32 unless noted). */
@@ -303,7 +308,7 @@ int rsa_masked_attention(const void* q, const void* k, const void* v, void* out,
                          int kv_len, const int64_t q_stride[2], const int64_t k_stride[2],
                          const int64_t v_stride[2], const int64_t o_stride[2], const uint8_t* block_mask,
                          int n_q_blocks, int n_kv_blocks, void* workspace, size_t workspace_bytes, void* stream,
-                         int dtype /* enum rsa_dtype */);
+                         int dtype /* enum rsa_dtype */, int scale_dim /* 0 = 128; see rsa_attn_desc.scale_dim */);
 
 /* Selects the attention kernel implementation for this process: 0 = tcgen05/TMEM/TMA (product path),
  * 1 = mma.sync cross-check kernel (tests only).  Returns the previous value. */

@@ -26,6 +26,7 @@ int validate_desc(const rsa_attn_desc* d) {
     RSA_FAIL(RSA_ERR_UNSUPPORTED, "head_dim must be 128 (got %d); the reference asserts Lk in {16,32,64,128}", d->head_dim);
   if (d->batch <= 0 || d->heads <= 0 || d->seq <= 0) RSA_FAIL(RSA_ERR_ARG, "batch/heads/seq must be positive");
   if (d->dtype != RSA_DTYPE_BF16 && d->dtype != RSA_DTYPE_F16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "dtype %d is not one of rsa_dtype (bf16, fp16)", d->dtype);
+  if (d->scale_dim < 0 || d->scale_dim > RSA_HEAD_DIM) RSA_FAIL(RSA_ERR_ARG, "scale_dim=%d out of [0, 128]", d->scale_dim);
   if ((int64_t)d->batch * d->heads > 65535) RSA_FAIL(RSA_ERR_UNSUPPORTED, "batch*heads > 65535");
   if (d->family != RSA_FAMILY_WAN && d->family != RSA_FAMILY_JOINT) RSA_FAIL(RSA_ERR_ARG, "unknown family %d", d->family);
   if (d->vis_len < 0 || d->vis_len > d->seq) RSA_FAIL(RSA_ERR_ARG, "vis_len=%d out of [0, seq]", d->vis_len);
@@ -149,7 +150,7 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->o_table = nullptr;
   a->peer_rows = a->peer_head0 = 0;
   a->peer_os[0] = a->peer_os[1] = 0;
-  a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.4426950408889634);
+  a->scale_log2 = (float)((1.0 / sqrt((double)scale_dim_of(d))) * 1.4426950408889634);
   a->f16 = d->dtype == RSA_DTYPE_F16;
   a->dbg = g_attention_dbg;
   a->dbg_flags = g_attention_dbg_flags;
@@ -532,9 +533,10 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
                                     int seq_kv, int kv_len, const int64_t q_stride[2], const int64_t k_stride[2],
                                     const int64_t v_stride[2], const int64_t o_stride[2], const uint8_t* block_mask,
                                     int n_q_blocks, int n_kv_blocks, void* workspace, size_t bytes, void* stream,
-                                    int dtype) {
+                                    int dtype, int scale_dim) {
   if (!q || !k || !v || !out || !block_mask) RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: null pointer");
   if (dtype != RSA_DTYPE_BF16 && dtype != RSA_DTYPE_F16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_masked_attention: dtype %d", dtype);
+  if (scale_dim < 0 || scale_dim > RSA_HEAD_DIM) RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: scale_dim=%d out of [0, 128]", scale_dim);
   if (bh <= 0 || bh > 65535 || seq_q <= 0 || seq_kv <= 0 || kv_len < 1 || kv_len > seq_kv)
     RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: bad sizes");
   if (n_q_blocks != (seq_q + 127) / 128 || n_kv_blocks != (seq_kv + 127) / 128)
@@ -584,7 +586,7 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   a.o_table = nullptr;
   a.peer_rows = a.peer_head0 = 0;
   a.peer_os[0] = a.peer_os[1] = 0;
-  a.scale_log2 = (float)((1.0 / sqrt(128.0)) * 1.4426950408889634);
+  a.scale_log2 = (float)((1.0 / sqrt(scale_dim > 0 ? (double)scale_dim : 128.0)) * 1.4426950408889634);
   a.f16 = dtype == RSA_DTYPE_F16;
   a.dbg = g_attention_dbg;
   a.dbg_flags = g_attention_dbg_flags;

@@ -56,6 +56,9 @@ inline RowMap row_map(const rsa_attn_desc* d) {
   return m;
 }
 
+// head dimension the softmax scale refers to (rsa_attn_desc.scale_dim)
+inline int scale_dim_of(const rsa_attn_desc* d) { return d->scale_dim > 0 ? d->scale_dim : d->head_dim; }
+
 int validate_desc(const rsa_attn_desc* d);
 WsLayout make_layout(const rsa_attn_desc* d);
 int check_ws(const rsa_attn_desc* d, const void* ws, size_t bytes, WsLayout* out);

@@ -146,7 +146,7 @@ class Plan:
     """One call's descriptor + workspace; build once per (shape, geometry) and reuse across layers/steps."""
 
     def __init__(self, q, k, v, geo: G.BlockGeometry, top_k, p_remain, nbr=None, debug_dump_probs=False, out=None,
-                 private_workspace=False, mask_cache=None):
+                 private_workspace=False, mask_cache=None, scale_dim=0):
         for t, n in ((q, "query"), (k, "key"), (v, "value")):
             _need_cuda(t, n)
             if t.dtype not in (torch.bfloat16, torch.float16) or t.dtype != q.dtype:
@@ -155,8 +155,9 @@ class Plan:
         if k.shape != q.shape or v.shape != q.shape:
             raise RuntimeError("query/key/value shapes differ")
         if d != 128:
-            # same precondition family as the reference's `assert Lk in {16, 32, 64, 128}` (wan21 :121)
-            raise AssertionError("head_dim must be 128")
+            # same precondition family as the reference's `assert Lk in {16, 32, 64, 128}` (wan21 :121); smaller
+            # head dimensions come in zero-padded (pad_head_dim / rectified_attention do that)
+            raise AssertionError("head_dim must be 128 (pad smaller heads with pad_head_dim and pass scale_dim)")
         if s != geo.seq:
             raise ValueError("geometry was built for a different sequence length")
         self.device = q.device
@@ -169,6 +170,7 @@ class Plan:
         desc = _fill_desc(N.AttnDesc(), (b, h, s, d), [_strides3(t) for t in (q, k, v, o4)], geo, top_k, p_remain,
                           self.nbr_dev, debug_dump_probs)
         desc.dtype = N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16
+        desc.scale_dim = int(scale_dim)     # model head_dim when q, k, v are zero-padded to 128 columns (pad_head_dim)
         self.desc = desc
         L = N.lib()
         self.ws_bytes = L.rsa_attn_workspace_bytes(C.byref(desc))
@@ -180,7 +182,7 @@ class Plan:
         self.mask_cache = mask_cache
         if mask_cache is not None:    # the cache owns the workspace (it survives this plan) and says what to re-use
             # the neighbour matrix is a constant of the latent grid: identified by the caller's storage, not its bytes
-            key = (self.shape, geo, int(top_k), float(p_remain),
+            key = (self.shape, geo, int(top_k), float(p_remain), int(scale_dim), str(q.dtype),
                    None if nbr is None else (nbr.data_ptr(), tuple(nbr.shape), nbr._version))
             self.mask_mode, self.ws = mask_cache.next_mode(key, q.device, self.ws_bytes)
         else:
@@ -423,6 +425,20 @@ def rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfus
     return out if shape_xfuse else out.view(b, s, h * d)
 
 
+def pad_head_dim(*tensors):
+    """[..., d] -> [..., 128] with zero columns for d in {16, 32, 64} (the reference kernel's other head dimensions,
+    `assert Lk in {16, 32, 64, 128}`, wan21 :121; CogVideoX has 64).  Zero columns change neither q.k^T, the pooled
+    statistics nor the GAPR test, and the padded output columns come out as zeros; the softmax scale must stay
+    d^-1/2, which the descriptor's `scale_dim` carries.  Twice the tensor-core work of a native d = 64 kernel: a
+    functional path for the one family that needs it, not a tuned one."""
+    d = tensors[0].shape[-1]
+    if d == 128:
+        return tensors, 0
+    if d not in (16, 32, 64):
+        raise AssertionError(f"head_dim must be one of 16, 32, 64, 128 (got {d})")
+    return tuple(torch.nn.functional.pad(t, (0, 128 - d)) for t in tensors), d
+
+
 class MaskCache:
     """Block selection kept across calls: one per attention layer.  The reference rebuilds its
     mask in every layer of every denoising step (rectified_hunyuan_attn.py:334-346); with a cache the selection is
@@ -476,7 +492,10 @@ def rectified_attention(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfuse=Fal
         if mask_cache is not None:
             raise RuntimeError("mask re-use needs device-resident tensors (the host-buffer call owns no lasting workspace)")
         return rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr, shape_xfuse)
-    out = Plan(q, k, v, geo, top_k, p_remain, nbr, mask_cache=mask_cache).run()
+    (q, k, v), d_model = pad_head_dim(q, k, v)
+    out = Plan(q, k, v, geo, top_k, p_remain, nbr, mask_cache=mask_cache, scale_dim=d_model).run()
+    if d_model:
+        out = out[..., :d_model].contiguous()
     b, s, h, d = out.shape
     return out if shape_xfuse else out.view(b, s, h * d)
 
@@ -485,12 +504,12 @@ def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None):
     """Kernel 4 alone on a dense block mask: the surface of _triton_block_sparse_attention_onehot
     (rectified_wan21_attn.py:108-117).  q,k,v [B,H,S,D] bf16, block_mask bool [B,H,NQ,NB] -> [B,H,S,D]."""
     _need_cuda(q, "q")
-    b, h, s, d = q.shape
-    assert d in (128,), "head_dim must be 128"
     if q.dtype not in (torch.bfloat16, torch.float16) or k.dtype != q.dtype or v.dtype != q.dtype:
         raise RuntimeError("q, k, v must all be bfloat16 or all float16")
-    if sm_scale is not None and abs(sm_scale - d ** -0.5) > 1e-7:
+    if sm_scale is not None and abs(sm_scale - q.shape[-1] ** -0.5) > 1e-7:
         raise ValueError("only sm_scale = head_dim ** -0.5 is supported")
+    (q, k, v), d_model = pad_head_dim(q, k, v)
+    b, h, s, d = q.shape
     q3, k3, v3 = (t.reshape(b * h, t.shape[2], d).contiguous() for t in (q, k, v))
     skv = k3.shape[1]
     nqb, nkb = (s + 127) // 128, (skv + 127) // 128
@@ -506,8 +525,10 @@ def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None):
         N.check(L.rsa_masked_attention(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o.data_ptr(), b * h, s, skv,
                                        int(kv_len), mk(q3), mk(k3), mk(v3), mk(o), m.data_ptr(), nqb, nkb,
                                        ws.data_ptr(), nbytes, _stream(q.device),
-                                       N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16), "rsa_masked_attention")
-    return o.view(b, h, s, d)
+                                       N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16, d_model),
+                "rsa_masked_attention")
+    o = o.view(b, h, s, d)
+    return o[..., :d_model].contiguous() if d_model else o
 
 
 def set_attention_impl(impl):

@@ -121,6 +121,11 @@ def test_descriptor_validation_and_workspace_size():
     assert lib.rsa_attn_workspace_bytes(C.byref(d)) == lib.rsa_attn_workspace_bytes(C.byref(_desc(G.wan(1000))))
     d.dtype = 7
     assert lib.rsa_attn_workspace_bytes(C.byref(d)) == 0 and b"dtype" in lib.rsa_last_error_string()
+    d = _desc(G.wan(1000))
+    d.scale_dim = 64                                        # 64-dimensional heads zero-padded to 128 columns
+    assert lib.rsa_attn_workspace_bytes(C.byref(d)) > 0
+    d.scale_dim = 129
+    assert lib.rsa_attn_workspace_bytes(C.byref(d)) == 0 and b"scale_dim" in lib.rsa_last_error_string()
     # stage calls refuse a null / short workspace before touching the device
     d = _desc(G.wan(1024))
     assert lib.rsa_block_scores(C.byref(d), None, 0, None) == -4

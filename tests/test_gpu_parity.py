@@ -760,3 +760,44 @@ def test_end_to_end_fp16_vs_oracle(dev, name):
         plan.qkv_prep(*(torch.zeros(1, case["s"], case["heads"] * 128, dtype=torch.float16, device=dev) for _ in range(3)))
     with pytest.raises(RuntimeError):                     # mixed dtypes
         ops.Plan(q.to(dev), k.to(dev).to(torch.bfloat16), v.to(dev), geo, case["top_k"], case["p"], None)
+
+
+# ------------------------------------------------------------------------------- head_dim 64 (CogVideoX)
+def test_head_dim_64_through_the_padded_path(dev):
+    """CogVideoX has 64-dimensional heads (the reference kernel takes Lk in {16, 32, 64, 128}, wan21 :121).  The
+    library's kernels are built for 128 columns; smaller heads run zero-padded with the softmax scale of the model's
+    head_dim (rsa_attn_desc.scale_dim).  Whole call against the oracle on the 64-column tensors, pooled statistics and
+    scores bit-exact against the oracle's (the extra fmaf steps add exact zeros), kernel 4 alone against SDPA."""
+    from rsa_b200 import geometry as G
+    from rsa_b200 import ops
+    heads, t, h, w, text = 2, 4, 16, 16, 226
+    nv = t * h * w
+    s = nv + text
+    q, k, v = O.synth_qkv(heads, s, 64, "walk", 31)
+    nbr = GO.gilbert_block_neighbors(t, h, w)
+    tq, tk, tv = (torch.from_numpy(a).to(dev).to(torch.bfloat16) for a in (q, k, v))
+    geo = G.cogvideo(s, text)
+    out = ops.rectified_attention(tq, tk, tv, geo, 2, 0.3, torch.from_numpy(nbr))
+    assert out.shape == (1, s, heads * 64)
+    ogeo = O.geometry_cogvideo(s, text, 2, 0.3)
+    ref = O.forward(q, k, v, ogeo, nbr)
+    got = out.float().cpu().numpy()
+    assert np.abs(got - ref).max() <= ATOL_OUT and cos_sim(got, ref) >= COS_OUT
+    # stage level: the padded plan's pooled scores are the oracle's 64-column ones, bit for bit
+    (pq, pk, pv), d_model = ops.pad_head_dim(tq, tk, tv)
+    assert d_model == 64 and pq.shape[-1] == 128
+    plan = ops.Plan(pq, pk, pv, geo, 2, 0.3, torch.from_numpy(nbr), debug_dump_probs=True, scale_dim=64)
+    plan.pool_stats()
+    plan.block_scores()
+    plan.block_select()
+    torch.cuda.synchronize()
+    vw = plan.view()
+    _, st = O.head_forward(q[0, 0], k[0, 0], v[0, 0], ogeo, nbr, return_stages=True)
+    assert np.array_equal(vw["q_pool"][0, :, :64].cpu().numpy(), st["qp"]) and not vw["q_pool"][0, :, 64:].any()
+    assert np.array_equal(vw["scores"][0].cpu().numpy(), st["scores"])
+    np.testing.assert_allclose(vw["probs"][0].cpu().numpy(), st["probs"], rtol=3e-5, atol=1e-9)
+    # kernel 4 alone (dense): the surface fullattn(mode="flash") uses on CogVideoX's warm-up steps
+    mask = torch.ones(1, heads, (s + 127) // 128, (s + 127) // 128, dtype=torch.bool, device=dev)
+    dense = ops.masked_attention(tq, tk, tv, mask, s)
+    sd = torch.nn.functional.scaled_dot_product_attention(tq.float(), tk.float(), tv.float())
+    assert dense.shape == tq.shape and (dense.float() - sd).abs().max().item() <= ATOL_OUT

@@ -273,3 +273,36 @@ def test_processor_mask_refresh_interval():
         assert c.calls == 3 and c.valid
         for o in outs:
             assert torch.equal(o[0], ref[0]) and torch.equal(o[1], ref[1])
+
+
+@pytest.mark.gpu
+def test_cogvideox_processor_with_64_dim_heads():
+    """CogVideoX1.5's real geometry: 64-dimensional heads, LayerNorm(64) on q/k, 226 text tokens.  Kernel 0 does not
+    apply (it is built for 128 columns), so the processor runs the reference's op sequence and the attention goes
+    through the zero-padded path (`ops.pad_head_dim`, `scale_dim`); dense warm-up call (kernel 4, all blocks) and
+    sparse call in the dense limit must agree with each other and with PyTorch SDPA through the same module."""
+    from rectified_spaattn import _processors as P
+    dev = torch.device("cuda:0")
+    dim, heads, nv = 256, 4, 1024
+    attn = FakeAttention(dim, heads, head_dim=64, norm="layer").to(dev).to(torch.bfloat16)
+    x = torch.randn(1, nv, dim, device=dev).to(torch.bfloat16)
+    txt = torch.randn(1, 226, dim, device=dev).to(torch.bfloat16)
+    cos, sin, _ = _rope_tables(nv, 64, dev)
+    sp = cog.RectifiedCogVideoXVideoSpaAttnProcessor2_0("sparse", 99, None, 0.3)
+    with torch.no_grad():
+        hd, ed = sp(attn, x, txt, None, (cos, sin))      # call 0: dense (warm-up), kernel 4 with every block kept
+        sp.current_step = 5
+        h, e = sp(attn, x, txt, None, (cos, sin))        # sparse, dense limit
+        # the same layer by hand with SDPA
+        hs = torch.cat([x, txt], dim=1)                  # the processor moves the text tokens last
+        q, k, v = (P.heads_first(f(hs), heads) for f in (attn.to_q, attn.to_k, attn.to_v))
+        q, k = attn.norm_q(q), attn.norm_k(k)
+        q = torch.cat([P.rope_real(q[:, :, :nv], (cos, sin)), q[:, :, nv:]], dim=2)
+        k = torch.cat([P.rope_real(k[:, :, :nv], (cos, sin)), k[:, :, nv:]], dim=2)
+        o = torch.nn.functional.scaled_dot_product_attention(q, k, v).transpose(1, 2).flatten(2, 3)
+        o = attn.to_out[1](attn.to_out[0](o))
+    assert h.shape == (1, nv, dim) and e.shape == (1, 226, dim)
+    _close(h, hd)
+    _close(e, ed)
+    _close(h, o[:, :nv])
+    _close(e, o[:, nv:])

@@ -80,7 +80,10 @@ int rsa_permute_rows(const void* src, void* dst, const int64_t* index, int batch
  * after the per-family geometry (hunyuan :313-332, flux :307-317, cogvideo :307-322, wan21 :299-313) has been
  * reduced to integers by the caller. */
 typedef struct rsa_attn_desc {
-  int32_t batch, heads, seq, head_dim; /* query/key/value are [batch, heads, seq, head_dim] views          */
+  int32_t batch, heads, seq, head_dim; /* query/key/value are [batch, heads, seq, head_dim] views; head_dim */
+                                       /* 128, or 64 (CogVideoX): the kernels work on 128 columns and read the  */
+                                       /* missing ones as zeros (no copy), which changes neither q.k, the pooled */
+                                       /* statistics nor the GAPR test; the scale is head_dim^-1/2 either way    */
   int64_t q_stride[3];                 /* element strides of (batch, head, token); head_dim is contiguous  */
   int64_t k_stride[3];
   int64_t v_stride[3];
@@ -113,11 +116,6 @@ typedef struct rsa_attn_desc {
   int32_t dtype;                       /* enum rsa_dtype of query / key / value / out (kernels 2 and 4; pooled   */
                                        /* statistics, scores and selection are fp32 either way).  Kernel 0       */
                                        /* (rsa_qkv_prep*) follows diffusers' bf16 rounding points: bf16 only.    */
-  int32_t scale_dim;                   /* 0 = head_dim.  Otherwise the softmax scale is scale_dim^-1/2 (block    */
-                                       /* scoring and kernel 4): the tensors are a model's head_dim-scale_dim    */
-                                       /* heads (CogVideoX: 64) zero-padded to 128 columns by the caller -- zero  */
-                                       /* columns change neither q.k, the pooled statistics nor the GAPR test,    */
-                                       /* and the padded output columns are zero.  1 <= scale_dim <= 128.         */
 } rsa_attn_desc;
 
 /* Pointers into the caller's workspace (all device memory, fp32 unless noted). */
@@ -301,14 +299,14 @@ int rsa_rectified_attention_pooled_scatter(const rsa_attn_desc* d, const void* q
 
 /* Kernel 4 alone on a caller-supplied dense block mask (bytes, [BH, n_q_blocks, n_kv_blocks]) -- the literal
  * surface of _triton_block_sparse_attention_onehot(q, k, v, seqlens, block_mask, sm_scale) (wan21 :108-117).
- * q/k/v/out are [BH, seq, 128] with the given token strides; R = 1, C = 0.  workspace must hold
+ * q/k/v/out are [BH, seq, head_dim] with the given token strides; R = 1, C = 0.  workspace must hold
  * rsa_masked_attention_workspace_bytes(). */
 size_t rsa_masked_attention_workspace_bytes(int bh, int n_q_blocks, int n_kv_blocks);
 int rsa_masked_attention(const void* q, const void* k, const void* v, void* out, int bh, int seq_q, int seq_kv,
                          int kv_len, const int64_t q_stride[2], const int64_t k_stride[2],
                          const int64_t v_stride[2], const int64_t o_stride[2], const uint8_t* block_mask,
                          int n_q_blocks, int n_kv_blocks, void* workspace, size_t workspace_bytes, void* stream,
-                         int dtype /* enum rsa_dtype */, int scale_dim /* 0 = 128; see rsa_attn_desc.scale_dim */);
+                         int dtype /* enum rsa_dtype */, int head_dim /* 128 or 64 */);
 
 /* Selects the attention kernel implementation for this process: 0 = tcgen05/TMEM/TMA (product path),
  * 1 = mma.sync cross-check kernel (tests only).  Returns the previous value. */

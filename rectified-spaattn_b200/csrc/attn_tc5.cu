@@ -467,7 +467,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             a.dbg[32768 + 128 + row] = m_ref;
           }
         }
-        if (store) {
+        if (store && c4 * 32 < a.head_dim) {
 #pragma unroll
           for (int j = 0; j < 32; j += 8) {
             uint32_t w[4];
@@ -514,13 +514,15 @@ EncodeTiledFn encode_fn() {
 // [batch, heads, rows, 128] bf16 view with element strides st = (batch, head, row) -> 4-D tensor map whose box is
 // one granule: 64 head_dim elements x 128 rows, 128-byte swizzle; rows past the end read as zeros (the
 // reference zero-pads to a multiple of 128, rectified_wan21_attn.py:299-302).
-int make_map(CUtensorMap* m, const __nv_bfloat16* base, int batch, int heads, int rows, const int64_t* st, bool f16) {
+int make_map(CUtensorMap* m, const __nv_bfloat16* base, int batch, int heads, int rows, const int64_t* st, bool f16,
+             int head_dim) {
   EncodeTiledFn fn = encode_fn();
   if (!fn) RSA_FAIL(RSA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   if ((uintptr_t)base % 16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "q/k/v must be 16-byte aligned");
-  cuuint64_t dims[4] = {128, (cuuint64_t)rows, (cuuint64_t)heads, (cuuint64_t)batch};
+  // head_dim 64: the second 64-column granule of every tile lies outside the tensor and is zero-filled by TMA
+  cuuint64_t dims[4] = {(cuuint64_t)head_dim, (cuuint64_t)rows, (cuuint64_t)heads, (cuuint64_t)batch};
   int64_t sr = st[2], sh = st[1], sb = st[0];
-  if (sr < 128) RSA_FAIL(RSA_ERR_UNSUPPORTED, "token stride must be >= head_dim");
+  if (sr < head_dim) RSA_FAIL(RSA_ERR_UNSUPPORTED, "token stride must be >= head_dim");
   if (heads == 1 && sh == 0) sh = sr * rows;  // a size-1 dimension's stride is never used but must be valid
   if (batch == 1 && sb == 0) sb = sh * heads > sr * rows ? sh * heads : sr * rows;
   if (sh <= 0 || sb <= 0) RSA_FAIL(RSA_ERR_UNSUPPORTED, "head/batch strides must be positive");
@@ -569,14 +571,14 @@ int launch_attention_tc5(const AttnArgs& a, cudaStream_t s) {
   // visual rows [0, vis) and text rows [vis, seq) of each tensor (RowMap); without a text segment the text maps are
   // never used and simply repeat the visual ones
   const int vis_q = a.vis_len < a.seq_q ? a.vis_len : a.seq_q, vis_kv = a.vis_len < a.seq_kv ? a.vis_len : a.seq_kv;
-  if ((rc = make_map(&m.q, a.q, a.batch, a.heads, vis_q, a.qs, a.f16 != 0)) != RSA_OK) return rc;
-  if ((rc = make_map(&m.k, a.k, a.batch, a.heads, vis_kv, a.ks, a.f16 != 0)) != RSA_OK) return rc;
-  if ((rc = make_map(&m.v, a.v, a.batch, a.heads, vis_kv, a.vs, a.f16 != 0)) != RSA_OK) return rc;
+  if ((rc = make_map(&m.q, a.q, a.batch, a.heads, vis_q, a.qs, a.f16 != 0, a.head_dim)) != RSA_OK) return rc;
+  if ((rc = make_map(&m.k, a.k, a.batch, a.heads, vis_kv, a.ks, a.f16 != 0, a.head_dim)) != RSA_OK) return rc;
+  if ((rc = make_map(&m.v, a.v, a.batch, a.heads, vis_kv, a.vs, a.f16 != 0, a.head_dim)) != RSA_OK) return rc;
   m.qt = m.q, m.kt = m.k, m.vt = m.v;
-  if (a.seq_q > vis_q && (rc = make_map(&m.qt, a.q + (int64_t)vis_q * a.qs[2], a.batch, a.heads, a.seq_q - vis_q, a.qs, a.f16 != 0)) != RSA_OK) return rc;
+  if (a.seq_q > vis_q && (rc = make_map(&m.qt, a.q + (int64_t)vis_q * a.qs[2], a.batch, a.heads, a.seq_q - vis_q, a.qs, a.f16 != 0, a.head_dim)) != RSA_OK) return rc;
   if (a.seq_kv > vis_kv) {
-    if ((rc = make_map(&m.kt, a.k + (int64_t)vis_kv * a.ks[2], a.batch, a.heads, a.seq_kv - vis_kv, a.ks, a.f16 != 0)) != RSA_OK) return rc;
-    if ((rc = make_map(&m.vt, a.v + (int64_t)vis_kv * a.vs[2], a.batch, a.heads, a.seq_kv - vis_kv, a.vs, a.f16 != 0)) != RSA_OK) return rc;
+    if ((rc = make_map(&m.kt, a.k + (int64_t)vis_kv * a.ks[2], a.batch, a.heads, a.seq_kv - vis_kv, a.ks, a.f16 != 0, a.head_dim)) != RSA_OK) return rc;
+    if ((rc = make_map(&m.vt, a.v + (int64_t)vis_kv * a.vs[2], a.batch, a.heads, a.seq_kv - vis_kv, a.vs, a.f16 != 0, a.head_dim)) != RSA_OK) return rc;
   }
   const dim3 grid((a.nqt + 1) / 2, a.batch * a.heads);
   if (a.f16) return a.dbg ? launch<true, kDefaultPolyPairs, true>(grid, s, m, a) : launch<false, kDefaultPolyPairs, true>(grid, s, m, a);

@@ -413,7 +413,7 @@ int launch_block_select(const rsa_attn_desc* d, char* ws, const WsLayout& L, cud
   a.text_end_block = d->text_end_block;
   a.kv_blocks_valid = (d->kv_len + 127) / 128;
   a.p_remain = d->p_remain;
-  a.scale = (float)(1.0 / sqrt((double)scale_dim_of(d)));  // == float32(head_dim ** -0.5) of the model's head_dim
+  a.scale = (float)(1.0 / sqrt((double)d->head_dim));  // == float32(head_dim ** -0.5)
   if (L.nqt == 0) return RSA_OK;
   dim3 grid(L.nqt, L.bh);
   block_select_kernel<<<grid, kThreads, 0, s>>>(a);

@@ -59,7 +59,7 @@ struct HostPlan {
 rsa_attn_desc chunk_desc(const rsa_attn_desc* d, int heads, bool out_token_major) {
   rsa_attn_desc c = *d;
   c.heads = heads;
-  const int64_t S = d->seq, D = RSA_HEAD_DIM;
+  const int64_t S = d->seq, D = d->head_dim;
   const int64_t in_st[3] = {heads * S * D, S * D, D};
   for (int i = 0; i < 3; ++i) c.q_stride[i] = c.k_stride[i] = c.v_stride[i] = in_st[i];
   if (out_token_major) {
@@ -81,8 +81,8 @@ int make_host_plan(const rsa_attn_desc* d, int heads_per_chunk, HostPlan* p) {
   p->body_heads = d->heads - tail;
   p->body_chunks = (p->body_heads + p->hc - 1) / p->hc;
   p->n_chunks = p->body_chunks + tail;
-  p->out_token_major = d->o_stride[1] == RSA_HEAD_DIM;
-  p->tensor_bytes = align_up((size_t)d->batch * p->hc * d->seq * RSA_HEAD_DIM * 2, 256);
+  p->out_token_major = d->o_stride[1] == d->head_dim;
+  p->tensor_bytes = align_up((size_t)d->batch * p->hc * d->seq * d->head_dim * 2, 256);
   const rsa_attn_desc c = chunk_desc(d, p->hc, p->out_token_major);
   p->ws_bytes = align_up(make_layout(&c).total, 256);
   size_t o = 0;
@@ -96,9 +96,8 @@ int make_host_plan(const rsa_attn_desc* d, int heads_per_chunk, HostPlan* p) {
 }
 
 // host [B, H, S, D] view (element strides hs) heads [h0, h0+n) -> device [B, n, S, D] contiguous
-int copy_in(const __nv_bfloat16* host, const int64_t* hs, char* dev, int batch, int h0, int n, int64_t S,
+int copy_in(const __nv_bfloat16* host, const int64_t* hs, char* dev, int batch, int h0, int n, int64_t S, int64_t D,
             cudaStream_t s) {
-  const int64_t D = RSA_HEAD_DIM;
   const size_t head_bytes = (size_t)S * D * 2;
   for (int b = 0; b < batch; ++b) {
     const __nv_bfloat16* src0 = host + b * hs[0] + (int64_t)h0 * hs[1];
@@ -121,8 +120,7 @@ int copy_in(const __nv_bfloat16* host, const int64_t* hs, char* dev, int batch, 
 
 // device chunk ([B, S, n, D] if token_major else [B, n, S, D]) -> host view with element strides os
 int copy_out(const char* dev, __nv_bfloat16* host, const int64_t* os, bool token_major, int batch, int h0, int n,
-             int64_t S, cudaStream_t s) {
-  const int64_t D = RSA_HEAD_DIM;
+             int64_t S, int64_t D, cudaStream_t s) {
   for (int b = 0; b < batch; ++b) {
     const char* src0 = dev + (size_t)b * S * n * D * 2;
     __nv_bfloat16* dst0 = host + b * os[0] + (int64_t)h0 * os[1];
@@ -183,7 +181,7 @@ extern "C" int rsa_rectified_attention_host(const rsa_attn_desc* d, const void* 
     if (c >= 2) RSA_CUDA_CHECK(cudaStreamWaitEvent(lanes->h2d, lanes->computed[slot], 0));
     for (int t = 0; t < 3; ++t)
       if ((rc = copy_in((const __nv_bfloat16*)host_in[t], host_st[t], base + p.off_in[slot][t], d->batch, h0, n,
-                        d->seq, lanes->h2d)) != RSA_OK)
+                        d->seq, d->head_dim, lanes->h2d)) != RSA_OK)
         return rc;
     RSA_CUDA_CHECK(cudaEventRecord(lanes->in_ready[slot], lanes->h2d));
     // compute lane (the caller's stream): needs the inputs, and the slot's output staging drained (chunk c-2)
@@ -198,7 +196,7 @@ extern "C" int rsa_rectified_attention_host(const rsa_attn_desc* d, const void* 
     // D2H lane
     RSA_CUDA_CHECK(cudaStreamWaitEvent(lanes->d2h, lanes->computed[slot], 0));
     if ((rc = copy_out(base + p.off_out[slot], (__nv_bfloat16*)out, d->o_stride, p.out_token_major, d->batch, h0, n,
-                       d->seq, lanes->d2h)) != RSA_OK)
+                       d->seq, d->head_dim, lanes->d2h)) != RSA_OK)
       return rc;
     RSA_CUDA_CHECK(cudaEventRecord(lanes->out_done[slot], lanes->d2h));
   }

@@ -63,6 +63,7 @@ struct PoolArgs {
   float* mad[3];              // q_mad, k_mad, nullptr
   int out_rows[3];            // rows per head of the mean arrays (NQ, NKC, NB)
   int heads;
+  int head_dim;               // 128 or 64: columns >= head_dim do not exist in x and pool as zeros
   // text keys copied as fp32 rows behind the pooled keys
   int text_keys, text_from;   // a, memory row of the first text token (= vis_len)
 };
@@ -275,7 +276,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const 
       const __nv_bfloat16* src = a.x[1] + b * a.stride[1][0] + h * a.stride[1][1] + (int64_t)tok * a.stride[1][2];
       float f[8];
       uint4 u = make_uint4(0, 0, 0, 0);
-      if (tok + a.gap < a.valid_rows[1]) u = *reinterpret_cast<const uint4*>(src + 8 * (tid & 15));
+      if (tok + a.gap < a.valid_rows[1] && 8 * (tid & 15) < a.head_dim) u = *reinterpret_cast<const uint4*>(src + 8 * (tid & 15));
       unpack8<kF16>(u, f);
       float* dst = a.mean[1] + ((int64_t)bh * a.out_rows[1] + a.n_blk[1] + t) * 128 + 8 * (tid & 15);
       reinterpret_cast<float4*>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
@@ -323,7 +324,7 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const 
     for (int it = 0; it < 8; ++it) {
       const int r = row0 + 2 * it;
       raw[it] = make_uint4(0, 0, 0, 0);
-      if (r < valid) raw[it] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(r - shift) * ts + col));
+      if (r < valid && col < a.head_dim) raw[it] = __ldg(reinterpret_cast<const uint4*>(base + (int64_t)(r - shift) * ts + col));
     }
   }
 
@@ -418,6 +419,7 @@ static PoolArgs pool_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a.out_rows[1] = L.nkc;
   a.out_rows[2] = L.nb;
   a.heads = d->heads;
+  a.head_dim = d->head_dim;
   a.text_keys = L.a;
   a.text_from = rm.vis_len;
   return a;
@@ -497,6 +499,7 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
   } else {
     a = PoolArgs{};
     a.heads = d->heads;
+    a.head_dim = d->head_dim;
     a.nq_vis = rm.nq_vis;
     a.vis_len = rm.vis_len;
     a.gap = rm.gap;

@@ -22,11 +22,10 @@ void set_error(const char* fmt, ...) {
 
 int validate_desc(const rsa_attn_desc* d) {
   if (!d) RSA_FAIL(RSA_ERR_ARG, "descriptor is null");
-  if (d->head_dim != RSA_HEAD_DIM)
-    RSA_FAIL(RSA_ERR_UNSUPPORTED, "head_dim must be 128 (got %d); the reference asserts Lk in {16,32,64,128}", d->head_dim);
+  if (d->head_dim != RSA_HEAD_DIM && d->head_dim != 64)
+    RSA_FAIL(RSA_ERR_UNSUPPORTED, "head_dim must be 128 or 64 (got %d); the reference asserts Lk in {16,32,64,128}", d->head_dim);
   if (d->batch <= 0 || d->heads <= 0 || d->seq <= 0) RSA_FAIL(RSA_ERR_ARG, "batch/heads/seq must be positive");
   if (d->dtype != RSA_DTYPE_BF16 && d->dtype != RSA_DTYPE_F16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "dtype %d is not one of rsa_dtype (bf16, fp16)", d->dtype);
-  if (d->scale_dim < 0 || d->scale_dim > RSA_HEAD_DIM) RSA_FAIL(RSA_ERR_ARG, "scale_dim=%d out of [0, 128]", d->scale_dim);
   if ((int64_t)d->batch * d->heads > 65535) RSA_FAIL(RSA_ERR_UNSUPPORTED, "batch*heads > 65535");
   if (d->family != RSA_FAMILY_WAN && d->family != RSA_FAMILY_JOINT) RSA_FAIL(RSA_ERR_ARG, "unknown family %d", d->family);
   if (d->vis_len < 0 || d->vis_len > d->seq) RSA_FAIL(RSA_ERR_ARG, "vis_len=%d out of [0, seq]", d->vis_len);
@@ -150,7 +149,8 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->o_table = nullptr;
   a->peer_rows = a->peer_head0 = 0;
   a->peer_os[0] = a->peer_os[1] = 0;
-  a->scale_log2 = (float)((1.0 / sqrt((double)scale_dim_of(d))) * 1.4426950408889634);
+  a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.4426950408889634);
+  a->head_dim = d->head_dim;
   a->f16 = d->dtype == RSA_DTYPE_F16;
   a->dbg = g_attention_dbg;
   a->dbg_flags = g_attention_dbg_flags;
@@ -161,7 +161,7 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
 // pair schedule kernel 4 walks (mask re-use)
 static int launch_attention(const AttnArgs& a, cudaStream_t s, bool reschedule = true) {
   if (g_attention_impl == 1) {
-    if (a.f16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "the mma.sync cross-check kernel is bf16 only");
+    if (a.f16 || a.head_dim != RSA_HEAD_DIM) RSA_FAIL(RSA_ERR_UNSUPPORTED, "the mma.sync cross-check kernel is bf16 / head_dim 128 only");
     return launch_attention_mma(a, s);
   }
   int rc = reschedule ? launch_pair_schedule(a, s) : RSA_OK;
@@ -398,6 +398,7 @@ extern "C" int rsa_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, cons
   if (rc != RSA_OK) return rc;
   if (!p) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: descriptor is null");
   if (d->dtype != RSA_DTYPE_BF16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep follows diffusers' bf16 rounding points: bf16 only");
+  if (d->head_dim != RSA_HEAD_DIM) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: head_dim 128 only");
   if (!q_src || !k_src || !v_src || !q || !k || !v) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: null tensor");
   const RowMap rm = row_map(d);
   if (p->rows < 1) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep: rows must be positive");
@@ -448,7 +449,7 @@ extern "C" int rsa_qkv_prep_gather(const rsa_prep_desc* p, const rsa_attn_desc* 
   if (rc != RSA_OK) return rc;
   if ((rc = validate_route(d, route, true, false)) != RSA_OK) return rc;
   if (!p || !q || !k || !v) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: null pointer");
-  if (d->dtype != RSA_DTYPE_BF16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep_gather: bf16 only");
+  if (d->dtype != RSA_DTYPE_BF16 || d->head_dim != RSA_HEAD_DIM) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep_gather: bf16 and head_dim 128 only");
   if (p->rows != d->seq || p->dst_row != 0) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rows must be seq and dst_row 0");
   if (p->norm != 0 && p->norm != 1) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep_gather: norm must be 0 or 1");
   if (p->norm && (!p->q_weight || !p->k_weight)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: norm weights are null");
@@ -467,6 +468,7 @@ extern "C" int rsa_rectified_attention_pooled_scatter(const rsa_attn_desc* d, co
   int rc = check_ws(d, workspace, bytes, &L);
   if (rc != RSA_OK) return rc;
   if ((rc = validate_route(d, route, false, true)) != RSA_OK) return rc;
+  if (d->head_dim != RSA_HEAD_DIM) RSA_FAIL(RSA_ERR_UNSUPPORTED, "the scatter epilogue is built for head_dim 128");
   if (!q || !k || !v) RSA_FAIL(RSA_ERR_ARG, "rsa_rectified_attention_pooled_scatter: null tensor");
   if (g_attention_impl != 0) RSA_FAIL(RSA_ERR_UNSUPPORTED, "the scatter epilogue exists in the tcgen05 kernel only");
   char* ws = (char*)workspace;
@@ -533,10 +535,10 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
                                     int seq_kv, int kv_len, const int64_t q_stride[2], const int64_t k_stride[2],
                                     const int64_t v_stride[2], const int64_t o_stride[2], const uint8_t* block_mask,
                                     int n_q_blocks, int n_kv_blocks, void* workspace, size_t bytes, void* stream,
-                                    int dtype, int scale_dim) {
+                                    int dtype, int head_dim) {
   if (!q || !k || !v || !out || !block_mask) RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: null pointer");
   if (dtype != RSA_DTYPE_BF16 && dtype != RSA_DTYPE_F16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_masked_attention: dtype %d", dtype);
-  if (scale_dim < 0 || scale_dim > RSA_HEAD_DIM) RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: scale_dim=%d out of [0, 128]", scale_dim);
+  if (head_dim != RSA_HEAD_DIM && head_dim != 64) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_masked_attention: head_dim must be 128 or 64 (got %d)", head_dim);
   if (bh <= 0 || bh > 65535 || seq_q <= 0 || seq_kv <= 0 || kv_len < 1 || kv_len > seq_kv)
     RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: bad sizes");
   if (n_q_blocks != (seq_q + 127) / 128 || n_kv_blocks != (seq_kv + 127) / 128)
@@ -586,7 +588,8 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   a.o_table = nullptr;
   a.peer_rows = a.peer_head0 = 0;
   a.peer_os[0] = a.peer_os[1] = 0;
-  a.scale_log2 = (float)((1.0 / sqrt(scale_dim > 0 ? (double)scale_dim : 128.0)) * 1.4426950408889634);
+  a.scale_log2 = (float)((1.0 / sqrt((double)head_dim)) * 1.4426950408889634);
+  a.head_dim = head_dim;
   a.f16 = dtype == RSA_DTYPE_F16;
   a.dbg = g_attention_dbg;
   a.dbg_flags = g_attention_dbg_flags;

@@ -32,9 +32,7 @@ def build_index(query, key, geo, top_k, prob_threshold, block_neighbor_list):
         # the reference passes query[:, :, :normal_tokens]; the kernels index the visual rows themselves
         pad = torch.zeros(b, h, s - query.shape[2], d, dtype=query.dtype, device=query.device)
         query = torch.cat([query, pad], dim=2)
-    (query, key), d_model = ops.pad_head_dim(query, key)
-    plan = ops.Plan(query, key, key, geo, top_k, prob_threshold, block_neighbor_list, debug_dump_probs=True,
-                    scale_dim=d_model)
+    plan = ops.Plan(query, key, key, geo, top_k, prob_threshold, block_neighbor_list, debug_dump_probs=True)
     plan.pool_stats()
     plan.block_scores()
     plan.block_select()

@@ -30,7 +30,7 @@ class AttnDesc(C.Structure):
         ("kv_len", C.c_int32), ("kv_zero_from", C.c_int32), ("text_end_block", C.c_int32),
         ("text_q_valid", C.c_int32), ("top_k", C.c_int32), ("p_remain", C.c_float),
         ("first_frame_blocks", C.c_int32), ("nbr_rows", C.c_int32), ("nbr_cols", C.c_int32),
-        ("nbr", C.c_void_p), ("debug_dump_probs", C.c_int32), ("vis_len", C.c_int32), ("dtype", C.c_int32), ("scale_dim", C.c_int32),
+        ("nbr", C.c_void_p), ("debug_dump_probs", C.c_int32), ("vis_len", C.c_int32), ("dtype", C.c_int32),
     ]
 
 

@@ -146,7 +146,7 @@ class Plan:
     """One call's descriptor + workspace; build once per (shape, geometry) and reuse across layers/steps."""
 
     def __init__(self, q, k, v, geo: G.BlockGeometry, top_k, p_remain, nbr=None, debug_dump_probs=False, out=None,
-                 private_workspace=False, mask_cache=None, scale_dim=0):
+                 private_workspace=False, mask_cache=None):
         for t, n in ((q, "query"), (k, "key"), (v, "value")):
             _need_cuda(t, n)
             if t.dtype not in (torch.bfloat16, torch.float16) or t.dtype != q.dtype:
@@ -154,10 +154,10 @@ class Plan:
         b, h, s, d = q.shape
         if k.shape != q.shape or v.shape != q.shape:
             raise RuntimeError("query/key/value shapes differ")
-        if d != 128:
-            # same precondition family as the reference's `assert Lk in {16, 32, 64, 128}` (wan21 :121); smaller
-            # head dimensions come in zero-padded (pad_head_dim / rectified_attention do that)
-            raise AssertionError("head_dim must be 128 (pad smaller heads with pad_head_dim and pass scale_dim)")
+        if d not in (64, 128):
+            # same precondition family as the reference's `assert Lk in {16, 32, 64, 128}` (wan21 :121); 128 is what
+            # every BASELINE model has, 64 is CogVideoX (the kernels read the missing 64 columns as zeros)
+            raise AssertionError("head_dim must be 128 or 64")
         if s != geo.seq:
             raise ValueError("geometry was built for a different sequence length")
         self.device = q.device
@@ -170,7 +170,6 @@ class Plan:
         desc = _fill_desc(N.AttnDesc(), (b, h, s, d), [_strides3(t) for t in (q, k, v, o4)], geo, top_k, p_remain,
                           self.nbr_dev, debug_dump_probs)
         desc.dtype = N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16
-        desc.scale_dim = int(scale_dim)     # model head_dim when q, k, v are zero-padded to 128 columns (pad_head_dim)
         self.desc = desc
         L = N.lib()
         self.ws_bytes = L.rsa_attn_workspace_bytes(C.byref(desc))
@@ -182,7 +181,7 @@ class Plan:
         self.mask_cache = mask_cache
         if mask_cache is not None:    # the cache owns the workspace (it survives this plan) and says what to re-use
             # the neighbour matrix is a constant of the latent grid: identified by the caller's storage, not its bytes
-            key = (self.shape, geo, int(top_k), float(p_remain), int(scale_dim), str(q.dtype),
+            key = (self.shape, geo, int(top_k), float(p_remain), str(q.dtype),
                    None if nbr is None else (nbr.data_ptr(), tuple(nbr.shape), nbr._version))
             self.mask_mode, self.ws = mask_cache.next_mode(key, q.device, self.ws_bytes)
         else:
@@ -254,8 +253,9 @@ class Plan:
         [B, rows, H*128] (head split, per-head RMSNorm with bf16 weights, rotary embedding on the first `rope_rows`
         tokens, re-layout) and, with pool=True, the pooled statistics of those blocks."""
         b, h, s, d = self.shape
-        if self.q.dtype != torch.bfloat16:
-            raise RuntimeError("kernel 0 follows diffusers' bf16 rounding points: bfloat16 only")
+        if self.q.dtype != torch.bfloat16 or d != 128:
+            raise RuntimeError("kernel 0 follows diffusers' bf16 rounding points and is built for 128 columns: "
+                               "bfloat16, head_dim 128 only")
         for t, n in ((q_src, "q_src"), (k_src, "k_src"), (v_src, "v_src")):
             _need_cuda(t, n)
             if t.dtype != torch.bfloat16 or t.dim() != 3 or t.shape[0] != b or t.shape[2] != h * d or t.stride(2) != 1:
@@ -395,8 +395,8 @@ def rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfus
     b, h, s, d = q.shape
     if k.shape != q.shape or v.shape != q.shape:
         raise RuntimeError("query/key/value shapes differ")
-    if d != 128:
-        raise AssertionError("head_dim must be 128")
+    if d not in (64, 128):
+        raise AssertionError("head_dim must be 128 or 64")
     if s != geo.seq:
         raise ValueError("geometry was built for a different sequence length")
     if out is None:
@@ -423,20 +423,6 @@ def rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfus
                                                _stream(device)), "rsa_rectified_attention_host")
     out = out.view(b, s, h, d)
     return out if shape_xfuse else out.view(b, s, h * d)
-
-
-def pad_head_dim(*tensors):
-    """[..., d] -> [..., 128] with zero columns for d in {16, 32, 64} (the reference kernel's other head dimensions,
-    `assert Lk in {16, 32, 64, 128}`, wan21 :121; CogVideoX has 64).  Zero columns change neither q.k^T, the pooled
-    statistics nor the GAPR test, and the padded output columns come out as zeros; the softmax scale must stay
-    d^-1/2, which the descriptor's `scale_dim` carries.  Twice the tensor-core work of a native d = 64 kernel: a
-    functional path for the one family that needs it, not a tuned one."""
-    d = tensors[0].shape[-1]
-    if d == 128:
-        return tensors, 0
-    if d not in (16, 32, 64):
-        raise AssertionError(f"head_dim must be one of 16, 32, 64, 128 (got {d})")
-    return tuple(torch.nn.functional.pad(t, (0, 128 - d)) for t in tensors), d
 
 
 class MaskCache:
@@ -492,10 +478,7 @@ def rectified_attention(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfuse=Fal
         if mask_cache is not None:
             raise RuntimeError("mask re-use needs device-resident tensors (the host-buffer call owns no lasting workspace)")
         return rectified_attention_host(q, k, v, geo, top_k, p_remain, nbr, shape_xfuse)
-    (q, k, v), d_model = pad_head_dim(q, k, v)
-    out = Plan(q, k, v, geo, top_k, p_remain, nbr, mask_cache=mask_cache, scale_dim=d_model).run()
-    if d_model:
-        out = out[..., :d_model].contiguous()
+    out = Plan(q, k, v, geo, top_k, p_remain, nbr, mask_cache=mask_cache).run()
     b, s, h, d = out.shape
     return out if shape_xfuse else out.view(b, s, h * d)
 
@@ -508,8 +491,9 @@ def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None):
         raise RuntimeError("q, k, v must all be bfloat16 or all float16")
     if sm_scale is not None and abs(sm_scale - q.shape[-1] ** -0.5) > 1e-7:
         raise ValueError("only sm_scale = head_dim ** -0.5 is supported")
-    (q, k, v), d_model = pad_head_dim(q, k, v)
     b, h, s, d = q.shape
+    if d not in (64, 128):
+        raise AssertionError("head_dim must be 128 or 64")
     q3, k3, v3 = (t.reshape(b * h, t.shape[2], d).contiguous() for t in (q, k, v))
     skv = k3.shape[1]
     nqb, nkb = (s + 127) // 128, (skv + 127) // 128
@@ -525,10 +509,9 @@ def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None):
         N.check(L.rsa_masked_attention(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o.data_ptr(), b * h, s, skv,
                                        int(kv_len), mk(q3), mk(k3), mk(v3), mk(o), m.data_ptr(), nqb, nkb,
                                        ws.data_ptr(), nbytes, _stream(q.device),
-                                       N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16, d_model),
+                                       N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16, d),
                 "rsa_masked_attention")
-    o = o.view(b, h, s, d)
-    return o[..., :d_model].contiguous() if d_model else o
+    return o.view(b, h, s, d)
 
 
 def set_attention_impl(impl):

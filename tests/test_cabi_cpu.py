@@ -110,7 +110,9 @@ def test_descriptor_validation_and_workspace_size():
     d = _desc(G.hunyuan(1280, 1224))
     n = lib.rsa_attn_workspace_bytes(C.byref(d))
     assert n > 0 and n % 256 == 0
-    d.head_dim = 64
+    d.head_dim = 64                                         # CogVideoX: same workspace (statistics are 128 wide)
+    assert lib.rsa_attn_workspace_bytes(C.byref(d)) == n
+    d.head_dim = 96
     assert lib.rsa_attn_workspace_bytes(C.byref(d)) == 0
     assert b"head_dim" in lib.rsa_last_error_string()
     d = _desc(G.wan(1000))
@@ -122,10 +124,8 @@ def test_descriptor_validation_and_workspace_size():
     d.dtype = 7
     assert lib.rsa_attn_workspace_bytes(C.byref(d)) == 0 and b"dtype" in lib.rsa_last_error_string()
     d = _desc(G.wan(1000))
-    d.scale_dim = 64                                        # 64-dimensional heads zero-padded to 128 columns
-    assert lib.rsa_attn_workspace_bytes(C.byref(d)) > 0
-    d.scale_dim = 129
-    assert lib.rsa_attn_workspace_bytes(C.byref(d)) == 0 and b"scale_dim" in lib.rsa_last_error_string()
+    d.head_dim = 32                                         # 128 and 64 (CogVideoX) are built, nothing else
+    assert lib.rsa_attn_workspace_bytes(C.byref(d)) == 0 and b"head_dim" in lib.rsa_last_error_string()
     # stage calls refuse a null / short workspace before touching the device
     d = _desc(G.wan(1024))
     assert lib.rsa_block_scores(C.byref(d), None, 0, None) == -4

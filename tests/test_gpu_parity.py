@@ -763,11 +763,12 @@ def test_end_to_end_fp16_vs_oracle(dev, name):
 
 
 # ------------------------------------------------------------------------------- head_dim 64 (CogVideoX)
-def test_head_dim_64_through_the_padded_path(dev):
+def test_head_dim_64(dev):
     """CogVideoX has 64-dimensional heads (the reference kernel takes Lk in {16, 32, 64, 128}, wan21 :121).  The
-    library's kernels are built for 128 columns; smaller heads run zero-padded with the softmax scale of the model's
-    head_dim (rsa_attn_desc.scale_dim).  Whole call against the oracle on the 64-column tensors, pooled statistics and
-    scores bit-exact against the oracle's (the extra fmaf steps add exact zeros), kernel 4 alone against SDPA."""
+    kernels work on 128 columns and read the missing 64 as zeros (kernel 2 by predication, kernel 4 through TMA's
+    out-of-bounds fill), with the scale of the real head_dim; no copy.  Whole call against the oracle on the 64-column
+    tensors; pooled statistics and scores bit-exact (the extra fmaf steps add exact zeros); kernel 4 alone against
+    SDPA; the host-buffer call bit-identical to the device call."""
     from rsa_b200 import geometry as G
     from rsa_b200 import ops
     heads, t, h, w, text = 2, 4, 16, 16, 226
@@ -783,10 +784,7 @@ def test_head_dim_64_through_the_padded_path(dev):
     ref = O.forward(q, k, v, ogeo, nbr)
     got = out.float().cpu().numpy()
     assert np.abs(got - ref).max() <= ATOL_OUT and cos_sim(got, ref) >= COS_OUT
-    # stage level: the padded plan's pooled scores are the oracle's 64-column ones, bit for bit
-    (pq, pk, pv), d_model = ops.pad_head_dim(tq, tk, tv)
-    assert d_model == 64 and pq.shape[-1] == 128
-    plan = ops.Plan(pq, pk, pv, geo, 2, 0.3, torch.from_numpy(nbr), debug_dump_probs=True, scale_dim=64)
+    plan = ops.Plan(tq, tk, tv, geo, 2, 0.3, torch.from_numpy(nbr), debug_dump_probs=True)
     plan.pool_stats()
     plan.block_scores()
     plan.block_select()
@@ -801,3 +799,10 @@ def test_head_dim_64_through_the_padded_path(dev):
     dense = ops.masked_attention(tq, tk, tv, mask, s)
     sd = torch.nn.functional.scaled_dot_product_attention(tq.float(), tk.float(), tv.float())
     assert dense.shape == tq.shape and (dense.float() - sd).abs().max().item() <= ATOL_OUT
+    # host-buffer call
+    hq, hk, hv = (x.cpu().pin_memory() for x in (tq, tk, tv))
+    hout = ops.rectified_attention_host(hq, hk, hv, geo, 2, 0.3, torch.from_numpy(nbr))
+    torch.cuda.synchronize()
+    assert torch.equal(hout.view(torch.int16), out.cpu().view(torch.int16))
+    with pytest.raises(RuntimeError):                     # kernel 0 is built for 128 columns
+        plan.qkv_prep(*(torch.zeros(1, s, heads * 64, dtype=torch.bfloat16, device=dev) for _ in range(3)))

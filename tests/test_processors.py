@@ -279,7 +279,7 @@ def test_processor_mask_refresh_interval():
 def test_cogvideox_processor_with_64_dim_heads():
     """CogVideoX1.5's real geometry: 64-dimensional heads, LayerNorm(64) on q/k, 226 text tokens.  Kernel 0 does not
     apply (it is built for 128 columns), so the processor runs the reference's op sequence and the attention goes
-    through the zero-padded path (`ops.pad_head_dim`, `scale_dim`); dense warm-up call (kernel 4, all blocks) and
+    through kernels 2-4 with head_dim 64 (missing columns read as zeros); dense warm-up call (kernel 4, all blocks) and
     sparse call in the dense limit must agree with each other and with PyTorch SDPA through the same module."""
     from rectified_spaattn import _processors as P
     dev = torch.device("cuda:0")

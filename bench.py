@@ -112,17 +112,17 @@ def measured_peaks():
     return dict(bf16=1590.0, bf16_sustained=1400.0, hbm=6650.0, source="fallback")
 
 
-def synth_heads_device(heads, head0, s, regime, dev, seed=0):
-    """Q, K, V [1, heads, s, 128] bf16 on the device (SURVEY 8d regimes), one generator stream per global head."""
+def synth_heads_device(heads, head0, s, regime, dev, seed=0, d=128):
+    """Q, K, V [1, heads, s, d] bf16 on the device (SURVEY 8d regimes), one generator stream per global head."""
     import torch
     nb = (s + 127) // 128
-    outs = [torch.empty(1, heads, s, 128, dtype=torch.bfloat16, device=dev) for _ in range(3)]
+    outs = [torch.empty(1, heads, s, d, dtype=torch.bfloat16, device=dev) for _ in range(3)]
     for hi in range(heads):
         g = torch.Generator(device=dev).manual_seed(seed * 1000 + head0 + hi)
         for ti in range(3):
-            x = torch.randn(nb * 128, 128, generator=g, device=dev)
+            x = torch.randn(nb * 128, d, generator=g, device=dev)
             if ti < 2 and regime != "iid":
-                mu = torch.randn(nb, 128, generator=g, device=dev) * (0.35 if regime == "walk" else 1.0)
+                mu = torch.randn(nb, d, generator=g, device=dev) * (0.35 if regime == "walk" else 1.0)
                 if regime == "walk":
                     mu = torch.cumsum(mu, dim=0)
                 x = x + mu.repeat_interleave(128, dim=0)

@@ -318,7 +318,9 @@ int rsa_set_attention_impl(int impl);
  * this DEVICE buffer of >= 34048 floats. */
 void rsa_debug_set_attention_dump(float* device_buffer);
 /* Bring-up ablations, honoured only while a dump buffer is set: bit 0 = skip the softmax arithmetic (results are
- * garbage; measures the TMA + tensor pipeline alone), bit 1 = no K/V loads after the first ring fill. */
+ * garbage; measures the TMA + tensor pipeline alone), bit 1 = no K/V loads after the first ring fill.  Bit 2 is
+ * honoured without a dump buffer: head_dim 64 runs through the 128-column instantiation (second granule = TMA zero
+ * fill) instead of the 64-column one -- the cross-check and the A/B timing of the two forms. */
 void rsa_debug_set_attention_flags(int flags);
 
 #ifdef __cplusplus

@@ -59,10 +59,9 @@ enum {
 static_assert(B_COUNT * 8 + 4 <= 256, "barrier region");
 static_assert(kSmemBytes <= 232448, "shared memory per CTA");
 
-constexpr uint32_t kIdescQK = umma_idesc_bf16(128, 128, false);
-constexpr uint32_t kIdescPV = umma_idesc_bf16(128, 128, true);
-constexpr uint32_t kIdescQKh = umma_idesc_f16(128, 128, false);  // fp16 operands (rsa_attn_desc.dtype)
-constexpr uint32_t kIdescPVh = umma_idesc_f16(128, 128, true);
+// head_dim 64 instantiation: share of the exponentials on the FMA pipe (see kDefaultPolyPairs); that form has 640
+// tensor-pipe cycles per kept pair against 1024 MUFU cycles, so unlike the 128-column form it is MUFU-bound
+constexpr int kDefaultPolyPairs64 = 1;  // CogVideoX1.5 shape, kernel 4: 8.30 / 8.09 / 8.30 ms for 0 / 1 / 2; RSA_TC5_POLY overrides
 
 __device__ __forceinline__ float u2f(uint32_t u) { return __uint_as_float(u); }
 __device__ __forceinline__ uint32_t f2u(float f) { return __float_as_uint(f); }
@@ -94,7 +93,11 @@ constexpr int kTraceBase = 33024, kTraceSteps = 64, kTraceSlots = 16;
       a.dbg[kTraceBase + (step) * kTraceSlots + (slot)] = (float)(clock64() - t0);                     \
   } while (0)
 
-template <bool kDebug, int kPolyPairs, bool kF16 = false>
+// kD: head_dim the instantiation is built for.  128: two 64-column granules per Q/K/V tile (a tensor whose head_dim is
+// 64 can still run here: its tensor maps zero-fill the second granule).  64 (CogVideoX): one granule per tile, S = Q K^T
+// over 4 k-steps instead of 8, O = P V as N = 64 MMAs into 64 TMEM columns -- 640 instead of 1024 tensor-pipe cycles
+// per kept pair, half the K/V bytes; the softmax side is the same, so this form is MUFU-bound rather than tensor-bound.
+template <bool kDebug, int kPolyPairs, bool kF16 = false, int kD = 128>
 __global__ void __launch_bounds__(kThreads, 1)
 attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                 const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmQt,
@@ -120,6 +123,10 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int nsh = min(max(a.pair_shared[(int64_t)bh * gridDim.x + pair], 0), min(cnt0, cnt1));
   const int rounds = max(cnt0, cnt1);
 
+  constexpr int kG = kD / 64;                       // granules per Q/K/V tile
+  constexpr uint32_t kTileBytes = kG * kGranule;
+  constexpr uint32_t kIdQK = kF16 ? umma_idesc_f16(128, 128, false) : umma_idesc_bf16(128, 128, false);
+  constexpr uint32_t kIdPV = kF16 ? umma_idesc_f16(128, kD, true) : umma_idesc_bf16(128, kD, true);
   const long long t0 = kDebug ? clock64() : 0;
   const bool dbg = kDebug && a.dbg != nullptr && lrow0 == 0;
   const uint32_t sbase = smem_u32(smem);
@@ -171,9 +178,9 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool txt = tile >= a.nq_vis;
             const void* map = txt ? (const void*)&tmQt : (const void*)&tmQ;
             const int row = (txt ? tile - a.nq_vis : tile) * 128;
-            mbar_arrive_expect_tx(bar(B_QFULL + s), 2 * kGranule);
+            mbar_arrive_expect_tx(bar(B_QFULL + s), kTileBytes);
             tma_load_4d(sbase + kOffQ + 2 * s * kGranule, map, bar(B_QFULL + s), 0, row, h, b);
-            tma_load_4d(sbase + kOffQ + (2 * s + 1) * kGranule, map, bar(B_QFULL + s), 64, row, h, b);
+            if (kG == 2) tma_load_4d(sbase + kOffQ + (2 * s + 1) * kGranule, map, bar(B_QFULL + s), 64, row, h, b);
           }
         }
       }
@@ -205,9 +212,9 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 if (kDebug && (a.dbg_flags & 2) && n >= kStages) {  // ablation: no K/V traffic after the first fill
                   mbar_arrive(bar(B_KVFULL + st));
                 } else {
-                  mbar_arrive_expect_tx(bar(B_KVFULL + st), 2 * kGranule);
+                  mbar_arrive_expect_tx(bar(B_KVFULL + st), kTileBytes);
                   tma_load_4d(dst, map, bar(B_KVFULL + st), 0, row, h, b);
-                  tma_load_4d(dst + kGranule, map, bar(B_KVFULL + st), 64, row, h, b);
+                  if (kG == 2) tma_load_4d(dst + kGranule, map, bar(B_KVFULL + st), 64, row, h, b);
                 }
                 ++n;
               }
@@ -249,13 +256,13 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (leader) {
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks)  // 16 keys = 16 rows of 128 B; P: 16 bf16 = 8 TMEM columns
-                umma_ts(tO, tS + ks * 8, vd + 128 * ks, kF16 ? kIdescPVh : kIdescPV, (r > 1 || ks > 0) ? 1u : 0u);
+                umma_ts(tO, tS + ks * 8, vd + 128 * ks, kIdPV, (r > 1 || ks > 0) ? 1u : 0u);
             }
             mbar_wait(bar(B_PHALF + 2 * s + 1), (r - 1) & 1);
             tc_fence_after();
             if (leader) {
 #pragma unroll
-              for (int ks = 4; ks < 8; ++ks) umma_ts(tO, tS + ks * 8, vd + 128 * ks, kF16 ? kIdescPVh : kIdescPV, 1u);
+              for (int ks = 4; ks < 8; ++ks) umma_ts(tO, tS + ks * 8, vd + 128 * ks, kIdPV, 1u);
               if (release) umma_commit(bar(B_KVEMPTY + st));
               if (r == cnt) umma_commit(bar(B_OFULL + s));
             }
@@ -278,9 +285,9 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             RSA_TRACE(dbg && s == 0 && leader, r, 12);
             if (leader) {
 #pragma unroll
-              for (int ks = 0; ks < 8; ++ks) {  // 16 head_dim elements = 32 bytes inside the swizzle atom
+              for (int ks = 0; ks < kD / 16; ++ks) {  // 16 head_dim elements = 32 bytes inside the swizzle atom
                 const uint32_t off = (ks >> 2) * (kGranule >> 4) + 2 * (ks & 3);
-                umma_ss(tS, qd + off, kd + off, kF16 ? kIdescQKh : kIdescQK, ks != 0);
+                umma_ss(tS, qd + off, kd + off, kIdQK, ks != 0);
               }
               if (release) umma_commit(bar(B_KVEMPTY + st));
               umma_commit(bar(B_SFULL + s));
@@ -374,7 +381,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (need) m_ref = mx_s;
             l *= alpha;
 #pragma unroll
-            for (int c4 = 0; c4 < 4; ++c4) {
+            for (int c4 = 0; c4 < kD / 32; ++c4) {
               uint32_t o[32];
               tmem_ld32(tO + c4 * 32, o);
               tmem_wait_ld();
@@ -450,7 +457,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         tc_fence_after();
       }
 #pragma unroll
-      for (int c4 = 0; c4 < 4; ++c4) {
+      for (int c4 = 0; c4 < kD / 32; ++c4) {
         uint32_t o[32];
         if (cnt > 0) {
           tmem_ld32(tO + c4 * 32, o);
@@ -540,26 +547,26 @@ struct Maps {
   CUtensorMap q, k, v, qt, kt, vt;
 };
 
-template <bool kDebug, int kPolyPairs, bool kF16 = false>
+template <bool kDebug, int kPolyPairs, bool kF16 = false, int kD = 128>
 int launch(dim3 grid, cudaStream_t s, const Maps& m, const AttnArgs& a) {
   static bool configured = false;  // one flag per instantiation
   if (!configured) {
-    RSA_CUDA_CHECK(cudaFuncSetAttribute(attn_tc5_kernel<kDebug, kPolyPairs, kF16>,
+    RSA_CUDA_CHECK(cudaFuncSetAttribute(attn_tc5_kernel<kDebug, kPolyPairs, kF16, kD>,
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
-  attn_tc5_kernel<kDebug, kPolyPairs, kF16><<<grid, kThreads, kSmemBytes, s>>>(m.q, m.k, m.v, m.qt, m.kt, m.vt, a);
+  attn_tc5_kernel<kDebug, kPolyPairs, kF16, kD><<<grid, kThreads, kSmemBytes, s>>>(m.q, m.k, m.v, m.qt, m.kt, m.vt, a);
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;
 }
 
-int poly_pairs() {
-  static int v = -1;
-  if (v < 0) {
+int poly_pairs(int dflt = kDefaultPolyPairs) {
+  static int v = -2;
+  if (v == -2) {
     const char* e = getenv("RSA_TC5_POLY");
-    v = (e && e[0] >= '0' && e[0] <= '4' && !e[1]) ? e[0] - '0' : kDefaultPolyPairs;
+    v = (e && e[0] >= '0' && e[0] <= '4' && !e[1]) ? e[0] - '0' : -1;
   }
-  return v;
+  return v >= 0 ? v : dflt;
 }
 
 }  // namespace
@@ -581,6 +588,14 @@ int launch_attention_tc5(const AttnArgs& a, cudaStream_t s) {
     if ((rc = make_map(&m.vt, a.v + (int64_t)vis_kv * a.vs[2], a.batch, a.heads, a.seq_kv - vis_kv, a.vs, a.f16 != 0, a.head_dim)) != RSA_OK) return rc;
   }
   const dim3 grid((a.nqt + 1) / 2, a.batch * a.heads);
+  if (a.head_dim == 64 && !a.dbg && !(a.dbg_flags & 4)) {  // the 64-column instantiations (the debug kernel stays 128 wide)
+    if (a.f16) return launch<false, kDefaultPolyPairs64, true, 64>(grid, s, m, a);
+    switch (poly_pairs(kDefaultPolyPairs64)) {
+      case 1: return launch<false, 1, false, 64>(grid, s, m, a);
+      case 2: return launch<false, 2, false, 64>(grid, s, m, a);
+      default: return launch<false, 0, false, 64>(grid, s, m, a);
+    }
+  }
   if (a.f16) return a.dbg ? launch<true, kDefaultPolyPairs, true>(grid, s, m, a) : launch<false, kDefaultPolyPairs, true>(grid, s, m, a);
   if (a.dbg) return poly_pairs() == 1 ? launch<true, 1>(grid, s, m, a) : poly_pairs() == 2 ? launch<true, 2>(grid, s, m, a) : launch<true, kDefaultPolyPairs>(grid, s, m, a);
   switch (poly_pairs()) {

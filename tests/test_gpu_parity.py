@@ -799,6 +799,21 @@ def test_head_dim_64(dev):
     dense = ops.masked_attention(tq, tk, tv, mask, s)
     sd = torch.nn.functional.scaled_dot_product_attention(tq.float(), tk.float(), tv.float())
     assert dense.shape == tq.shape and (dense.float() - sd).abs().max().item() <= ATOL_OUT
+    # the 64-column instantiation of kernel 4 (4 k-steps of Q K^T, N = 64 P V) against the 128-column one reading the
+    # same tensors with the second granule zero-filled by TMA: the extra MMAs add exact zeros
+    ops.set_attention_flags(4)
+    try:
+        wide = ops.rectified_attention(tq, tk, tv, geo, 2, 0.3, torch.from_numpy(nbr))
+        dense_wide = ops.masked_attention(tq, tk, tv, mask, s)
+    finally:
+        ops.set_attention_flags(0)
+    assert (wide.float() - out.float()).abs().max().item() <= 1e-3
+    assert (dense_wide.float() - dense.float()).abs().max().item() <= 1e-3
+    # fp16 tensors through the 64-column instantiation
+    hq16, hk16, hv16 = (x.to(torch.float16) for x in (tq, tk, tv))
+    dense16 = ops.masked_attention(hq16, hk16, hv16, mask, s)
+    sd16 = torch.nn.functional.scaled_dot_product_attention(hq16.float(), hk16.float(), hv16.float())
+    assert (dense16.float() - sd16).abs().max().item() <= ATOL_OUT
     # host-buffer call
     hq, hk, hv = (x.cpu().pin_memory() for x in (tq, tk, tv))
     hout = ops.rectified_attention_host(hq, hk, hv, geo, 2, 0.3, torch.from_numpy(nbr))

@@ -231,6 +231,9 @@ def main():
     ap.add_argument("--workload", default="c3b", choices=list(WORKLOADS))
     ap.add_argument("--regime", default="walk", choices=["walk", "iid", "cluster"])
     ap.add_argument("--attn-impl", type=int, default=0, help="0 = tcgen05 kernel (product); 1 = mma.sync cross-check")
+    ap.add_argument("--attn-flags", type=int, default=0,
+                    help="kernel 4 A/B switches (rsa_debug_set_attention_flags): 4 = head_dim 64 through the 128-column "
+                         "form")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-permute", action="store_true")
@@ -288,6 +291,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     assert native.lib().rsa_device_ok() == 1
     ops.set_attention_impl(args.attn_impl)
+    ops.set_attention_flags(args.attn_flags)
 
     heads = wp["heads"]
     if heads % world:
@@ -442,6 +446,7 @@ def main():
             "config": config, "ms_per_attn_call": ms_step, "kept_pair_density": density, "stages_ms": stages,
             "mask_reuse": reuse,
             "attention_impl": "tcgen05" if args.attn_impl == 0 else "mma.sync cross-check",
+            "attention_flags": args.attn_flags,
             "gpu_launches": 6 * args.steps,
             "roofline": {"bound": "tensor", "kernel": "rect_attn (kernel 4)", "achieved": achieved,
                          "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],

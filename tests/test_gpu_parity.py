@@ -807,8 +807,11 @@ def test_head_dim_64(dev):
         dense_wide = ops.masked_attention(tq, tk, tv, mask, s)
     finally:
         ops.set_attention_flags(0)
-    assert (wide.float() - out.float()).abs().max().item() <= 1e-3
-    assert (dense_wide.float() - dense.float()).abs().max().item() <= 1e-3
+    # (bit-identical when both evaluate the exponentials the same way; the 64-column form runs a quarter of them as an
+    # FMA-pipe polynomial of relative error 7.5e-5 by default, far below P's bf16 rounding: at most one output ulp)
+    for x, y in ((wide, out), (dense_wide, dense)):
+        d = (x.float() - y.float()).abs()
+        assert d.max().item() <= 2.0 ** -6 and d.mean().item() <= 2e-4
     # fp16 tensors through the 64-column instantiation
     hq16, hk16, hv16 = (x.to(torch.float16) for x in (tq, tk, tv))
     dense16 = ops.masked_attention(hq16, hk16, hv16, mask, s)

@@ -40,7 +40,6 @@ constexpr int kOffRing = 4 * kGranule;
 constexpr int kOffBar = kOffRing + kStages * 2 * kGranule;
 constexpr int kSmemBytes = kOffBar + 256;
 constexpr uint32_t kTmemCols = 512;       // S/P of slot s at [128 s, +128), O of slot s at [256 + 128 s, +128)
-constexpr float kRescaleThreshold = 8.f;  // log2 units: O and l are rescaled only when the max grows by > 2^8
 // Of every 4 float2 pairs of exponentials, this many are evaluated on the FMA pipe (Cody-Waite range reduction +
 // degree-3 polynomial, max relative error 7.5e-5, far below the bf16 rounding of P) instead of MUFU.EX2.  On B200
 // the FMA pipe turned out to be the scarcer resource for this loop, so the default is 0.
@@ -374,7 +373,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
         if (i == 0) {
           m_ref = mx_s;
         } else {
-          const bool need = mx_s > m_ref + kRescaleThreshold;
+          const bool need = mx_s > m_ref + a.rescale_thr;
           if (__any_sync(0xffffffffu, need)) {  // tcgen05.ld/st are warp-collective: rescale the warp's 32 rows
             const float alpha = need ? ex2(m_ref - mx_s) : 1.f;
             const float2 alpha2 = make_float2(alpha, alpha);

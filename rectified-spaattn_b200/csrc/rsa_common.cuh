@@ -56,6 +56,7 @@ inline RowMap row_map(const rsa_attn_desc* d) {
   return m;
 }
 
+float attention_rescale_threshold(bool f16);
 int validate_desc(const rsa_attn_desc* d);
 WsLayout make_layout(const rsa_attn_desc* d);
 int check_ws(const rsa_attn_desc* d, const void* ws, size_t bytes, WsLayout* out);
@@ -94,6 +95,7 @@ struct AttnArgs {
   int peer_rows, peer_head0;      // tokens per rank; first head of this rank inside a token of the result buffers
   int64_t peer_os[2];             // (batch, token) element strides of the result buffers
   float scale_log2;         // head_dim^-0.5 * log2(e)
+  float rescale_thr;        // kernel 4: O and l are rescaled only when a row maximum grows by more than 2^rescale_thr
   int head_dim;             // 128 or 64: columns that exist in q/k/v/o (the rest of the 128-column tiles reads as zeros)
   int f16;                  // q/k/v/o hold fp16 instead of bf16 (the pointer types above are nominal: 2-byte elements)
   int dbg_flags;            // bring-up ablations (rsa_debug_set_attention_flags), only read by the debug kernel

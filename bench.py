@@ -233,7 +233,7 @@ def main():
     ap.add_argument("--attn-impl", type=int, default=0, help="0 = tcgen05 kernel (product); 1 = mma.sync cross-check")
     ap.add_argument("--attn-flags", type=int, default=0,
                     help="kernel 4 A/B switches (rsa_debug_set_attention_flags): 4 = head_dim 64 through the 128-column "
-                         "form")
+                         "form, 16 = kernel 4 grid in the former order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-permute", action="store_true")

@@ -105,11 +105,45 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // block); tmQt/tmKt/tmVt cover the text rows, which start at memory row vis_len (RowMap, rsa_common.cuh).
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // pairs of adjacent query tiles; the last pairs hold the dense (text) tiles, the longest: schedule them first
-  const int pair = (int)gridDim.x - 1 - (int)blockIdx.x;
-  const int bh = blockIdx.y;
+  // Pairs of adjacent query tiles.  The pairs that hold the dense (text) tiles are several times longer than the
+  // others (C3b: 931 rounds against ~200, Flux: 516 against ~65), so the 1-D grid starts with the text pairs of ALL
+  // heads and then walks the visual pairs head by head (K/V of one head stay L2-resident): with the text pair of each
+  // head at the start of that head's batch, the last heads' text pairs ran on after everything else had finished.
+  const int n_pairs = (a.nqt + 1) / 2;
+  const int nqv = min(a.nq_vis, a.nqt);      // visual tiles (rsa_masked_attention passes "all of them" as 2^20)
+  const int vis_pairs = nqv / 2;             // pairs made of visual tiles only
+  const int txt_pairs = n_pairs - vis_pairs;  // pairs with a text tile (or the odd last tile)
+  int pair, bh;
+  {
+    int id = (int)blockIdx.x;
+    const int n_txt = txt_pairs * a.batch * a.heads;
+    if (a.dbg_flags & 16) {  // A/B: the former order (head by head, each head's text pairs first, no re-pairing)
+      bh = id / n_pairs;
+      pair = n_pairs - 1 - id % n_pairs;
+    } else if (id < n_txt) {
+      bh = id / txt_pairs;
+      pair = n_pairs - 1 - id % txt_pairs;
+    } else {
+      id -= n_txt;
+      bh = id / vis_pairs;
+      pair = vis_pairs - 1 - id % vis_pairs;
+    }
+  }
   const int b = bh / a.heads, h = bh % a.heads;
-  const int tile0 = 2 * pair, tile1 = 2 * pair + 1;
+  // Tiles of the pair: (2 pair, 2 pair + 1).  With an odd number of visual tiles and an even number of text tiles
+  // (HunyuanVideo 129 frames: 929 + 2) that rule would pair the last visual tile with a text tile and leave the other
+  // text tile alone -- two CTAs running a 931-block list mostly single-slot.  The tail is re-paired instead: the odd
+  // visual tile alone, the text tiles with each other.  Re-paired tiles walk their original ascending lists (kept_idx;
+  // the pair schedule was computed for the (2p, 2p+1) rule): text lists are all "every block with valid keys", so the
+  // whole list is common to both slots.
+  const int n_txt_tiles = a.nqt - nqv;
+  const bool repair = (nqv & 1) && n_txt_tiles >= 2 && !(n_txt_tiles & 1) && pair >= vis_pairs && !(a.dbg_flags & 16);
+  int tile0 = 2 * pair, tile1 = 2 * pair + 1;
+  if (repair) {
+    const int q = pair - vis_pairs;  // 0: the odd visual tile; q >= 1: text tiles (nq_vis + 2q - 2, nq_vis + 2q - 1)
+    tile0 = q == 0 ? nqv - 1 : nqv + 2 * q - 2;
+    tile1 = q == 0 ? a.nqt : tile0 + 1;
+  }
   const int64_t lrow0 = (int64_t)bh * a.nqt + tile0;
   // counts and prefix length are clamped so that a workspace that never saw a build (mask re-use misused) yields
   // garbage values, not an unbounded walk; out-of-range block numbers read as zero tiles through TMA
@@ -117,9 +151,10 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int cnt1 = tile1 < a.nqt ? min(max(a.kept_cnt[lrow0 + 1], 0), a.nb) : 0;
   // the pair schedule (rsa_api.cu: pair_schedule_kernel): both lists start with the nsh blocks the two tiles have in
   // common, in the same order, so over rounds [0, nsh) one K tile and one V tile serve both slots
-  const uint16_t* __restrict__ list0 = a.sched_idx + lrow0 * a.nb;
+  const uint16_t* __restrict__ list0 = (repair ? a.kept_idx : a.sched_idx) + lrow0 * a.nb;
   const uint16_t* __restrict__ list1 = list0 + a.nb;
-  const int nsh = min(max(a.pair_shared[(int64_t)bh * gridDim.x + pair], 0), min(cnt0, cnt1));
+  const int nsh = repair ? min(cnt0, cnt1)
+                         : min(max(a.pair_shared[(int64_t)bh * n_pairs + pair], 0), min(cnt0, cnt1));
   const int rounds = max(cnt0, cnt1);
 
   constexpr int kG = kD / 64;                       // granules per Q/K/V tile
@@ -586,7 +621,7 @@ int launch_attention_tc5(const AttnArgs& a, cudaStream_t s) {
     if ((rc = make_map(&m.kt, a.k + (int64_t)vis_kv * a.ks[2], a.batch, a.heads, a.seq_kv - vis_kv, a.ks, a.f16 != 0, a.head_dim)) != RSA_OK) return rc;
     if ((rc = make_map(&m.vt, a.v + (int64_t)vis_kv * a.vs[2], a.batch, a.heads, a.seq_kv - vis_kv, a.vs, a.f16 != 0, a.head_dim)) != RSA_OK) return rc;
   }
-  const dim3 grid((a.nqt + 1) / 2, a.batch * a.heads);
+  const dim3 grid((unsigned)((a.nqt + 1) / 2) * (unsigned)(a.batch * a.heads));
   if (a.head_dim == 64 && !a.dbg && !(a.dbg_flags & 4)) {  // the 64-column instantiations (the debug kernel stays 128 wide)
     if (a.f16) return launch<false, kDefaultPolyPairs64, true, 64>(grid, s, m, a);
     switch (poly_pairs(kDefaultPolyPairs64)) {

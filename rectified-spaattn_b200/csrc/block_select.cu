@@ -169,25 +169,46 @@ __device__ __forceinline__ void sort_steps(uint32_t (&x)[EPT], uint32_t* s_val, 
   else if constexpr (K < kThreads * EPT) sort_steps<EPT, 2 * K, K>(x, s_val, tid);
 }
 
-// s_p[0..n_ent) -> s_val[0..kThreads*EPT) sorted descending (entries >= n_ent count as +0)
+// s_p[0..n_net) -> s_val sorted descending (entries >= n_net count as +0).  The joint family's text aggregate
+// (entry n_net, the highest index, n_ent = n_net + 1) is not put through the network: in (value desc, index asc) order
+// it comes after every visual entry >= it, so it is inserted at position #{visual entries >= it} while the sorted values
+// are written out.  That keeps the network at the next power of two above the number of VISUAL blocks -- Flux at
+// 4096^2 has 512 of them, and 513 entries would double the network to 1024.
 template <int EPT>
-__device__ void sort_desc(const float* s_p, int n_ent, uint32_t* s_val, int tid) {
+__device__ void sort_desc(const float* s_p, int n_net, int n_ent, uint32_t* s_val, int* s_pos, int tid) {
   uint32_t x[EPT];
 #pragma unroll
   for (int r = 0; r < EPT; ++r) {
     const int e = tid * EPT + r;
-    x[r] = e < n_ent ? __float_as_uint(s_p[e]) : 0u;
+    x[r] = e < n_net ? __float_as_uint(s_p[e]) : 0u;
   }
+  if (tid == 0) *s_pos = 0;
   sort_steps<EPT, 2, 1>(x, s_val, tid);
   __syncthreads();
+  if (n_ent > n_net) {
+    const uint32_t extra = __float_as_uint(s_p[n_net]);
+    int ge = 0;
 #pragma unroll
-  for (int r = 0; r < EPT; ++r) s_val[tid * EPT + r] = x[r];
+    for (int r = 0; r < EPT; ++r) ge += (tid * EPT + r < n_net && x[r] >= extra) ? 1 : 0;
+    if (ge) atomicAdd(s_pos, ge);
+    __syncthreads();
+    const int pos = *s_pos;
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) {
+      const int e = tid * EPT + r;
+      if (e < n_net) s_val[e + (e >= pos ? 1 : 0)] = x[r];
+    }
+    if (tid == 0) s_val[pos] = extra;
+  } else {
+#pragma unroll
+    for (int r = 0; r < EPT; ++r) s_val[tid * EPT + r] = x[r];
+  }
   __syncthreads();
 }
 
 __global__ void __launch_bounds__(kThreads) block_select_kernel(const SelectArgs a) {
   __shared__ float s_p[kMaxEnt + 1];
-  __shared__ uint32_t s_val[kMaxEnt];  // sorted probability bit patterns
+  __shared__ uint32_t s_val[kMaxEnt + 1];  // sorted probability bit patterns
   __shared__ uint32_t s_thr;           // bit pattern of the n-th largest probability
   __shared__ int s_ties_needed, s_ties_total;
   __shared__ uint32_t s_mask[kMaxWords];
@@ -276,12 +297,13 @@ __global__ void __launch_bounds__(kThreads) block_select_kernel(const SelectArgs
   }
 
   // ---- sort the probabilities (descending); ties are resolved below by index, ascending
+  const int n_net = a.joint ? nq : n_ent;  // entries that go through the sorting network
   int n_sort = kThreads;
-  while (n_sort < n_ent) n_sort <<= 1;
-  if (n_sort == kThreads) sort_desc<1>(s_p, n_ent, s_val, tid);
-  else if (n_sort == 2 * kThreads) sort_desc<2>(s_p, n_ent, s_val, tid);
-  else if (n_sort == 4 * kThreads) sort_desc<4>(s_p, n_ent, s_val, tid);
-  else sort_desc<8>(s_p, n_ent, s_val, tid);
+  while (n_sort < n_net) n_sort <<= 1;
+  if (n_sort == kThreads) sort_desc<1>(s_p, n_net, n_ent, s_val, &s_ties_total, tid);
+  else if (n_sort == 2 * kThreads) sort_desc<2>(s_p, n_net, n_ent, s_val, &s_ties_total, tid);
+  else if (n_sort == 4 * kThreads) sort_desc<4>(s_p, n_net, n_ent, s_val, &s_ties_total, tid);
+  else sort_desc<8>(s_p, n_net, n_ent, s_val, &s_ties_total, tid);
 
   // ---- sequential fp32 cumulative sum over the sorted probabilities (wan21 :221-229)
   if (tid == 0) {

@@ -66,6 +66,7 @@ struct PoolArgs {
   int head_dim;               // 128 or 64: columns >= head_dim do not exist in x and pool as zeros
   // text keys copied as fp32 rows behind the pooled keys
   int text_keys, text_from;   // a, memory row of the first text token (= vis_len)
+  int pool_ctas;              // kernel 2's grid: x < pool_ctas pools block x, x >= pool_ctas copies 16 text keys
 };
 
 template <bool kF16 = false>
@@ -267,10 +268,12 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const 
   const int b = bh / a.heads, h = bh % a.heads;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
-  if (!kPrep && which == 3) {
-    // text keys -> fp32 rows [NQ, NQ + a) of k_cat; one 16-lane group per row
+  if (!kPrep && jblk >= a.pool_ctas) {
+    // the CTAs behind the pooling ones (tensor 1 only): text keys -> fp32 rows [NQ, NQ + a) of k_cat; one 16-lane
+    // group per row
+    if (which != 1) return;
     const int rows_per_cta = kThreads / 16;
-    const int t = blk * rows_per_cta + (tid >> 4);
+    const int t = (jblk - a.pool_ctas) * rows_per_cta + (tid >> 4);
     if (t < a.text_keys) {
       const int tok = a.text_from + t;
       const __nv_bfloat16* src = a.x[1] + b * a.stride[1][0] + h * a.stride[1][1] + (int64_t)tok * a.stride[1][2];
@@ -422,6 +425,7 @@ static PoolArgs pool_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a.head_dim = d->head_dim;
   a.text_keys = L.a;
   a.text_from = rm.vis_len;
+  a.pool_ctas = L.nb;
   return a;
 }
 
@@ -429,8 +433,7 @@ int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, cons
                       const WsLayout& L, cudaStream_t s) {
   const PoolArgs a = pool_args(d, q, k, v, ws, L);
   const int text_ctas = (L.a + 15) / 16;
-  const int gx = L.nb > text_ctas ? L.nb : text_ctas;
-  dim3 grid(gx, L.bh, L.a > 0 ? 4 : 3);
+  dim3 grid(L.nb + text_ctas, L.bh, 3);  // (a fourth z plane for the text keys launched nb - text_ctas empty CTAs per head)
   if (d->dtype == RSA_DTYPE_F16) pool_stats_kernel<false, 3, 0, false, false, true><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
   else pool_stats_kernel<false, 3><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
   RSA_CUDA_CHECK(cudaGetLastError());

@@ -435,7 +435,7 @@ int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, cons
   const int text_ctas = (L.a + 15) / 16;
   dim3 grid(L.nb + text_ctas, L.bh, 3);  // (a fourth z plane for the text keys launched nb - text_ctas empty CTAs per head)
   if (d->dtype == RSA_DTYPE_F16) pool_stats_kernel<false, 3, 0, false, false, true><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
-  else pool_stats_kernel<false, 3><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
+  else pool_stats_kernel<false, 3><<<grid, kThreads, 0, s>>>(a, PrepArgs{});  // 4 CTAs per SM (64 registers, 68 B of spills): 0.49 against 0.465 ms at C3b
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;
 }

@@ -811,7 +811,7 @@ def test_head_dim_64(dev):
     # FMA-pipe polynomial of relative error 7.5e-5 by default, far below P's bf16 rounding: at most one output ulp)
     for x, y in ((wide, out), (dense_wide, dense)):
         d = (x.float() - y.float()).abs()
-        assert d.max().item() <= 2.0 ** -6 and d.mean().item() <= 2e-4
+        assert bool((d <= 2.0 ** -7 * y.float().abs() + 1e-3).all()) and d.mean().item() <= 2e-4
     # fp16 tensors through the 64-column instantiation
     hq16, hk16, hv16 = (x.to(torch.float16) for x in (tq, tk, tv))
     dense16 = ops.masked_attention(hq16, hk16, hv16, mask, s)

@@ -12,7 +12,14 @@ namespace rsa {
 static thread_local char g_err[512] = "";
 int g_attention_impl = 0;
 float* g_attention_dbg = nullptr;
-int g_attention_dbg_flags = 0;
+// RSA_ATTN_FLAGS: switches that stay set for the whole process (A/B runs of the test suite), OR-ed into whatever
+// rsa_debug_set_attention_flags sets
+static int env_attention_flags() {
+  const char* e = getenv("RSA_ATTN_FLAGS");
+  return e ? atoi(e) : 0;
+}
+static const int g_env_attention_flags = env_attention_flags();
+int g_attention_dbg_flags = g_env_attention_flags;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -307,7 +314,7 @@ extern "C" int rsa_set_attention_impl(int impl) {
 }
 
 extern "C" void rsa_debug_set_attention_dump(float* device_buffer) { g_attention_dbg = device_buffer; }
-extern "C" void rsa_debug_set_attention_flags(int flags) { g_attention_dbg_flags = flags; }
+extern "C" void rsa_debug_set_attention_flags(int flags) { g_attention_dbg_flags = flags | g_env_attention_flags; }
 
 extern "C" size_t rsa_attn_workspace_bytes(const rsa_attn_desc* d) {
   if (validate_desc(d) != RSA_OK) return 0;

@@ -447,7 +447,7 @@ def main():
             "mask_reuse": reuse,
             "attention_impl": "tcgen05" if args.attn_impl == 0 else "mma.sync cross-check",
             "attention_flags": args.attn_flags,
-            "gpu_launches": 6 * args.steps,
+            "gpu_launches": 7 * args.steps,
             "roofline": {"bound": "tensor", "kernel": "rect_attn (kernel 4)", "achieved": achieved,
                          "peak": peaks["bf16"], "unit": "TFLOP/s", "frac": achieved / peaks["bf16"],
                          "peak_source": f"{peaks['source']} cuBLAS bf16 burst (kernel timed alone, back to back); "

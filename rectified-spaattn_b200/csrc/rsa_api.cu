@@ -122,6 +122,12 @@ WsLayout make_layout(const rsa_attn_desc* d) {
   L.off_C = take((size_t)L.bh * L.nqt * 128 * f);
   L.off_sched = take((size_t)L.bh * L.nqt * L.nb * 2);
   L.off_pshared = take((size_t)L.bh * ((L.nqt + 1) / 2) * 4);
+  L.ldq = (int)align_up(L.nq > 0 ? L.nq : 1, 4);
+  L.ldk = (int)align_up(L.nkc > 0 ? L.nkc : 1, 4);
+  L.off_q_pool_t = take((size_t)L.bh * 128 * L.ldq * f);
+  L.off_q_mad_t = take((size_t)L.bh * 128 * L.ldq * f);
+  L.off_k_cat_t = take((size_t)L.bh * 128 * L.ldk * f);
+  L.off_k_mad_t = take((size_t)L.bh * 128 * L.ldq * f);
   L.total = o;
   return L;
 }

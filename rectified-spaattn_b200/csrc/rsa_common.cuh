@@ -29,6 +29,9 @@ inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 // Workspace carve-up shared by every stage (offsets in bytes from a 256-B aligned base).
 struct WsLayout {
   int bh, nq, nb, nqt, a, nkc, score_ld, n_entries, ent_ld, mask_words, nogapr_ld;
+  // transposed copies [bh][128][ldq | ldk] of q_pool, q_mad, k_cat, k_mad: what kernel 3a stages from (coalesced)
+  size_t off_q_pool_t, off_q_mad_t, off_k_cat_t, off_k_mad_t;
+  int ldq, ldk;
   size_t off_q_pool, off_q_mad, off_k_cat, off_k_mad, off_v_pool, off_scores, off_nogapr, off_probs, off_w,
       off_mask, off_kidx, off_kcnt, off_nneed, off_R, off_C, off_sched, off_pshared, total;
 };

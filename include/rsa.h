@@ -320,7 +320,9 @@ void rsa_debug_set_attention_dump(float* device_buffer);
 /* Bring-up ablations, honoured only while a dump buffer is set: bit 0 = skip the softmax arithmetic (results are
  * garbage; measures the TMA + tensor pipeline alone), bit 1 = no K/V loads after the first ring fill.  Bit 2 is
  * honoured without a dump buffer: head_dim 64 runs through the 128-column instantiation (second granule = TMA zero
- * fill) instead of the 64-column one -- the cross-check and the A/B timing of the two forms. */
+ * fill) instead of the 64-column one -- the cross-check and the A/B timing of the two forms; bit 4 likewise: kernel 4's
+ * grid in its former order (head by head, no re-pairing of the tail) for A/B timing.  The environment variable
+ * RSA_ATTN_FLAGS holds bits for the whole process (OR-ed into whatever this call sets). */
 void rsa_debug_set_attention_flags(int flags);
 
 #ifdef __cplusplus

@@ -106,9 +106,10 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Pairs of adjacent query tiles.  The pairs that hold the dense (text) tiles are several times longer than the
-  // others (C3b: 931 rounds against ~200, Flux: 516 against ~65), so the 1-D grid starts with the text pairs of ALL
-  // heads and then walks the visual pairs head by head (K/V of one head stay L2-resident): with the text pair of each
-  // head at the start of that head's batch, the last heads' text pairs ran on after everything else had finished.
+  // others (C3b: 931 rounds against ~200, Flux: 516 against ~65).  The 1-D grid walks the heads in order, each head's
+  // text pairs first and then its visual pairs (K/V of one head stay L2-resident and are read from HBM once) -- except
+  // that the text pairs of the LAST front_text_heads heads are moved to the very start of the grid: where they stood,
+  // they ran on after everything else had finished (a text pair lasts as long as several heads' worth of visual pairs).
   const int n_pairs = (a.nqt + 1) / 2;
   const int nqv = min(a.nq_vis, a.nqt);      // visual tiles (rsa_masked_attention passes "all of them" as 2^20)
   const int vis_pairs = nqv / 2;             // pairs made of visual tiles only
@@ -116,16 +117,20 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   int pair, bh;
   {
     int id = (int)blockIdx.x;
-    const int n_txt = txt_pairs * a.batch * a.heads;
-    if (a.dbg_flags & 16) {  // A/B: the former order (head by head, each head's text pairs first, no re-pairing)
+    const int n_bh = a.batch * a.heads;
+    const int front = (a.dbg_flags & 16) ? 0 : min(max(a.front_text_heads, 0), n_bh);  // flag 16 (A/B): the former order
+    const int n_front = front * txt_pairs;
+    const int n_inline = (n_bh - front) * n_pairs;
+    if (id < n_front) {  // text pairs of the last `front` heads
+      bh = n_bh - front + id / txt_pairs;
+      pair = n_pairs - 1 - id % txt_pairs;
+    } else if (id - n_front < n_inline) {  // the other heads: text pairs, then visual pairs
+      id -= n_front;
       bh = id / n_pairs;
       pair = n_pairs - 1 - id % n_pairs;
-    } else if (id < n_txt) {
-      bh = id / txt_pairs;
-      pair = n_pairs - 1 - id % txt_pairs;
-    } else {
-      id -= n_txt;
-      bh = id / vis_pairs;
+    } else {  // visual pairs of the last `front` heads
+      id -= n_front + n_inline;
+      bh = n_bh - front + id / vis_pairs;
       pair = vis_pairs - 1 - id % vis_pairs;
     }
   }

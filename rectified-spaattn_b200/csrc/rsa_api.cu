@@ -179,6 +179,22 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.4426950408889634);
   a->head_dim = d->head_dim;
   a->rescale_thr = attention_rescale_threshold(d->dtype == RSA_DTYPE_F16);
+  // A text pair walks all n_blocks blocks; one head's visual pairs take about vis_pairs * kept / SMs rounds per SM, with
+  // kept >= top_k.  The text pairs of the heads whose batch would start less than one text pair before the end go first.
+  a->front_text_heads = 0;
+  if (L.nqt > L.nq && L.nq >= 2) {
+    static int sms = 0;
+    if (!sms) {
+      int dev = 0;
+      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+    }
+    const double per_head = (double)(L.nq / 2) * (double)(d->top_k > 0 ? d->top_k : 1) / (double)sms;
+    const double f = (double)L.nb / (per_head > 1e-9 ? per_head : 1e-9);
+    a->front_text_heads = f >= (double)L.bh ? L.bh : (int)f + 2;
+    if (a->front_text_heads > L.bh) a->front_text_heads = L.bh;
+  } else if (L.nq < 2) {
+    a->front_text_heads = L.bh;  // no visual pairs at all: every pair is in the front set
+  }
   a->f16 = d->dtype == RSA_DTYPE_F16;
   a->dbg = g_attention_dbg;
   a->dbg_flags = g_attention_dbg_flags;
@@ -619,6 +635,7 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   a.scale_log2 = (float)((1.0 / sqrt((double)head_dim)) * 1.4426950408889634);
   a.head_dim = head_dim;
   a.rescale_thr = attention_rescale_threshold(dtype == RSA_DTYPE_F16);
+  a.front_text_heads = 0;
   a.f16 = dtype == RSA_DTYPE_F16;
   a.dbg = g_attention_dbg;
   a.dbg_flags = g_attention_dbg_flags;

@@ -98,6 +98,7 @@ struct AttnArgs {
   int peer_rows, peer_head0;      // tokens per rank; first head of this rank inside a token of the result buffers
   int64_t peer_os[2];             // (batch, token) element strides of the result buffers
   float scale_log2;         // head_dim^-0.5 * log2(e)
+  int front_text_heads;     // kernel 4's grid: the text pairs of this many last heads are scheduled before everything else
   float rescale_thr;        // kernel 4: O and l are rescaled only when a row maximum grows by more than 2^rescale_thr
   int head_dim;             // 128 or 64: columns that exist in q/k/v/o (the rest of the 128-column tiles reads as zeros)
   int f16;                  // q/k/v/o hold fp16 instead of bf16 (the pointer types above are nominal: 2-byte elements)

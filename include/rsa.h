@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RSA_VERSION 101
+#define RSA_VERSION 102
 #define RSA_BLOCK 128
 #define RSA_HEAD_DIM 128
 #define RSA_MAX_ENTRIES 2048 /* max sortable entries per query block: NQ (+1 for the text aggregate) */

@@ -69,6 +69,9 @@ EXPORTS = [
 _lib = None
 
 
+ABI_VERSION = 102
+
+
 def lib():
     global _lib
     if _lib is not None:
@@ -81,6 +84,9 @@ def lib():
     p, i32, i64, sz = C.c_void_p, C.c_int, C.c_int64, C.c_size_t
     L.rsa_last_error_string.restype = C.c_char_p
     L.rsa_version.restype = i32
+    if L.rsa_version() != ABI_VERSION:   # the ctypes structures below mirror include/rsa.h of exactly this version
+        raise RsaError(f"{LIB_PATH} has ABI version {L.rsa_version()}, this package expects {ABI_VERSION}: rebuild it "
+                       "with `python rectified-spaattn_b200/build_native.py`")
     L.rsa_device_ok.restype = i32
     L.rsa_gilbert_map.argtypes = [i32, i32, i32, C.c_char_p, p, p]
     L.rsa_gilbert_block_neighbors.argtypes = [i32, i32, i32, i32, C.c_char_p, p]

@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in rsa.h but not exported"
     assert declared == set(N.EXPORTS)
-    assert lib.rsa_version() == 101
+    assert lib.rsa_version() == 102
 
 
 def test_struct_layout_matches_header():

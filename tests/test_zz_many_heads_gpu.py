@@ -76,3 +76,45 @@ def test_grid_order_with_many_heads(dev, grid, text):
         assert bool((d <= ATOL_OUT + 2.0 ** -7 * ref_all.float().abs()).all()), f"tcgen05 vs mma.sync max-abs {float(d.max()):.4f}"
         cos = float(torch.nn.functional.cosine_similarity(out.float().flatten(), ref_all.float().flatten(), dim=0))
         assert cos >= 0.9999
+
+
+def test_selection_with_power_of_two_visual_blocks(dev):
+    """Kernel 3b leaves the joint family's text aggregate out of the sorting network and inserts it afterwards exactly
+    when that halves the network: the visual blocks alone fill a power of two >= 256 (Flux at 4096^2: 512).  No case of
+    oracle/cases.py has that shape, so here is one: Flux geometry with 256 visual blocks (1 x 128 x 256 latent + 512 text
+    tokens), one head, stage level only (the CPU oracle's attention would take minutes).  Probabilities against the
+    oracle; selection bit-exact from the kernel's own probabilities (n_needed, mask), as in test_select_and_rectify."""
+    import numpy as np
+
+    from oracle import rsa_oracle as O
+    from rsa_b200 import geometry as G
+    from rsa_b200 import ops
+    t, h, w, text, top_k = 1, 128, 256, 512, 25
+    nv = t * h * w
+    s = nv + text
+    q, k, v = O.synth_qkv(1, s, 128, "walk", 11)
+    nbr = ops.gilbert_block_neighbors(t, h, w).numpy()
+    geo = O.geometry_flux(s, text, top_k, 0.3)
+    nq = geo.nq_blocks
+    assert nq == 256 and geo.n_blocks == 260
+    # oracle stages (rsa_oracle.head_forward without the attention)
+    q0, k0, v0 = O.padded_inputs(q[0, 0], k[0, 0], v[0, 0], geo)
+    qp, dq = O.pool_stats(q0, geo.seq + geo.gap, nq)
+    kp, dk = O.pool_stats(k0, geo.kv_zero_from, nq)
+    a, _ = O.block_scores(qp, dq, kp, dk, k0[nq * 128: nq * 128 + geo.text_keys])
+    p_ref = O.probs_from_scores(a, nq, 128, True)
+    # kernels 2, 3a, 3b
+    tq, tk, tv = (torch.from_numpy(x).to(dev).to(torch.bfloat16) for x in (q, k, v))
+    plan = ops.Plan(tq, tk, tv, G.flux(s, text), top_k, 0.3, torch.from_numpy(nbr), debug_dump_probs=True,
+                    private_workspace=True)
+    plan.pool_stats()
+    plan.block_scores()
+    plan.block_select()
+    torch.cuda.synchronize()
+    vw = plan.view()
+    assert np.array_equal(vw["scores"][0].cpu().numpy(), a)
+    p_gpu = vw["probs"][0].cpu().numpy()
+    np.testing.assert_allclose(p_gpu, p_ref, rtol=3e-5, atol=1e-9)
+    m, n = O.select_blocks(p_gpu, geo, nbr)
+    assert np.array_equal(vw["n_needed"][0].cpu().numpy(), n)
+    assert np.array_equal(plan.dense_mask()[0, :nq].cpu().numpy(), m)

@@ -324,6 +324,12 @@ void rsa_debug_set_attention_dump(float* device_buffer);
  * grid in its former order (head by head, no re-pairing of the tail) for A/B timing.  The environment variable
  * RSA_ATTN_FLAGS holds bits for the whole process (OR-ed into whatever this call sets). */
 void rsa_debug_set_attention_flags(int flags);
+/* Host-side views of kernel 4's grid order (tests): the (batch*head, pair, tile0, tile1, repaired) CTA `id` of a launch
+ * over n_bh heads works on, given the number of last heads whose text pairs go first -- the same inline function the
+ * kernel calls -- and that number as the library computes it for a descriptor (-1: invalid descriptor). */
+void rsa_debug_attention_grid_slot(int id, int n_q_tiles, int nq_vis, int n_bh, int front_heads, int former_order,
+                                   int out[5]);
+int rsa_debug_front_text_heads(const rsa_attn_desc* d);
 
 #ifdef __cplusplus
 }

@@ -105,50 +105,13 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // block); tmQt/tmKt/tmVt cover the text rows, which start at memory row vis_len (RowMap, rsa_common.cuh).
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  // Pairs of adjacent query tiles.  The pairs that hold the dense (text) tiles are several times longer than the
-  // others (C3b: 931 rounds against ~200, Flux: 516 against ~65).  The 1-D grid walks the heads in order, each head's
-  // text pairs first and then its visual pairs (K/V of one head stay L2-resident and are read from HBM once) -- except
-  // that the text pairs of the LAST front_text_heads heads are moved to the very start of the grid: where they stood,
-  // they ran on after everything else had finished (a text pair lasts as long as several heads' worth of visual pairs).
+  // which pair of query tiles this CTA works on: attention_grid_slot (rsa_common.cuh) explains the order
+  const GridSlot gs = attention_grid_slot((int)blockIdx.x, a.nqt, a.nq_vis, a.batch * a.heads, a.front_text_heads,
+                                          (a.dbg_flags & 16) != 0);
   const int n_pairs = (a.nqt + 1) / 2;
-  const int nqv = min(a.nq_vis, a.nqt);      // visual tiles (rsa_masked_attention passes "all of them" as 2^20)
-  const int vis_pairs = nqv / 2;             // pairs made of visual tiles only
-  const int txt_pairs = n_pairs - vis_pairs;  // pairs with a text tile (or the odd last tile)
-  int pair, bh;
-  {
-    int id = (int)blockIdx.x;
-    const int n_bh = a.batch * a.heads;
-    const int front = (a.dbg_flags & 16) ? 0 : min(max(a.front_text_heads, 0), n_bh);  // flag 16 (A/B): the former order
-    const int n_front = front * txt_pairs;
-    const int n_inline = (n_bh - front) * n_pairs;
-    if (id < n_front) {  // text pairs of the last `front` heads
-      bh = n_bh - front + id / txt_pairs;
-      pair = n_pairs - 1 - id % txt_pairs;
-    } else if (id - n_front < n_inline) {  // the other heads: text pairs, then visual pairs
-      id -= n_front;
-      bh = id / n_pairs;
-      pair = n_pairs - 1 - id % n_pairs;
-    } else {  // visual pairs of the last `front` heads
-      id -= n_front + n_inline;
-      bh = n_bh - front + id / vis_pairs;
-      pair = vis_pairs - 1 - id % vis_pairs;
-    }
-  }
+  const int pair = gs.pair, bh = gs.bh, tile0 = gs.tile0, tile1 = gs.tile1;
+  const bool repair = gs.repaired;
   const int b = bh / a.heads, h = bh % a.heads;
-  // Tiles of the pair: (2 pair, 2 pair + 1).  With an odd number of visual tiles and an even number of text tiles
-  // (HunyuanVideo 129 frames: 929 + 2) that rule would pair the last visual tile with a text tile and leave the other
-  // text tile alone -- two CTAs running a 931-block list mostly single-slot.  The tail is re-paired instead: the odd
-  // visual tile alone, the text tiles with each other.  Re-paired tiles walk their original ascending lists (kept_idx;
-  // the pair schedule was computed for the (2p, 2p+1) rule): text lists are all "every block with valid keys", so the
-  // whole list is common to both slots.
-  const int n_txt_tiles = a.nqt - nqv;
-  const bool repair = (nqv & 1) && n_txt_tiles >= 2 && !(n_txt_tiles & 1) && pair >= vis_pairs && !(a.dbg_flags & 16);
-  int tile0 = 2 * pair, tile1 = 2 * pair + 1;
-  if (repair) {
-    const int q = pair - vis_pairs;  // 0: the odd visual tile; q >= 1: text tiles (nq_vis + 2q - 2, nq_vis + 2q - 1)
-    tile0 = q == 0 ? nqv - 1 : nqv + 2 * q - 2;
-    tile1 = q == 0 ? a.nqt : tile0 + 1;
-  }
   const int64_t lrow0 = (int64_t)bh * a.nqt + tile0;
   // counts and prefix length are clamped so that a workspace that never saw a build (mask re-use misused) yields
   // garbage values, not an unbounded walk; out-of-range block numbers read as zero tiles through TMA

@@ -142,6 +142,26 @@ int check_ws(const rsa_attn_desc* d, const void* ws, size_t bytes, WsLayout* out
   return RSA_OK;
 }
 
+// Kernel 4's grid (attention_grid_slot): how many of the last heads have their text pairs moved to the front.  A text
+// pair walks all n_blocks blocks; one head's visual pairs take about vis_pairs * kept / SMs rounds per SM, with
+// kept >= top_k.  The text pairs of the heads whose batch would start less than one text pair before the end go first.
+static int front_text_heads(const WsLayout& L, int top_k) {
+  if (L.nq < 2) return L.bh;    // no visual pairs at all: every pair is in the front set
+  if (L.nqt <= L.nq) return 0;  // no text tiles
+  static int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) {
+      (void)cudaGetLastError();
+      sms = 148;
+    }
+  }
+  const double per_head = (double)(L.nq / 2) * (double)(top_k > 0 ? top_k : 1) / (double)sms;
+  const double f = (double)L.nb / per_head;
+  return f >= (double)L.bh ? L.bh : ((int)f + 2 > L.bh ? L.bh : (int)f + 2);
+}
+
 static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, const void* v, void* out, char* ws,
                           const WsLayout& L, AttnArgs* a) {
   a->q = (const __nv_bfloat16*)q;
@@ -179,22 +199,7 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.4426950408889634);
   a->head_dim = d->head_dim;
   a->rescale_thr = attention_rescale_threshold(d->dtype == RSA_DTYPE_F16);
-  // A text pair walks all n_blocks blocks; one head's visual pairs take about vis_pairs * kept / SMs rounds per SM, with
-  // kept >= top_k.  The text pairs of the heads whose batch would start less than one text pair before the end go first.
-  a->front_text_heads = 0;
-  if (L.nqt > L.nq && L.nq >= 2) {
-    static int sms = 0;
-    if (!sms) {
-      int dev = 0;
-      if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
-    }
-    const double per_head = (double)(L.nq / 2) * (double)(d->top_k > 0 ? d->top_k : 1) / (double)sms;
-    const double f = (double)L.nb / (per_head > 1e-9 ? per_head : 1e-9);
-    a->front_text_heads = f >= (double)L.bh ? L.bh : (int)f + 2;
-    if (a->front_text_heads > L.bh) a->front_text_heads = L.bh;
-  } else if (L.nq < 2) {
-    a->front_text_heads = L.bh;  // no visual pairs at all: every pair is in the front set
-  }
+  a->front_text_heads = front_text_heads(L, d->top_k);
   a->f16 = d->dtype == RSA_DTYPE_F16;
   a->dbg = g_attention_dbg;
   a->dbg_flags = g_attention_dbg_flags;
@@ -336,6 +341,15 @@ extern "C" int rsa_set_attention_impl(int impl) {
 }
 
 extern "C" void rsa_debug_set_attention_dump(float* device_buffer) { g_attention_dbg = device_buffer; }
+extern "C" void rsa_debug_attention_grid_slot(int id, int n_q_tiles, int nq_vis, int n_bh, int front_heads,
+                                              int former_order, int out[5]) {
+  const GridSlot g = attention_grid_slot(id, n_q_tiles, nq_vis, n_bh, front_heads, former_order != 0);
+  out[0] = g.bh, out[1] = g.pair, out[2] = g.tile0, out[3] = g.tile1, out[4] = g.repaired ? 1 : 0;
+}
+extern "C" int rsa_debug_front_text_heads(const rsa_attn_desc* d) {
+  if (validate_desc(d) != RSA_OK) return -1;
+  return front_text_heads(make_layout(d), d->top_k);
+}
 extern "C" void rsa_debug_set_attention_flags(int flags) { g_attention_dbg_flags = flags | g_env_attention_flags; }
 
 extern "C" size_t rsa_attn_workspace_bytes(const rsa_attn_desc* d) {

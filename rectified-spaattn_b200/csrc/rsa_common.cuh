@@ -60,6 +60,58 @@ inline RowMap row_map(const rsa_attn_desc* d) {
 }
 
 float attention_rescale_threshold(bool f16);
+// Kernel 4's 1-D grid: which pair of query tiles CTA `id` works on.
+// Pairs of adjacent query tiles.  The pairs that hold the dense (text) tiles are several times longer than the others
+// (C3b: 931 rounds against ~200, Flux: 516 against ~65).  The grid walks the heads in order, each head's text pairs first
+// and then its visual pairs (K/V of one head stay L2-resident and are read from HBM once) -- except that the text pairs
+// of the LAST front_text_heads heads are moved to the very start of the grid: where they stood, they ran on after
+// everything else had finished (a text pair lasts as long as several heads' worth of visual pairs).
+// Tiles of a pair: (2 pair, 2 pair + 1).  With an odd number of visual tiles and an even number of text tiles
+// (HunyuanVideo 129 frames: 929 + 2) that rule would pair the last visual tile with a text tile and leave the other text
+// tile alone -- two CTAs running a 931-block list mostly single-slot.  The tail is re-paired instead: the odd visual tile
+// alone, the text tiles with each other (`repaired`: such tiles walk their original ascending lists, kept_idx, because
+// the pair schedule was computed for the (2p, 2p+1) rule; text lists are all "every block with valid keys", so the whole
+// list is common to both slots).  former_order (attention flag 16, A/B): head by head, no re-pairing.
+struct GridSlot {
+  int bh, pair, tile0, tile1;  // tile1 >= nqt: the pair has one tile
+  bool repaired;
+};
+__host__ __device__ inline GridSlot attention_grid_slot(int id, int nqt, int nq_vis, int n_bh, int front_text_heads,
+                                                        bool former_order) {
+  GridSlot g;
+  const int n_pairs = (nqt + 1) / 2;
+  const int nqv = nq_vis < nqt ? nq_vis : nqt;  // visual tiles (rsa_masked_attention passes "all of them" as 2^20)
+  const int vis_pairs = nqv / 2;                // pairs made of visual tiles only
+  const int txt_pairs = n_pairs - vis_pairs;    // pairs with a text tile (or the odd last tile)
+  int front = front_text_heads < 0 ? 0 : front_text_heads;
+  if (front > n_bh) front = n_bh;
+  if (former_order) front = 0;
+  const int n_front = front * txt_pairs;
+  const int n_inline = (n_bh - front) * n_pairs;
+  if (id < n_front) {  // text pairs of the last `front` heads
+    g.bh = n_bh - front + id / txt_pairs;
+    g.pair = n_pairs - 1 - id % txt_pairs;
+  } else if (id - n_front < n_inline) {  // the other heads: text pairs, then visual pairs
+    id -= n_front;
+    g.bh = id / n_pairs;
+    g.pair = n_pairs - 1 - id % n_pairs;
+  } else {  // visual pairs of the last `front` heads
+    id -= n_front + n_inline;
+    g.bh = n_bh - front + id / vis_pairs;
+    g.pair = vis_pairs - 1 - id % vis_pairs;
+  }
+  const int n_txt_tiles = nqt - nqv;
+  g.repaired = (nqv & 1) && n_txt_tiles >= 2 && !(n_txt_tiles & 1) && g.pair >= vis_pairs && !former_order;
+  g.tile0 = 2 * g.pair;
+  g.tile1 = 2 * g.pair + 1;
+  if (g.repaired) {
+    const int q = g.pair - vis_pairs;  // 0: the odd visual tile; q >= 1: text tiles (nq_vis + 2q - 2, nq_vis + 2q - 1)
+    g.tile0 = q == 0 ? nqv - 1 : nqv + 2 * q - 2;
+    g.tile1 = q == 0 ? nqt : g.tile0 + 1;
+  }
+  return g;
+}
+
 int validate_desc(const rsa_attn_desc* d);
 WsLayout make_layout(const rsa_attn_desc* d);
 int check_ws(const rsa_attn_desc* d, const void* ws, size_t bytes, WsLayout* out);

@@ -64,6 +64,7 @@ EXPORTS = [
     "rsa_rectified_attention_host", "rsa_qkv_prep", "rsa_rectified_attention_pooled", "rsa_peer_alloc",
     "rsa_peer_free", "rsa_peer_export", "rsa_peer_open", "rsa_peer_close", "rsa_qkv_prep_gather",
     "rsa_rectified_attention_pooled_scatter", "rsa_rectified_attention_reuse",
+    "rsa_debug_attention_grid_slot", "rsa_debug_front_text_heads",
 ]
 
 _lib = None
@@ -122,6 +123,10 @@ def lib():
     L.rsa_debug_set_attention_dump.restype = None
     L.rsa_debug_set_attention_flags.argtypes = [i32]
     L.rsa_debug_set_attention_flags.restype = None
+    L.rsa_debug_attention_grid_slot.argtypes = [i32, i32, i32, i32, i32, i32, C.POINTER(C.c_int * 5)]
+    L.rsa_debug_attention_grid_slot.restype = None
+    L.rsa_debug_front_text_heads.argtypes = [C.POINTER(AttnDesc)]
+    L.rsa_debug_front_text_heads.restype = i32
     for n in EXPORTS:
         f = getattr(L, n)
         if f.restype is C.c_int and n not in ("rsa_version", "rsa_device_ok", "rsa_set_attention_impl"):

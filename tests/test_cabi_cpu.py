@@ -182,3 +182,62 @@ def test_peer_route_validation():
     d2 = _desc(G.hunyuan(1256, 1200))                                             # ragged visual segment: refused
     r.rows_per_rank = 628
     assert lib.rsa_qkv_prep_gather(C.byref(p), C.byref(d2), C.byref(r), 16, 16, 16, 0, None, 0, None) in (-1, -2)
+
+
+def test_attention_grid_order_visits_every_tile_once():
+    """Kernel 4's 1-D grid (attention_grid_slot, the inline function the kernel itself calls, through its host-side debug
+    entry): for every mix of visual / text tile counts, head counts and front-set sizes, the CTAs of a launch visit each
+    (head, query tile) exactly once; text pairs of the last `front` heads come first; with an odd number of visual tiles
+    and an even number of text tiles the tail is re-paired (odd visual tile alone, text tiles together); the former order
+    (flag) is head by head with the (2p, 2p+1) pairing."""
+    lib = N.lib()
+    out = (C.c_int * 5)()
+
+    def slot(i, nqt, nqv, n_bh, front, former=0):
+        lib.rsa_debug_attention_grid_slot(i, nqt, nqv, n_bh, front, former, C.byref(out))
+        return tuple(out)
+
+    for nqv in range(0, 10):
+        for ntxt in range(0, 5):
+            nqt = nqv + ntxt
+            if nqt == 0:
+                continue
+            n_pairs = (nqt + 1) // 2
+            for n_bh in (1, 2, 3, 7):
+                for front in {0, 1, 2, n_bh, n_bh + 3}:
+                    if nqv < 2:
+                        front = n_bh                 # what the library passes when there are no visual pairs
+                    elif ntxt == 0:
+                        front = 0
+                    for former in (0, 1):
+                        for nqv_arg in {nqv, (1 << 20) if ntxt == 0 else nqv}:    # rsa_masked_attention's "all visual"
+                            seen = {}
+                            for i in range(n_pairs * n_bh):
+                                bh, pair, t0, t1, rep = slot(i, nqt, nqv_arg, n_bh, front, former)
+                                assert 0 <= bh < n_bh and 0 <= pair < n_pairs and 0 <= t0 < nqt
+                                if former:
+                                    assert (bh, pair, t0, t1, rep) == (i // n_pairs, n_pairs - 1 - i % n_pairs,
+                                                                       2 * pair, 2 * pair + 1, 0)
+                                for t in (t0, t1):
+                                    if t < nqt:
+                                        seen[(bh, t)] = seen.get((bh, t), 0) + 1
+                            assert len(seen) == n_bh * nqt and set(seen.values()) == {1}
+    # HunyuanVideo 129 frames: 929 visual + 2 text tiles, 24 heads, text pairs of the last 3 heads in front
+    nqt, nqv, n_bh, front = 931, 929, 24, 3
+    # (two "text pairs" per head here: the re-paired text tiles, and the odd visual tile on its own)
+    assert [slot(i, nqt, nqv, n_bh, front) for i in range(4)] == [(21, 465, 929, 930, 1), (21, 464, 928, 931, 1),
+                                                                  (22, 465, 929, 930, 1), (22, 464, 928, 931, 1)]
+    assert slot(6, nqt, nqv, n_bh, front) == (0, 465, 929, 930, 1)      # head 0 in order: its text tiles ...
+    assert slot(7, nqt, nqv, n_bh, front) == (0, 464, 928, 931, 1)      # ... the odd visual tile alone ...
+    assert slot(8, nqt, nqv, n_bh, front) == (0, 463, 926, 927, 0)      # ... then the visual pairs, descending
+    assert slot(6 + 21 * 466, nqt, nqv, n_bh, front) == (21, 463, 926, 927, 0)   # last heads: their visual pairs
+    assert slot(24 * 466 - 1, nqt, nqv, n_bh, front) == (23, 0, 0, 1, 0)
+    # and the number of front heads the library derives from a descriptor (148 SMs assumed without a device)
+    d = _desc(G.hunyuan(119056, 119000), h=24, top_k=185)
+    assert lib.rsa_debug_front_text_heads(C.byref(d)) == 3
+    d = _desc(G.flux(66048, 512), h=24, top_k=51)
+    assert lib.rsa_debug_front_text_heads(C.byref(d)) == 7
+    d = _desc(G.wan(75600, 28), h=40, top_k=147)
+    assert lib.rsa_debug_front_text_heads(C.byref(d)) == 0
+    d = _desc(G.hunyuan(1280, 1224))                                   # tiny: every head is in the front set
+    assert lib.rsa_debug_front_text_heads(C.byref(d)) == 2

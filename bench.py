@@ -92,6 +92,34 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "reasons": sorted(reasons)}
 
 
+def bind_to_gpu_numa_node(local_rank):
+    """Multi-rank runs: pin this process to the CPUs of its GPU's NUMA node before any host buffer is allocated, so that
+    the pinned tensors of the end-to-end leg live in the memory next to the GPU's PCIe root (what `numactl
+    --cpunodebind` does for a one-process-per-GPU launch).  At 8 ranks the H2D copies otherwise fall from 55 to 23 GB/s
+    per GPU (`profiles/r01_bench_c3b_8gpu.json`): the buffers of all ranks sit in one socket's memory.  Returns the node
+    or None (no NUMA information, or anything unexpected: the run simply goes on unbound)."""
+    try:
+        import torch
+        p = torch.cuda.get_device_properties(local_rank)
+        bus = f"{p.pci_domain_id:04x}:{p.pci_bus_id:02x}:{p.pci_device_id:02x}.0"
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            for part in f.read().strip().split(","):
+                lo, _, hi = part.partition("-")
+                cpus.update(range(int(lo), int(hi or lo) + 1))
+        allowed = os.sched_getaffinity(0) & cpus
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
+
+
 def ncu_traffic(workload):
     """DRAM bytes per launch of kernel 4 from the committed ncu --set full capture of this workload (or None)."""
     p = os.path.join(REPO, "profiles", f"r01_ncu_summary_{workload}.json")
@@ -287,6 +315,7 @@ def main():
     assert torch.cuda.is_available(), "bench.py needs a GPU (no CPU fallback on the product path)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    numa_node = bind_to_gpu_numa_node(local_rank) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert native.lib().rsa_device_ok() == 1
@@ -432,7 +461,7 @@ def main():
                "path": f"public per-family entry point on pinned host tensors -> rsa_rectified_attention_host, "
                        f"{host_chunk} head(s) per chunk (the last {host_chunk} heads one per chunk), H2D | kernels | D2H on three streams",
                "ms_per_step_unpipelined": ms_serial,
-               "h2d_only_ms": ms_h2d}
+               "h2d_only_ms": ms_h2d, "host_numa_node_rank0": numa_node}
 
     if rank == 0:
         peaks = measured_peaks()

@@ -16,13 +16,22 @@ CASES = {
     "hunyuan_ragged": ("hunyuan", (5, 12, 13), 256, 200, 2, 2, 0.3, "walk", 9),
 }
 
+# Cases outside CASES (the GPU parity tests iterate over CASES and assume 128 columns): name -> the CASES tuple + head_dim.
+# cog_d64 = CogVideoX's real head dimension (the reference kernel takes Lk in {16, 32, 64, 128}, wan21 :121); it pins the
+# oracle's 64-column arithmetic (scale 64^-1/2, pooled statistics, GAPR, R, C) against the unmodified reference on CPU.
+EXTRA_CASES = {
+    "cog_d64": ("cogvideo", (8, 16, 32), 226, 226, 2, 6, 0.3, "walk", 31, 64),
+}
+
 # cases the unmodified reference cannot run on the caller's tensors (fixtures are made on the explicitly padded layout)
 REFERENCE_NEEDS_PADDED_LAYOUT = ("hunyuan_ragged",)
 
 
 def case_inputs(name):
-    fam, (t, h, w), text_len, ntrue_d, heads, top_k, p, regime, seed = CASES[name]
+    spec = CASES[name] if name in CASES else EXTRA_CASES[name]
+    fam, (t, h, w), text_len, ntrue_d, heads, top_k, p, regime, seed = spec[:9]
+    head_dim = spec[9] if len(spec) > 9 else 128
     nv = t * h * w
     s = nv + text_len
-    q, k, v = O.synth_qkv(heads, s, 128, regime, seed)
+    q, k, v = O.synth_qkv(heads, s, head_dim, regime, seed)
     return fam, (t, h, w), nv, s, text_len, ntrue_d, heads, top_k, p, q, k, v

@@ -105,6 +105,8 @@ def _varlen_dense(q, k, v, cu_q, cu_k):
 def _dense_masked_kernel(q, k, v, seqlens, block_mask, sm_scale, bm=128, bn=128):
     """Stand-in for the Triton launch inside the combined call (dense masked softmax, fp32)."""
     b, h, s, d = q.shape
+    # the stand-in computes with d^-1/2 (rsa_oracle.masked_attention); hold the reference to passing exactly that
+    assert abs(float(sm_scale) - d ** -0.5) < 1e-12, (sm_scale, d)
     out = torch.zeros_like(q)
     for bi in range(b):
         for hi in range(h):
@@ -114,7 +116,7 @@ def _dense_masked_kernel(q, k, v, seqlens, block_mask, sm_scale, bm=128, bn=128)
     return out
 
 
-from oracle.cases import CASES, case_inputs  # noqa: E402
+from oracle.cases import CASES, EXTRA_CASES, case_inputs  # noqa: E402
 
 
 def run_reference_case(name):
@@ -185,8 +187,9 @@ def run_reference_case(name):
     out = call(_dense_masked_kernel)
     nq = cap["mask"].shape[2]
     rows_vis = min(nq * 128, s)
-    oc = out_c.reshape(1, s, heads, 128)[0].permute(1, 0, 2)      # [H, S, D]
-    orc = out_rc.reshape(1, s, heads, 128)[0].permute(1, 0, 2)
+    hd = q.shape[-1]                                               # 128, or 64 for cog_d64
+    oc = out_c.reshape(1, s, heads, hd)[0].permute(1, 0, 2)       # [H, S, D]
+    orc = out_rc.reshape(1, s, heads, hd)[0].permute(1, 0, 2)
     idx = torch.arange(0, rows_vis, 128)
     c = oc[:, idx]                                                 # [H, NQ, D]
     r = (orc[:, idx] - c).mean(dim=-1)                             # [H, NQ]  (R + C - C, 128 identical columns)
@@ -329,8 +332,9 @@ if __name__ == "__main__":
     if "gilbert" in what:
         make_gilbert()
     if "masks" in what:
-        for n in CASES:
-            if n in what or not any(w in CASES for w in what):   # `masks <case> ...` regenerates only those
+        every = list(CASES) + list(EXTRA_CASES)
+        for n in every:
+            if n in what or not any(w in every for w in what):   # `masks <case> ...` regenerates only those
                 run_reference_case(n)
     if "kernel" in what:
         make_kernel_fp16()

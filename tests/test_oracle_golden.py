@@ -76,6 +76,32 @@ def test_mask_builder_against_reference(name, gold_dir):
         assert np.all(st["R"] > 0) and np.all(st["R"] <= 1 + 1e-6)
 
 
+def test_mask_builder_head_dim_64_against_reference(gold_dir):
+    """CogVideoX's real head dimension.  `mask_cog_d64.npz` is the unmodified reference (rectified_cogvideo_attn.py) run
+    on CPU on 64-column fp32 tensors (oracle/make_golden.py, EXTRA_CASES; the generator also holds the reference to
+    passing sm_scale = 64^-1/2 to its kernel): probabilities, mask, GAPR bytes, R, C and the output of the oracle on the
+    same tensors -- the checker the GPU's head_dim 64 path is held to in test_head_dim_64."""
+    name = "cog_d64"
+    fam, (t, h, w), nv, s, text_len, ntrue_d, heads, top_k, p, q, k, v = C.case_inputs(name)
+    assert q.shape[-1] == 64
+    g = np.load(os.path.join(gold_dir, f"mask_{name}.npz"))
+    mask_ref = _unpack(g["mask"], g["mask_shape"])
+    nogapr_ref = _unpack(g["nogapr"], g["nogapr_shape"])
+    nbr = _unpack(g["nbr"], g["nbr_shape"])
+    assert np.array_equal(G.gilbert_block_neighbors(t, h, w), nbr)
+    geo = _geo(fam, nv, s, text_len, ntrue_d, top_k, p, t)
+    out_ref = g["out"].reshape(s, heads, 64)
+    for hi in range(heads):
+        out, st = O.head_forward(q[0, hi], k[0, hi], v[0, hi], geo, nbr, return_stages=True)
+        np.testing.assert_allclose(st["probs"], g["probs"][hi], rtol=2e-5, atol=1e-7)
+        assert np.array_equal(st["mask"], mask_ref[hi]), f"head {hi}: mask differs"
+        assert np.array_equal(st["nogapr"], nogapr_ref[hi]), f"head {hi}: nogapr differs"
+        np.testing.assert_allclose(st["R"], g["R"][hi], rtol=0, atol=2e-6)
+        np.testing.assert_allclose(st["C"], g["C"][hi], rtol=1e-4, atol=2e-6)
+        np.testing.assert_allclose(out, out_ref[:, hi], rtol=1e-4, atol=2e-5)
+        assert float(st["R"].min()) < 0.9                       # a case in which the rectification matters
+
+
 def test_triton_kernel_semantics_fp16(gold_dir):
     """The literal reference kernel (TRITON_INTERPRET, fp16) vs the oracle's dense masked restatement."""
     import torch

@@ -51,6 +51,13 @@ int rsa_version(void);
 /* 1 if the library was built with the tcgen05/TMEM/TMA attention kernel and the current device is sm_100. */
 int rsa_device_ok(void);
 
+/* The reference's recursion gilbert_xyz2d_r (utils/jenga_gilbert.py:84-288): index, counted from cur_idx, of the point
+ * (x_dst, y_dst, z_dst) on the generalised Hilbert curve through the box with origin (x, y, z) spanned by the major, mid
+ * and minor vectors a, b, c (axis-parallel, signed).  -1 if the point is outside the box or the box is degenerate. */
+int64_t rsa_gilbert_xyz2d_r(int64_t cur_idx, int64_t x_dst, int64_t y_dst, int64_t z_dst, int64_t x, int64_t y, int64_t z,
+                            int64_t ax, int64_t ay, int64_t az, int64_t bx, int64_t by, int64_t bz, int64_t cx,
+                            int64_t cy, int64_t cz);
+
 /* ------------------------------------------------------------------------------------------------------
  * Host geometry (pure CPU).  Replaces utils/jenga_gilbert.py:
  *   gilbert_mapping(t,h,w,axis_order)                 :458-504  -> rsa_gilbert_map

@@ -326,9 +326,66 @@ def make_prep():
     print("prep golden", tuple(q.shape), float(q.float().abs().mean()), flush=True)
 
 
+# ------------------------------------------------------------------- recursion helpers and the public API surface
+def make_helpers():
+    """gilbert_helpers.json: sgn / in_bounds / gilbert_xyz2d_r of the reference on seeded random frames (the three
+    frame forms of gilbert_xyz2d :34-54 plus the fourth permutation, shifted origins, index offsets, flipped major axis).
+    api_signatures.json: names, parameter names, kinds and defaults of every function and class (__init__, __call__)
+    the reference's hot-path modules define -- what "drop-in" means for the mirror modules of this repo."""
+    import inspect
+    import random
+
+    g = ref_loader.load(["jenga_gilbert"])["jenga_gilbert"]
+    rnd = random.Random(5)
+    rows = []
+    while len(rows) < 200:
+        w, h, d = (rnd.randint(1, 9) for _ in range(3))
+        a, b, c = rnd.choice([((w, 0, 0), (0, h, 0), (0, 0, d)), ((0, h, 0), (w, 0, 0), (0, 0, d)),
+                              ((0, 0, d), (w, 0, 0), (0, h, 0)), ((0, 0, d), (0, h, 0), (w, 0, 0))])
+        o = [rnd.randint(-5, 5) for _ in range(3)]
+        pt = (o[0] + rnd.randrange(w), o[1] + rnd.randrange(h), o[2] + rnd.randrange(d))
+        ci = rnd.randint(0, 1000)
+        if rnd.random() < 0.3:
+            ax = [i for i in range(3) if a[i] != 0][0]
+            o[ax] += a[ax] - 1
+            a = tuple(-v for v in a)
+        outside = (pt[0] + rnd.choice((-11, 11)), pt[1], pt[2])
+        frame = [*o, *a, *b, *c]
+        rows.append({"args": [ci, *pt, *frame], "index": g.gilbert_xyz2d_r(ci, *pt, *frame),
+                     "in_bounds": bool(g.in_bounds(*pt, *frame)), "outside": list(outside),
+                     "outside_in_bounds": bool(g.in_bounds(*outside, *frame))})
+    with open(os.path.join(GOLD, "gilbert_helpers.json"), "w") as f:
+        json.dump({"sgn": {str(v): g.sgn(v) for v in (-7, -1, 0, 1, 12)}, "cases": rows}, f)
+
+    mods = ["rectified_wan21_attn", "rectified_wan22_attn", "rectified_hunyuan_attn", "rectified_flux_attn",
+            "rectified_cogvideo_attn", "attn", "gapr_mask", "attn_processor", "jenga_gilbert"]
+    ref = ref_loader.load(mods)
+
+    def sig(fn):
+        return [[p.name, p.kind.name, None if p.default is inspect._empty else repr(p.default)]
+                for p in inspect.signature(fn).parameters.values()]
+
+    api = {}
+    for name, m in ref.items():
+        entry = {}
+        for k, v in vars(m).items():
+            if k.startswith("__") or getattr(v, "__module__", None) != m.__name__:
+                continue
+            if inspect.isfunction(v):
+                entry[k] = {"kind": "function", "params": sig(v)}
+            elif inspect.isclass(v):
+                entry[k] = {"kind": "class", "init": sig(v.__init__)}
+                if "__call__" in vars(v):
+                    entry[k]["call"] = sig(v.__call__)
+        api[name] = entry
+    with open(os.path.join(GOLD, "api_signatures.json"), "w") as f:
+        json.dump(api, f, indent=1)
+    print("helpers", len(rows), "api", {k: len(v) for k, v in api.items()}, flush=True)
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    what = sys.argv[1:] or ["gilbert", "masks", "kernel", "prep"]
+    what = sys.argv[1:] or ["gilbert", "masks", "kernel", "prep", "helpers"]
     if "gilbert" in what:
         make_gilbert()
     if "masks" in what:
@@ -340,3 +397,5 @@ if __name__ == "__main__":
         make_kernel_fp16()
     if "prep" in what:
         make_prep()
+    if "helpers" in what:
+        make_helpers()

@@ -170,6 +170,17 @@ bool frame_for(int t, int h, int w, const char* axis_order, V3* a, V3* b, V3* c)
 
 }  // namespace
 
+extern "C" int64_t rsa_gilbert_xyz2d_r(int64_t cur_idx, int64_t x_dst, int64_t y_dst, int64_t z_dst, int64_t x,
+                                       int64_t y, int64_t z, int64_t ax, int64_t ay, int64_t az, int64_t bx, int64_t by,
+                                       int64_t bz, int64_t cx, int64_t cy, int64_t cz) {
+  const V3 p{x_dst, y_dst, z_dst}, o{x, y, z}, a{ax, ay, az}, b{bx, by, bz}, c{cx, cy, cz};
+  if (sum(a) == 0 || sum(b) == 0 || sum(c) == 0 || !inside(p, o, a, b, c)) {
+    rsa::set_error("rsa_gilbert_xyz2d_r: the point is not inside the frame (or the frame is degenerate)");
+    return -1;
+  }
+  return cur_idx + gilbert_index(p - o, a, b, c);  // the curve depends on the frame only through p - o
+}
+
 extern "C" int rsa_gilbert_map(int t, int h, int w, const char* axis_order, int64_t* l2h, int64_t* h2l) {
   if (t <= 0 || h <= 0 || w <= 0) {
     rsa::set_error("rsa_gilbert_map: grid sizes must be positive (t=%d h=%d w=%d)", t, h, w);

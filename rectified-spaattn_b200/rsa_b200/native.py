@@ -64,7 +64,7 @@ EXPORTS = [
     "rsa_rectified_attention_host", "rsa_qkv_prep", "rsa_rectified_attention_pooled", "rsa_peer_alloc",
     "rsa_peer_free", "rsa_peer_export", "rsa_peer_open", "rsa_peer_close", "rsa_qkv_prep_gather",
     "rsa_rectified_attention_pooled_scatter", "rsa_rectified_attention_reuse",
-    "rsa_debug_attention_grid_slot", "rsa_debug_front_text_heads",
+    "rsa_debug_attention_grid_slot", "rsa_debug_front_text_heads", "rsa_gilbert_xyz2d_r",
 ]
 
 _lib = None
@@ -91,6 +91,8 @@ def lib():
     L.rsa_device_ok.restype = i32
     L.rsa_gilbert_map.argtypes = [i32, i32, i32, C.c_char_p, p, p]
     L.rsa_gilbert_block_neighbors.argtypes = [i32, i32, i32, i32, C.c_char_p, p]
+    L.rsa_gilbert_xyz2d_r.argtypes = [i64] * 16
+    L.rsa_gilbert_xyz2d_r.restype = i64
     L.rsa_permute_rows.argtypes = [p, p, p, i32, i64, i64, i64, i64, i64, p]
     L.rsa_attn_workspace_bytes.argtypes = [C.POINTER(AttnDesc)]
     L.rsa_attn_workspace_bytes.restype = sz

@@ -241,3 +241,83 @@ def test_attention_grid_order_visits_every_tile_once():
     assert lib.rsa_debug_front_text_heads(C.byref(d)) == 0
     d = _desc(G.hunyuan(1280, 1224))                                   # tiny: every head is in the front set
     assert lib.rsa_debug_front_text_heads(C.byref(d)) == 2
+
+
+def test_gilbert_recursion_helpers_against_reference():
+    """sgn / in_bounds / gilbert_xyz2d_r keep their reference names and results (`gilbert_helpers.json`: the reference's
+    own functions on seeded random frames -- shifted origins, index offsets, flipped major axis; oracle/make_golden.py).
+    The recursion runs in csrc/gilbert.cc (rsa_gilbert_xyz2d_r); a point outside the frame is an error, not a value."""
+    import json
+
+    import utils.jenga_gilbert as J
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "gilbert_helpers.json")) as f:
+        g = json.load(f)
+    for v, want in g["sgn"].items():
+        assert J.sgn(int(v)) == want
+    for c in g["cases"]:
+        a = c["args"]
+        assert J.in_bounds(*a[1:]) == c["in_bounds"]
+        assert J.in_bounds(*c["outside"], *a[4:]) == c["outside_in_bounds"]
+        assert J.gilbert_xyz2d_r(*a) == c["index"]
+        if not c["outside_in_bounds"]:
+            with pytest.raises(ValueError):
+                J.gilbert_xyz2d_r(a[0], *c["outside"], *a[4:])
+
+
+# names of the reference that this repo does not provide, each with the reason (DESIGN.md section 7)
+NOT_PROVIDED = {
+    "jenga_gilbert": {"transpose_gilbert_mapping", "sliced_gilbert_mapping", "block_wise_mapping",
+                      "sliced_gilbert_block_neighbor_mapping",            # variants no reference script calls
+                      "visualize_gilbert_curve", "visualize_gilbert_curves_comparison"},   # matplotlib visualisers
+}
+
+
+def test_api_surface_matches_reference():
+    """`api_signatures.json` lists every function and class (__init__, __call__) the reference's hot-path modules define,
+    with parameter names, kinds and defaults (inspect.signature on the unmodified reference, oracle/make_golden.py).  The
+    mirror modules must define the same names with the same parameters in the same order and the same defaults; they may
+    give a default where the reference has none and may append parameters that have defaults (mask re-use, fused
+    pre-attention steps)."""
+    import importlib
+    import inspect
+    import json
+
+    with open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "api_signatures.json")) as f:
+        api = json.load(f)
+
+    def sig(fn):
+        return [(p.name, p.kind.name, None if p.default is inspect._empty else repr(p.default))
+                for p in inspect.signature(fn).parameters.values()]
+
+    def compare(ref_params, fn, where, problems):
+        ours = sig(fn)
+        for i, (name, kind, default) in enumerate(ref_params):
+            if i >= len(ours):
+                problems.append(f"{where}: parameter {name} is missing")
+                continue
+            oname, okind, odefault = ours[i]
+            if oname != name or okind != kind:
+                problems.append(f"{where}: parameter {i} is {oname} ({okind}), the reference has {name} ({kind})")
+            elif default is not None and odefault != default:
+                problems.append(f"{where}: {name} defaults to {odefault}, the reference to {default}")
+        for name, kind, default in ours[len(ref_params):]:
+            if default is None and kind not in ("VAR_POSITIONAL", "VAR_KEYWORD"):
+                problems.append(f"{where}: extra parameter {name} has no default")
+
+    problems = []
+    for mod, entry in api.items():
+        ours = importlib.import_module("utils.jenga_gilbert" if mod == "jenga_gilbert" else "rectified_spaattn." + mod)
+        for name, e in entry.items():
+            if name in NOT_PROVIDED.get(mod, ()):
+                assert not hasattr(ours, name)
+                continue
+            obj = getattr(ours, name, None)
+            if obj is None:
+                problems.append(f"{mod}.{name} is missing")
+            elif e["kind"] == "function":
+                compare(e["params"], obj, f"{mod}.{name}", problems)
+            else:
+                compare(e["init"], obj.__init__, f"{mod}.{name}.__init__", problems)
+                if "call" in e:
+                    compare(e["call"], obj.__call__, f"{mod}.{name}.__call__", problems)
+    assert not problems, "\n".join(problems)

@@ -321,3 +321,48 @@ def test_api_surface_matches_reference():
                 if "call" in e:
                     compare(e["call"], obj.__call__, f"{mod}.{name}.__call__", problems)
     assert not problems, "\n".join(problems)
+
+
+def test_attn_processor_helpers():
+    """get_attn_processors / set_attn_processor (reference attn_processor.py:6-62) on a small module tree of fake
+    attention layers: key naming, one processor for all, a dict keyed like the getter's (consumed while it is applied),
+    ValueError on a dict of the wrong size.  The expected values are what the reference itself returns on this tree
+    (checked in the build container)."""
+    import torch
+
+    from rectified_spaattn.attn_processor import get_attn_processors, set_attn_processor
+
+    class Attn(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.p, self.inner = "default", torch.nn.Linear(2, 2)
+
+        def get_processor(self):
+            return self.p
+
+        def set_processor(self, p):
+            self.p = p
+
+    class Block(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.attn1, self.attn2, self.ff = Attn(), Attn(), torch.nn.Linear(2, 2)
+
+    class Model(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.blocks, self.single = torch.nn.ModuleList([Block(), Block()]), Attn()
+            self.proj = torch.nn.Linear(2, 2)
+
+    m = Model()
+    keys = ["blocks.0.attn1.processor", "blocks.0.attn2.processor", "blocks.1.attn1.processor",
+            "blocks.1.attn2.processor", "single.processor"]
+    assert sorted(get_attn_processors(m)) == keys and set(get_attn_processors(m).values()) == {"default"}
+    set_attn_processor(m, "X")
+    assert get_attn_processors(m) == {k: "X" for k in keys}
+    procs = {k: k.upper() for k in keys}
+    arg = dict(procs)
+    set_attn_processor(m, arg)
+    assert get_attn_processors(m) == procs and arg == {}
+    with pytest.raises(ValueError, match="number of processors 1 does not match"):
+        set_attn_processor(m, {"a": 1})

@@ -366,3 +366,21 @@ def test_attn_processor_helpers():
     assert get_attn_processors(m) == procs and arg == {}
     with pytest.raises(ValueError, match="number of processors 1 does not match"):
         set_attn_processor(m, {"a": 1})
+
+
+def test_attn_helpers_against_reference_values():
+    """get_cu_seqlens / get_attn_mask / get_flash_attn_params of rectified_spaattn/attn.py (reference :34-57, :157-178).
+    The reference allocates on "cuda" unconditionally; the expected values below are its own results with that
+    allocation redirected to the CPU in the build container."""
+    import torch
+
+    from rectified_spaattn import attn as A
+    cu = A.get_cu_seqlens(1000, 256, [200], device="cpu")
+    assert cu.dtype == torch.int32 and cu.tolist() == [0, 1200, 1256]
+    cu = A.get_cu_seqlens(64, 16, [3, 16, 0], device="cpu")
+    assert cu.tolist() == [0, 67, 80, 160, 160, 224, 240]
+    m = A.get_attn_mask(64, 16, [3, 16, 0], device="cpu")
+    assert m.shape == (3, 1, 1, 80) and m.dtype == torch.bool
+    assert m[:, 0, 0].sum(1).tolist() == [67, 80, 64] and bool(m[0, 0, 0, :67].all()) and not bool(m[0, 0, 0, 67:].any())
+    cq, ck, sq, sk = A.get_flash_attn_params(1000, 256, [200], device="cpu")
+    assert cq.tolist() == ck.tolist() == [0, 1200, 1256] and (sq, sk) == (1256, 1256)

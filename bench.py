@@ -92,6 +92,16 @@ class ClockSampler(threading.Thread):
                 "samples": len(self.rows), "reasons": sorted(reasons)}
 
 
+def parse_cpulist(text):
+    """sysfs cpulist ("0-7,16-23", "5") -> set of CPU numbers."""
+    cpus = set()
+    for part in text.strip().split(","):
+        if part:
+            lo, _, hi = part.partition("-")
+            cpus.update(range(int(lo), int(hi or lo) + 1))
+    return cpus
+
+
 def bind_to_gpu_numa_node(local_rank):
     """Multi-rank runs: pin this process to the CPUs of its GPU's NUMA node before any host buffer is allocated, so that
     the pinned tensors of the end-to-end leg live in the memory next to the GPU's PCIe root (what `numactl
@@ -106,11 +116,8 @@ def bind_to_gpu_numa_node(local_rank):
             node = int(f.read().strip())
         if node < 0:
             return None
-        cpus = set()
         with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
-            for part in f.read().strip().split(","):
-                lo, _, hi = part.partition("-")
-                cpus.update(range(int(lo), int(hi or lo) + 1))
+            cpus = parse_cpulist(f.read())
         allowed = os.sched_getaffinity(0) & cpus
         if not allowed:
             return None

@@ -70,3 +70,23 @@ def test_ulysses_exchange_world2(tmp_path):
     world = 2
     mp.spawn(_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
     assert all((tmp_path / f"ok{r}").exists() for r in range(world))
+
+
+def test_bench_cpulist_parser_and_unbound_fallback():
+    """bench.py binds the ranks of a multi-rank run to their GPU's NUMA node; the sysfs cpulist parser, and the fallback:
+    without a CUDA device (this container) the binding returns None and leaves the affinity alone."""
+    import os
+    import sys
+    argv, sys.argv = sys.argv, [sys.argv[0]]
+    try:
+        sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+        import bench
+    finally:
+        sys.argv = argv
+    assert bench.parse_cpulist("0-7\n") == set(range(8))
+    assert bench.parse_cpulist("0-3,8-11,40") == {0, 1, 2, 3, 8, 9, 10, 11, 40}
+    assert bench.parse_cpulist("5") == {5} and bench.parse_cpulist("") == set()
+    import torch
+    if not torch.cuda.is_available():
+        before = os.sched_getaffinity(0)
+        assert bench.bind_to_gpu_numa_node(0) is None and os.sched_getaffinity(0) == before

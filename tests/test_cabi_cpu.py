@@ -384,3 +384,23 @@ def test_attn_helpers_against_reference_values():
     assert m[:, 0, 0].sum(1).tolist() == [67, 80, 64] and bool(m[0, 0, 0, :67].all()) and not bool(m[0, 0, 0, 67:].any())
     cq, ck, sq, sk = A.get_flash_attn_params(1000, 256, [200], device="cpu")
     assert cq.tolist() == ck.tolist() == [0, 1200, 1256] and (sq, sk) == (1256, 1256)
+
+
+def test_product_never_imports_the_oracle():
+    """The oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it.
+    No Python file of the package, and no C/CUDA source, refers to it; bench.py imports it inside cpu_sample only."""
+    import re
+    pkg = os.path.join(REPO, "rectified-spaattn_b200")
+    offenders = []
+    for root, dirs, files in os.walk(pkg):
+        dirs[:] = [d for d in dirs if d not in ("build", "__pycache__")]
+        for fn in files:
+            if fn.endswith((".py", ".cu", ".cuh", ".cc", ".h")):
+                text = open(os.path.join(root, fn), encoding="utf-8", errors="replace").read()
+                if re.search(r"^\s*(from|import)\s+oracle\b", text, re.M) or "oracle/" in text:
+                    offenders.append(os.path.join(root, fn))
+    assert not offenders, offenders
+    bench_src = open(os.path.join(REPO, "bench.py"), encoding="utf-8").read()
+    body = bench_src.split("def cpu_sample(", 1)[1].split("\ndef ", 1)[0]
+    imports = re.findall(r"^\s*from oracle import .*$", bench_src, re.M)
+    assert imports and all(line.strip() in body for line in imports)

@@ -196,64 +196,210 @@ def entry_point(wp):
 
 
 # --------------------------------------------------------------------------------------------- CPU baseline
-def cpu_sample(wp, regime, budget_s=12.0, threads=None):
-    """The oracle (a CPU port of the reference algorithm) on a bounded sample of the workload: ONE head, the mask
-    build for every query block of that head, and the attention for the first n query blocks (n sized to the time
-    budget).  Returns dense-equivalent TFLOP/s extrapolated to the whole head."""
-    import numpy as np
+class CpuArm:
+    """The reference's CPU path on the host cores.  Unit of work = ONE HEAD through the whole call (heads are independent
+    and cost the same; a CPU runs them one after the other), every stage and every query block of it -- no proration.
+
+    kind "reference": the reference's own PyTorch code from baseline/_ref (mask builder, GAPR, IPAR, sort / cumsum /
+    scatter, R, C, epilogue, cat / permute) on fp32 CPU tensors, with its two CUDA-only pieces -- the Triton launch and
+    the flash-attn call -- restated (oracle/ref_cpu.py).  kind "port": the oracle's restatement of all of it, when the
+    reference files are not on the box.  Nothing of the product (rsa_b200, librsa_b200.so) is imported here."""
+
+    def __init__(self, wp, regime, threads=None, heads=1):
+        import torch
+
+        from oracle import gilbert_oracle as GO
+        from oracle import ref_cpu
+        from oracle import rsa_oracle as O
+
+        # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would silently make
+        # this a single-thread baseline)
+        torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
+        self.cores = torch.get_num_threads()
+        self.wp, self.O, self.torch = wp, O, torch
+        s = wp["s"]
+        self.heads = heads
+        q, k, v = O.synth_qkv(heads, s, 128, regime, 0)
+        t, h, w = wp["grid"]
+        self.nbr = GO.gilbert_block_neighbors(t, h, w)
+        self.kind = "reference" if ref_cpu.available() else "port"
+        if self.kind == "reference":
+            self.runner = ref_cpu.ReferenceOnCpu(wp["fam"])
+            self.q, self.k, self.v = (torch.from_numpy(x) for x in (q, k, v))
+            self.nbr_t = torch.from_numpy(self.nbr)
+        else:
+            self.q, self.k, self.v = q, k, v
+            if wp["fam"] == "wan":
+                self.geo = O.geometry_wan(s, wp["top_k"], P_REMAIN, wp["ffb_blocks"])
+            elif wp["fam"] == "hunyuan":
+                self.geo = O.geometry_hunyuan(s, wp["num_true"], wp["top_k"], P_REMAIN)
+            else:
+                self.geo = O.geometry_flux(s, wp["text"], wp["top_k"], P_REMAIN)
+
+    def head(self):
+        """`heads` heads (default ONE) through the whole call; returns seconds."""
+        wp = self.wp
+        t0 = time.perf_counter()
+        if self.kind == "reference":
+            self.runner.call(self.q, self.k, self.v, self.nbr_t, wp["top_k"], P_REMAIN, num_true=wp["num_true"],
+                             text_len=wp["text"], first_frame_blocks=wp["ffb_blocks"] or None)
+        else:
+            self.O.forward(self.q, self.k, self.v, self.geo, self.nbr)
+        return time.perf_counter() - t0
+
+    def describe(self, t_head, n_heads_timed):
+        wp = self.wp
+        what = ("the reference's own PyTorch mask builder / GAPR / R / C / epilogue from baseline/_ref on fp32 CPU tensors, "
+                "its Triton launch and flash-attn call restated (oracle/ref_cpu.py)" if self.kind == "reference"
+                else "oracle port (reference files not on this box)")
+        return dict(value=wp["dense_flop_per_head"] / t_head / 1e12, unit="TFLOP/s (dense-equivalent)", cores=self.cores,
+                    kind=self.kind,
+                    sample=f"{wp['name']}: ONE head of {wp['heads']} through the whole call (all stages, all "
+                           f"{(wp['s'] + 127) // 128} query blocks), {t_head:.2f} s per head, median of {n_heads_timed}; "
+                           f"heads are independent and run one after the other on a CPU; {what}",
+                    s_per_head=t_head,
+                    ms_per_call_all_heads_extrapolated=t_head * wp["heads"] * 1e3)
+
+
+def cpu_c1_full(regime):
+    """BASELINE.json configs[0] (C1: 4x16x16 = 1024 tokens, 12 heads) through the CPU arm IN FULL: all 12 heads,
+    median of 5 calls -- no extrapolation."""
+    wp = workload_params("c1")
+    wp["name"] = "c1"
+    arm = CpuArm(wp, regime, heads=wp["heads"])
+    arm.head()
+    ts = sorted(arm.head() for _ in range(5))
+    return {"workload": "c1: " + wp["desc"], "heads": wp["heads"], "ms_per_call": ts[2] * 1e3, "cores": arm.cores,
+            "kind": arm.kind, "dense_equiv_tflops": wp["dense_flop_per_head"] * wp["heads"] / ts[2] / 1e12,
+            "note": "the whole call, all 12 heads in one invocation, median of 5, no extrapolation"}
+
+
+# ------------------------------------------------------------------------------------- the reference on the GPU
+def load_reference_from_baseline(names):
+    """The UNMODIFIED reference's hot-path modules from baseline/_ref (staged by __graft_entry__.build(); git-ignored,
+    travels with gpurun).  diffusers / matplotlib are not installed: empty stand-ins for the names the reference imports
+    at module scope.  The reference keeps the package name `rectified_spaattn`, which this repo mirrors, so it is aliased."""
+    import importlib
+    import types
+    root = os.path.join(REPO, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(root, "rectified_spaattn")):
+        return None
+
+    def stub(name, **attrs):
+        if name not in sys.modules:
+            m = types.ModuleType(name)
+            m.__dict__.update(attrs)
+            sys.modules[name] = m
+    try:
+        import diffusers  # noqa: F401
+    except Exception:  # noqa: BLE001
+        for n in ("diffusers", "diffusers.models", "diffusers.models.transformers"):
+            stub(n)
+        stub("diffusers.models.attention_processor", Attention=object, AttentionProcessor=object)
+        stub("diffusers.models.transformers.transformer_wan", _get_qkv_projections=None, _get_added_kv_projections=None)
+    if "ref_rectified_spaattn" not in sys.modules:
+        pkg = types.ModuleType("ref_rectified_spaattn")
+        pkg.__path__ = [os.path.join(root, "rectified_spaattn")]
+        sys.modules["ref_rectified_spaattn"] = pkg
+    return {n: importlib.import_module("ref_rectified_spaattn." + n) for n in names}
+
+
+def reference_on_gpu(name, regime, dev, ours_ms_fn):
+    """SURVEY 8d "Reference beside it -- GPU": the unmodified reference (PyTorch eager mask builder in bf16, its Triton
+    JIT kernel, flash-attn for the text rows) through its own public entry point on the SAME inputs on this B200, and
+    this repository's call on them.  C3a (128 frames) is the largest HunyuanVideo shape the reference runs: on the
+    129-frame shape of the headline it raises (rectified_hunyuan_attn.py:356)."""
     import torch
-
-    from oracle import gilbert_oracle as GO  # noqa: F401
-    from oracle import rsa_oracle as O
-    from rsa_b200 import ops as host_ops  # only the pure-CPU geometry helper (no GPU, no kernels)
-
-    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1, which would silently make this
-    # a single-thread baseline)
-    torch.set_num_threads(threads or len(os.sched_getaffinity(0)))
-    cores = torch.get_num_threads()
-    s = wp["s"]
-    q, k, v = O.synth_qkv(1, s, 128, regime, 0)
-    q, k, v = q[0, 0], k[0, 0], v[0, 0]
+    from rsa_b200 import ops
+    wp = workload_params(name)
+    wp["name"] = name
+    modname = {"wan": "rectified_wan21_attn", "hunyuan": "rectified_hunyuan_attn", "flux": "rectified_flux_attn"}[wp["fam"]]
+    try:
+        mods = load_reference_from_baseline([modname])
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"reference import failed: {e!r}"[:300]}
+    if mods is None:
+        return {"unavailable": "baseline/_ref is not on this box (run __graft_entry__.build() where /root/reference exists)"}
+    ref = mods[modname]
     t, h, w = wp["grid"]
-    nbr = host_ops.gilbert_block_neighbors(t, h, w).numpy()
-    if wp["fam"] == "wan":
-        geo = O.geometry_wan(s, wp["top_k"], P_REMAIN, wp["ffb_blocks"])
-    elif wp["fam"] == "hunyuan":
-        geo = O.geometry_hunyuan(s, wp["num_true"], wp["top_k"], P_REMAIN)
-    else:
-        geo = O.geometry_flux(s, wp["text"], wp["top_k"], P_REMAIN)
-    t0 = time.perf_counter()
-    nq, nv = geo.nq_blocks, geo.nq_blocks * 128
-    q, k, v = O.padded_inputs(q, k, v, geo)          # identity unless the visual segment is ragged (c3b)
-    hole = (nv - geo.gap, nv) if geo.gap else None
-    seq_v = geo.seq + geo.gap
-    qp, dq = O.pool_stats(q, seq_v, nq)
-    kp, dk = O.pool_stats(k, geo.kv_zero_from, nq)
-    vp, _ = O.pool_stats(v, geo.kv_zero_from, geo.n_blocks, want_mad=False)
-    kt = k[nv: nv + geo.text_keys] if geo.family == "joint" else None
-    a, nogapr = O.block_scores(qp, dq, kp, dk, kt)
-    p = O.probs_from_scores(a, nq, 128, geo.family == "joint")
-    m, _ = O.select_blocks(p, geo, nbr)
-    O.rectify_factors(p, m, nogapr, vp, geo)
-    t_mask = time.perf_counter() - t0
-    # attention on a growing sample until the budget is used
-    n_done, t_attn = 0, 0.0
-    n = 2
-    while n_done < nq and t_attn < budget_s:
-        n = min(n, nq - n_done)
-        t1 = time.perf_counter()
-        O.masked_attention(q[n_done * 128:], k, v, m[n_done: n_done + n], geo.kv_len,
-                           min(n * 128, seq_v - n_done * 128), hole=hole)
-        t_attn += time.perf_counter() - t1
-        n_done += n
-        n *= 2
-    nqt = geo.n_blocks
-    t_head = t_mask + t_attn * (nqt / n_done)
-    tflops = wp["dense_flop_per_head"] / t_head / 1e12
-    return dict(value=tflops, unit="TFLOP/s (dense-equivalent)", cores=cores, kind="port",
-                sample=f"{wp['name']} one head of {wp['heads']}: mask build for all {nq} query blocks ({t_mask:.2f} s) + "
-                       f"attention of the first {n_done} of {nqt} query blocks ({t_attn:.2f} s), extrapolated to the head",
-                ms_per_call_extrapolated=t_head * wp["heads"] * 1e3)
+    nbr = ops.gilbert_block_neighbors(t, h, w)
+    q, k, v = synth_heads_device(wp["heads"], 0, wp["s"], regime, dev)
+    s = wp["s"]
+
+    def call_ref():
+        if wp["fam"] == "wan":
+            return ref.rectified_block_sparse_attention(q, k, v, None, wp["top_k"], block_neighbor_list=nbr,
+                                                        p_remain_rates=P_REMAIN, first_frame_blocks=wp["ffb_blocks"])
+        if wp["fam"] == "hunyuan":
+            am = (torch.arange(s, device=dev) < wp["num_true"]).view(1, 1, 1, s)
+            cu = torch.tensor([0, wp["num_true"], s], dtype=torch.int32, device=dev)
+            return ref.rectified_block_sparse_attention(q, k.clone(), v.clone(), am, wp["top_k"], cu_seqlens_q=cu,
+                                                        cu_seqlens_kv=cu, max_seqlen_q=s, max_seqlen_kv=s,
+                                                        block_neighbor_list=nbr, p_remain_rates=P_REMAIN)
+        cu = torch.tensor([0, s, s], dtype=torch.int32, device=dev)
+        return ref.rectified_block_sparse_attention(q, k, v, None, wp["top_k"], cu_seqlens_q=cu, cu_seqlens_kv=cu,
+                                                    max_seqlen_q=s, max_seqlen_kv=s, block_neighbor_list=nbr,
+                                                    p_remain_rates=P_REMAIN, text_length=wp["text"])
+
+    stage = {}
+    orig_build = ref._build_block_index_with_importance_optimized
+    orig_kernel = ref._triton_block_sparse_attention_onehot
+
+    def wrap(key, fn):
+        def inner(*a, **kw):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            r = fn(*a, **kw)
+            e1.record()
+            torch.cuda.synchronize()
+            stage.setdefault(key, []).append(e0.elapsed_time(e1))
+            if key == "kernel":
+                stage["kept_pairs"] = int(a[4].sum().item())
+            return r
+        return inner
+
+    def one():
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        o = call_ref()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1), o
+
+    try:
+        for _ in range(3):      # Triton JIT + warm-up
+            one()
+        tot = sorted(one()[0] for _ in range(5))
+        ref._build_block_index_with_importance_optimized = wrap("mask_build", orig_build)
+        ref._triton_block_sparse_attention_onehot = wrap("kernel", orig_kernel)
+        for _ in range(3):
+            _, o_ref = one()
+    except Exception as e:  # noqa: BLE001
+        return {"unavailable": f"reference call failed: {e!r}"[:300]}
+    finally:
+        ref._build_block_index_with_importance_optimized = orig_build
+        ref._triton_block_sparse_attention_onehot = orig_kernel
+    geo = product_geometry(wp)
+    plan = ops.Plan(q, k, v, geo, wp["top_k"], P_REMAIN, nbr)
+    ours_ms = ours_ms_fn(plan.run)
+    o_ours = plan.run()
+    torch.cuda.synchronize()
+    rows = min(wp["num_true"], s)
+    a, b = o_ours.reshape(1, s, -1)[0, :rows].float(), o_ref.reshape(1, s, -1)[0, :rows].float()
+    cos = float(torch.nn.functional.cosine_similarity(a.flatten(), b.flatten(), dim=0))
+    ms_ref = tot[len(tot) // 2]
+    dense = wp["dense_flop_per_head"] * wp["heads"]
+    return {"workload": f"{name}: {wp['desc']}", "regime": regime, "impl": "unmodified reference from baseline/_ref: "
+            "rectified_block_sparse_attention -> PyTorch eager mask builder (bf16) + Triton JIT kernel + flash-attn text rows",
+            "ms_per_call": ms_ref, "ms_all": tot, "mask_build_ms": sorted(stage["mask_build"])[1],
+            "kernel_ms": sorted(stage["kernel"])[1], "kept_pairs": stage.get("kept_pairs"),
+            "dense_equiv_tflops": dense / (ms_ref * 1e-3) / 1e12,
+            "ours_ms_per_call": ours_ms, "ours_dense_equiv_tflops": dense / (ours_ms * 1e-3) / 1e12,
+            "speedup": ms_ref / ours_ms, "output_cosine_ours_vs_reference": cos,
+            "note": "same synthetic bf16 inputs, same B200, same process; CUDA events around the whole public call; the "
+                    "reference's bf16 mask differs from the fp32 one on near-tie entries (SURVEY 0.5), so outputs agree "
+                    "in cosine, not element-wise"}
 
 
 # ------------------------------------------------------------------------------------------------------ main
@@ -271,6 +417,8 @@ def main():
                          "form, 16 = kernel 4 grid in the former order")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-reference-gpu", action="store_true",
+                    help="skip the reference_gpu key (the unmodified reference from baseline/_ref on this GPU)")
     ap.add_argument("--no-permute", action="store_true")
     ap.add_argument("--host-chunk", type=int, default=0,
                     help="heads per chunk of the pipelined host-buffer call (0 = library default: 2, or 1 below 8 heads)")
@@ -295,22 +443,24 @@ def main():
               "l2": "inputs (Q,K,V >= 0.4 GB) exceed the 126 MB L2; no explicit flush"}
 
     if args.impl == "reference":
-        # The reference's own CPU implementation of the path = PyTorch eager ops; its Python sources cannot travel
-        # to the GPU box, so this arm times the oracle port (same algorithm) on the host cores, rank 0 only.
+        # The reference's own CPU implementation of the path, on the box's host cores, rank 0 only: ONE step = ONE head
+        # of this arm's workload through the whole call (CpuArm).  W warm-up steps, then exactly K timed steps.
         if rank != 0:
             return
-        vals = []
-        base = None
-        for i in range(max(1, min(args.steps, 3))):
-            base = cpu_sample(wp, args.regime, budget_s=8.0)
-            vals.append(base["value"])
-        v = sorted(vals)[len(vals) // 2]
-        ms = wp["dense_flop_per_head"] * wp["heads"] / (v * 1e12) * 1e3
+        arm = CpuArm(wp, args.regime)
+        for _ in range(args.warmup):
+            arm.head()
+        ts = [arm.head() for _ in range(args.steps)]
+        t_head = sum(ts) / len(ts)
+        base = arm.describe(sorted(ts)[len(ts) // 2], len(ts))
+        v = wp["dense_flop_per_head"] / t_head / 1e12
         line = {"impl": "reference", "metric": "dense-equiv TFLOP/s per rectified sparse-attention call", "value": v,
-                "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": len(vals), "warmup": 0, "ms_per_step": ms,
+                "unit": "TFLOP/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+                "ms_per_step": t_head * 1e3, "step": "one head of the call (1/%d of its work) on the CPU" % wp["heads"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "config": config, "cpu_baseline": dict(base, value=v),
-                "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": v, "unit": "TFLOP/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "c1_full": cpu_c1_full(args.regime)}
         emit(line)
         return
 
@@ -499,7 +649,15 @@ def main():
         if e2e:
             line["e2e"] = e2e
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_sample(wp, args.regime)
+            arm = CpuArm(wp, args.regime)
+            line["cpu_baseline"] = arm.describe(arm.head(), 1)
+            line["cpu_baseline"]["c1_full"] = cpu_c1_full(args.regime)
+        if world == 1 and not args.no_reference_gpu:
+            # the bar to beat: the unmodified reference on this GPU, on the largest HunyuanVideo shape it can run
+            del plan, q, k, v
+            torch.cuda.empty_cache()
+            line["reference_gpu"] = reference_on_gpu("c3a" if args.workload == "c3b" else args.workload, args.regime, dev,
+                                                     lambda fn: timed(fn, max(5, args.steps // 2)))
         emit(line)
     if world > 1:
         dist.destroy_process_group()

@@ -1,4 +1,6 @@
 """ORACLE support (test infrastructure): the small synthetic cases shared by make_golden.py and tests/."""
+import numpy as np
+
 from oracle import rsa_oracle as O
 
 CASES = {
@@ -34,4 +36,35 @@ def case_inputs(name):
     nv = t * h * w
     s = nv + text_len
     q, k, v = O.synth_qkv(heads, s, head_dim, regime, seed)
+    return fam, (t, h, w), nv, s, text_len, ntrue_d, heads, top_k, p, q, k, v
+
+
+# Mid-size cases (one head each): large enough for the selection kernel's wider sorting-network instantiations
+# (rectified-spaattn_b200/csrc/block_select.cu: 256 threads x 1 / 2 / 4 / 8 entries per thread) and for the
+# joint family's text-aggregate insertion when the visual blocks alone fill a power of two (512), small enough that
+# the unmodified reference builds their masks on CPU in seconds (oracle/make_golden.py `mid`).  Only the mask-building
+# stages are pinned at these sizes (probabilities, GAPR bytes, selection, R, C); the attention itself is size-independent
+# and covered by CASES.  top_k = int((1 - sa_drop_rate) * img_blocks) as in the reference scripts.
+#   name: (family, grid(t,h,w), text_len, num_true_delta, heads, top_k, p, regime, seed)
+MID_CASES = {
+    "wan_300": ("wan", (3, 100, 128), 0, 0, 1, O.select_block_num(0.75, 300), 0.3, "walk", 41),            # 300 entries
+    "flux_512": ("flux", (1, 256, 256), 512, 512, 1, O.select_block_num(0.9, 512), 0.3, "walk", 42),       # 512 + aggregate
+    "flux_513": ("flux", (1, 216, 304), 512, 512, 1, O.select_block_num(0.9, 513), 0.3, "cluster", 43),    # 514 entries
+    "hunyuan_600": ("hunyuan", (6, 100, 128), 256, 200, 1, O.select_block_num(0.8, 600), 0.3, "iid", 44),  # threshold > top_k
+    "hunyuan_1100": ("hunyuan", (11, 100, 128), 256, 200, 1, O.select_block_num(0.8, 1100), 0.3, "walk", 45),
+    # every K block is a copy of the first block of its group of four: probabilities come in exact ties of four, and
+    # the cut (top_k = 75 = 18 groups + 3) falls inside a tie group -- the tie-break contract (probability desc, index asc)
+    "wan_ties": ("wan", (3, 100, 128), 0, 0, 1, O.select_block_num(0.75, 300), 0.3, "ties", 46),
+}
+
+
+def mid_case_inputs(name):
+    fam, (t, h, w), text_len, ntrue_d, heads, top_k, p, regime, seed = MID_CASES[name]
+    nv = t * h * w
+    s = nv + text_len
+    q, k, v = O.synth_qkv(heads, s, 128, "walk" if regime == "ties" else regime, seed)
+    if regime == "ties":
+        nb = nv // 128
+        kb = k[:, :, : nb * 128].reshape(k.shape[0], k.shape[1], nb, 128, k.shape[3])
+        kb[:] = kb[:, :, (np.arange(nb) // 4) * 4]
     return fam, (t, h, w), nv, s, text_len, ntrue_d, heads, top_k, p, q, k, v

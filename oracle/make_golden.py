@@ -116,11 +116,17 @@ def _dense_masked_kernel(q, k, v, seqlens, block_mask, sm_scale, bm=128, bn=128)
     return out
 
 
-from oracle.cases import CASES, EXTRA_CASES, case_inputs  # noqa: E402
+from oracle.cases import CASES, EXTRA_CASES, MID_CASES, case_inputs, mid_case_inputs  # noqa: E402
+
+MID_PROB_ROWS = 48   # rows of the probability matrix a mid-size fixture keeps (evenly spaced; the full matrix is MBs)
 
 
 def run_reference_case(name):
-    fam, (t, h, w), nv, s, text_len, ntrue_d, heads, top_k, p, q, k, v = case_inputs(name)
+    """CASES / EXTRA_CASES: everything, including the visual-row output.  MID_CASES (`mid`): the mask-building stages
+    only -- the attention stand-in is not run (it would take minutes at 140 000 tokens and is size-independent), the
+    probabilities are kept for MID_PROB_ROWS rows plus every row's sum."""
+    mid = name in MID_CASES
+    fam, (t, h, w), nv, s, text_len, ntrue_d, heads, top_k, p, q, k, v = (mid_case_inputs if mid else case_inputs)(name)
     modname = {"wan": "rectified_wan21_attn", "hunyuan": "rectified_hunyuan_attn", "flux": "rectified_flux_attn",
                "cogvideo": "rectified_cogvideo_attn"}[fam]
     mods = ref_loader.load([modname, "jenga_gilbert"])
@@ -184,7 +190,7 @@ def run_reference_case(name):
     ones = lambda q_, *a, **kw: torch.ones_like(q_)
     out_c = call(zeros)          # visual rows hold C (block-constant)
     out_rc = call(ones)          # visual rows hold R + C
-    out = call(_dense_masked_kernel)
+    out = out_c if mid else call(_dense_masked_kernel)
     nq = cap["mask"].shape[2]
     rows_vis = min(nq * 128, s)
     hd = q.shape[-1]                                               # 128, or 64 for cog_d64
@@ -198,6 +204,20 @@ def run_reference_case(name):
         out_rows = torch.cat([out_rows[:nv], out_rows[nv + gap:]], dim=0)
         assert out_rows.shape[0] == s_in
     HOLE = None
+    if mid:
+        pr = cap["probs"][0].numpy().astype(np.float32)             # [H, NQ, n_ent]
+        rows = np.unique(np.linspace(0, nq - 1, MID_PROB_ROWS).astype(np.int64))
+        np.savez_compressed(
+            os.path.join(GOLD, f"mask_{name}.npz"),
+            mask=np.packbits(cap["mask"][0].numpy().astype(np.uint8)), mask_shape=np.array(cap["mask"][0].shape),
+            prob_rows=rows, probs=pr[:, rows], prob_sum=pr.sum(axis=2, dtype=np.float64).astype(np.float32),
+            nogapr=np.packbits(cap["nogapr"][0].numpy().astype(np.uint8)),
+            nogapr_shape=np.array(cap["nogapr"][0].shape),
+            R=r.numpy().astype(np.float32), C=c.numpy().astype(np.float32),
+            nbr=np.packbits(nbr.numpy().astype(np.uint8)), nbr_shape=np.array(nbr.shape))
+        print("mid case", name, "NQ", nq, "mask density", float(cap["mask"].float().mean()), "nogapr",
+              float(cap["nogapr"].float().mean()), "R min/mean", float(r.min()), float(r.mean()), flush=True)
+        return
     np.savez_compressed(
         os.path.join(GOLD, f"mask_{name}.npz"),
         mask=np.packbits(cap["mask"][0].numpy().astype(np.uint8)), mask_shape=np.array(cap["mask"][0].shape),
@@ -385,13 +405,17 @@ def make_helpers():
 
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
-    what = sys.argv[1:] or ["gilbert", "masks", "kernel", "prep", "helpers"]
+    what = sys.argv[1:] or ["gilbert", "masks", "mid", "kernel", "prep", "helpers"]
     if "gilbert" in what:
         make_gilbert()
     if "masks" in what:
         every = list(CASES) + list(EXTRA_CASES)
         for n in every:
             if n in what or not any(w in every for w in what):   # `masks <case> ...` regenerates only those
+                run_reference_case(n)
+    if "mid" in what:
+        for n in MID_CASES:
+            if n in what or not any(w in MID_CASES for w in what):
                 run_reference_case(n)
     if "kernel" in what:
         make_kernel_fp16()

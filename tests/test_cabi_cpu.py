@@ -388,7 +388,8 @@ def test_attn_helpers_against_reference_values():
 
 def test_product_never_imports_the_oracle():
     """The oracle is test infrastructure: only tests/, __graft_entry__.smoke() and bench.py's CPU legs may import it.
-    No Python file of the package, and no C/CUDA source, refers to it; bench.py imports it inside cpu_sample only."""
+    No Python file of the package, and no C/CUDA source, refers to it; bench.py imports it inside the CPU arm (class
+    CpuArm) only -- and that arm imports nothing of the product (no rsa_b200, so no librsa_b200.so in its process)."""
     import re
     pkg = os.path.join(REPO, "rectified-spaattn_b200")
     offenders = []
@@ -401,6 +402,7 @@ def test_product_never_imports_the_oracle():
                     offenders.append(os.path.join(root, fn))
     assert not offenders, offenders
     bench_src = open(os.path.join(REPO, "bench.py"), encoding="utf-8").read()
-    body = bench_src.split("def cpu_sample(", 1)[1].split("\ndef ", 1)[0]
+    body = bench_src.split("class CpuArm", 1)[1].split("\ndef cpu_c1_full", 1)[0]
     imports = re.findall(r"^\s*from oracle import .*$", bench_src, re.M)
     assert imports and all(line.strip() in body for line in imports)
+    assert not re.search(r"^\s*(from|import)\s+(rsa_b200|rectified_spaattn|utils)\b", body, re.M)

@@ -102,6 +102,69 @@ def test_mask_builder_head_dim_64_against_reference(gold_dir):
         assert float(st["R"].min()) < 0.9                       # a case in which the rectification matters
 
 
+def _mid_geo(name):
+    fam, (t, h, w), nv, s, text_len, ntrue_d, heads, top_k, p, q, k, v = C.mid_case_inputs(name)
+    return fam, (t, h, w), nv, heads, _geo(fam, nv, s, text_len, ntrue_d, top_k, p, t), q, k, v
+
+
+@pytest.mark.parametrize("name", list(C.MID_CASES))
+def test_mask_builder_mid_sizes_against_reference(name, gold_dir):
+    """300 ... 1101 sortable entries per query block (the selection kernel's 2-, 4- and 8-entries-per-thread sorting
+    networks, the text aggregate inserted beside exactly 512 visual blocks, the cumulative threshold beyond top_k on iid
+    inputs, exact four-way ties across the cut).  `mask_<name>.npz` = the unmodified reference's
+    _build_block_index_with_importance_optimized + R + C on fp32 CPU tensors (oracle/make_golden.py `mid`)."""
+    fam, (t, h, w), nv, heads, geo, q, k, v = _mid_geo(name)
+    g = np.load(os.path.join(gold_dir, f"mask_{name}.npz"))
+    mask_ref = _unpack(g["mask"], g["mask_shape"])
+    nogapr_ref = _unpack(g["nogapr"], g["nogapr_shape"])
+    nbr = _unpack(g["nbr"], g["nbr_shape"])
+    assert np.array_equal(G.gilbert_block_neighbors(t, h, w), nbr)
+    ties = C.MID_CASES[name][7] == "ties"
+    for hi in range(heads):
+        st, _, _, _ = O.mask_stages(q[0, hi], k[0, hi], v[0, hi], geo, nbr)
+        assert st["mask"].shape == mask_ref[hi].shape
+        np.testing.assert_allclose(st["probs"][g["prob_rows"]], g["probs"][hi], rtol=2e-5, atol=1e-7)
+        np.testing.assert_allclose(st["probs"].sum(1, dtype=np.float64), g["prob_sum"][hi], atol=2e-6)
+        assert np.array_equal(st["nogapr"], nogapr_ref[hi]), f"{name} head {hi}: nogapr differs"
+        if not ties:
+            assert np.array_equal(st["mask"], mask_ref[hi]), f"{name} head {hi}: mask differs"
+            np.testing.assert_allclose(st["R"], g["R"][hi], rtol=0, atol=2e-6)
+            np.testing.assert_allclose(st["C"], g["C"][hi], rtol=1e-4, atol=2e-6)
+        else:
+            # torch.sort without stable=True (wan21 :220) leaves the order inside a tie group open, so the reference may
+            # keep other members of the group the cut falls into: same count per row, same selected probabilities --
+            # and this oracle keeps the LOWEST indices of that group (the documented tie-break)
+            p = st["probs"]
+            forced = np.zeros_like(st["mask"])
+            forced[:, : nbr.shape[1]] |= nbr[: forced.shape[0]]
+            forced[: geo.first_frame_blocks, : geo.first_frame_blocks] = True
+            order = np.argsort(-p, axis=1, kind="stable")
+            for i in range(p.shape[0]):
+                n = st["n_needed"][i]
+                cut = p[i, order[i, n - 1]]
+                above, grp = p[i] > cut, np.nonzero(p[i] == cut)[0]
+                need = n - int(above.sum())
+                ref_row = mask_ref[hi][i]
+                assert ref_row[above].all(), (name, i)                                # everything above the cut is kept
+                assert not (ref_row & (p[i] < cut) & ~forced[i]).any(), (name, i)     # nothing below it, unions aside
+                took = int(ref_row[grp].sum())
+                assert need <= took <= need + int(forced[i, grp].sum()), (name, i)    # `need` members of the tie group
+                mine = st["mask"][i] & ~forced[i]
+                kept = grp[mine[grp] | forced[i, grp]]
+                # this oracle's ranking keeps the LOWEST indices of the group (the documented tie-break)
+                pure = np.zeros(p.shape[1], dtype=bool)
+                pure[order[i, :n]] = True
+                assert np.array_equal(grp[pure[grp]], grp[:need]), (name, i)
+                assert np.array_equal(st["mask"][i], pure | forced[i]), (name, i)
+            assert (p[:, 0] == p[:, 1]).all() and (st["n_needed"] % 4 != 0).any()   # ties exist and a cut splits one
+            # R sums `part = mask | nogapr`: another member of the tie group may or may not be a GAPR entry already, so R
+            # can differ from the reference's by the group's probabilities
+            cutv = np.take_along_axis(p, order, 1)[np.arange(p.shape[0]), st["n_needed"] - 1]
+            assert np.all(np.abs(st["R"] - g["R"][hi]) <= 4 * cutv + 2e-6)
+        assert np.all(st["mask"].sum(1) >= min(geo.top_k, st["probs"].shape[1]))
+        assert np.all(st["R"] > 0) and np.all(st["R"] <= 1 + 1e-6)
+
+
 def test_triton_kernel_semantics_fp16(gold_dir):
     """The literal reference kernel (TRITON_INTERPRET, fp16) vs the oracle's dense masked restatement."""
     import torch

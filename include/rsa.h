@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RSA_VERSION 102
+#define RSA_VERSION 103
 #define RSA_BLOCK 128
 #define RSA_HEAD_DIM 128
 #define RSA_MAX_ENTRIES 2048 /* max sortable entries per query block: NQ (+1 for the text aggregate) */
@@ -147,6 +147,12 @@ typedef struct rsa_ws_view {
                          /* first the blocks both keep (ascending; K/V tiles loaded once for both), then the rest       */
   int32_t* pair_shared;  /* [BH, ceil(NQT/2)] length of that common prefix                                              */
 } rsa_ws_view;
+
+/* sizeof(rsa_attn_desc) / sizeof(rsa_prep_desc) / sizeof(rsa_peer_route) as THIS library was compiled: a binding written in
+ * another language checks its own struct against these before the first call. */
+size_t rsa_attn_desc_size(void);
+size_t rsa_prep_desc_size(void);
+size_t rsa_peer_route_size(void);
 
 size_t rsa_attn_workspace_bytes(const rsa_attn_desc* d);
 int rsa_attn_workspace_view(const rsa_attn_desc* d, void* workspace, size_t workspace_bytes, rsa_ws_view* out);

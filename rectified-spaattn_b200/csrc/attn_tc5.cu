@@ -523,8 +523,35 @@ EncodeTiledFn encode_fn() {
 // [batch, heads, rows, 128] bf16 view with element strides st = (batch, head, row) -> 4-D tensor map whose box is
 // one granule: 64 head_dim elements x 128 rows, 128-byte swizzle; rows past the end read as zeros (the
 // reference zero-pads to a multiple of 128, rectified_wan21_attn.py:299-302).
+// cuTensorMapEncodeTiled costs ~10 us on the host and a launch needs up to six maps: at C1 sizes that was most of the
+// call.  A tensor map is a pure function of (base, shape, strides, dtype), so the encoded maps are kept in a small
+// per-thread table keyed by exactly those values ("a TMA-descriptor cache keyed by (ptr, shape)"); a layer
+// that calls with the same tensors or the same allocator addresses every step never encodes again.
+struct MapKey {
+  const void* base;
+  int batch, heads, rows, head_dim, f16;
+  int64_t st[3];
+  bool operator==(const MapKey& o) const {
+    return base == o.base && batch == o.batch && heads == o.heads && rows == o.rows && head_dim == o.head_dim &&
+           f16 == o.f16 && st[0] == o.st[0] && st[1] == o.st[1] && st[2] == o.st[2];
+  }
+};
+constexpr int kMapCacheSize = 32;
+struct MapCache {
+  MapKey key[kMapCacheSize];
+  CUtensorMap map[kMapCacheSize];
+  int used = 0, next = 0;
+};
+
 int make_map(CUtensorMap* m, const __nv_bfloat16* base, int batch, int heads, int rows, const int64_t* st, bool f16,
              int head_dim) {
+  static thread_local MapCache cache;
+  const MapKey key{base, batch, heads, rows, head_dim, f16 ? 1 : 0, {st[0], st[1], st[2]}};
+  for (int i = 0; i < cache.used; ++i)
+    if (cache.key[i] == key) {
+      *m = cache.map[i];
+      return RSA_OK;
+    }
   EncodeTiledFn fn = encode_fn();
   if (!fn) RSA_FAIL(RSA_ERR_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   if ((uintptr_t)base % 16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "q/k/v must be 16-byte aligned");
@@ -542,6 +569,9 @@ int make_map(CUtensorMap* m, const __nv_bfloat16* base, int batch, int heads, in
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) RSA_FAIL(RSA_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  const int slot = cache.used < kMapCacheSize ? cache.used++ : (cache.next++ % kMapCacheSize);
+  cache.key[slot] = key;
+  cache.map[slot] = *m;
   return RSA_OK;
 }
 

@@ -68,7 +68,9 @@ int validate_desc(const rsa_attn_desc* d) {
   }
   const int n_ent = d->nq_blocks + (d->family == RSA_FAMILY_JOINT ? 1 : 0);
   if (n_ent > RSA_MAX_ENTRIES) RSA_FAIL(RSA_ERR_UNSUPPORTED, "more than %d sortable blocks per row", RSA_MAX_ENTRIES);
-  if (nb > 65535) RSA_FAIL(RSA_ERR_UNSUPPORTED, "more than 65535 KV blocks");
+  // kernel 3b keeps a row's kept-block bitmask in shared memory: RSA_MAX_ENTRIES / 32 + 1 words (block_select.cu)
+  if ((nb + 31) / 32 > RSA_MAX_ENTRIES / 32 + 1)
+    RSA_FAIL(RSA_ERR_UNSUPPORTED, "more than %d KV blocks (visual + text)", (RSA_MAX_ENTRIES / 32 + 1) * 32);
   if (d->kv_len < 1 || d->kv_len > seq_v) RSA_FAIL(RSA_ERR_ARG, "kv_len=%d out of [1, %d]", d->kv_len, seq_v);
   if (d->kv_zero_from < 0) RSA_FAIL(RSA_ERR_ARG, "kv_zero_from < 0");
   if (d->text_end_block < d->nq_blocks || d->text_end_block > nb) RSA_FAIL(RSA_ERR_ARG, "text_end_block out of range");
@@ -325,6 +327,9 @@ using namespace rsa;
 
 extern "C" const char* rsa_last_error_string(void) { return g_err; }
 extern "C" int rsa_version(void) { return RSA_VERSION; }
+extern "C" size_t rsa_attn_desc_size(void) { return sizeof(rsa_attn_desc); }
+extern "C" size_t rsa_prep_desc_size(void) { return sizeof(rsa_prep_desc); }
+extern "C" size_t rsa_peer_route_size(void) { return sizeof(rsa_peer_route); }
 
 extern "C" int rsa_device_ok(void) {
   int dev = 0;

@@ -111,10 +111,14 @@ def wan_rope_tables(emb, n):
     """fp32 (cos, sin) [n, 128] tables from either Wan rotary form: Wan2.1's complex `freqs` [1, 1, S, 64]
     (rectified_wan21_attn.py:433-438) or Wan2.2's (freqs_cos, freqs_sin) [1, S, 1, 128] (rectified_wan22_attn.py:52-64,
     which reads cos[..., 0::2] and sin[..., 1::2]).  Cached per tensor: the tables are constants of a generation."""
-    key = tuple((t.data_ptr(), tuple(t.shape), t._version) for t in (emb if isinstance(emb, (tuple, list)) else (emb,)))
+    src = tuple(emb) if isinstance(emb, (tuple, list)) else (emb,)
+    key = tuple((t.data_ptr(), tuple(t.shape), t._version) for t in src) + (n,)
     hit = _wan_rope_cache.get(key)
-    if hit is not None:
-        return hit
+    # the entry keeps the source tensors alive and is honoured only for the SAME tensor objects: diffusers rebuilds
+    # rotary_emb on every transformer forward and the caching allocator hands the same address back, so another latent
+    # grid with the same token count would otherwise hit a stale table (ADVICE r1)
+    if hit is not None and len(hit[0]) == len(src) and all(a is b for a, b in zip(hit[0], src)):
+        return hit[1]
     if isinstance(emb, torch.Tensor) and emb.is_complex() and emb.shape[-1] == 64 and emb.shape[-2] >= n:
         f = emb.reshape(-1, 64)[-emb.shape[-2]:][:n]
         cos, sin = f.real.float().repeat_interleave(2, dim=1), f.imag.float().repeat_interleave(2, dim=1)
@@ -125,8 +129,8 @@ def wan_rope_tables(emb, n):
         return None
     if len(_wan_rope_cache) > 8:
         _wan_rope_cache.clear()
-    _wan_rope_cache[key] = (cos.contiguous(), sin.contiguous())
-    return _wan_rope_cache[key]
+    _wan_rope_cache[key] = (src, (cos.contiguous(), sin.contiguous()))
+    return _wan_rope_cache[key][1]
 
 
 def head_norm_params(mod):

@@ -24,12 +24,20 @@ def _triton_block_sparse_attention_onehot(q, k, v, seqlens, block_mask, sm_scale
     """q,k,v [B,H,S,D] bf16; seqlens [B] valid KV length; block_mask [B,H,NQ,NB] bool -> [B,H,S,D].
     (name kept from the reference; the kernel is tcgen05/TMEM/TMA CUDA, not Triton)"""
     assert q.shape[-1] == k.shape[-1] == v.shape[-1]
-    assert k.shape[-1] in {128}, "only head_dim 128 is built"
+    # the reference asserts Lk in {16, 32, 64, 128} (:121); 128 (every BASELINE model) and 64 (CogVideoX) are built
+    assert k.shape[-1] in {64, 128}, "head_dim must be 128 or 64"
     _common.check_blocks(block_size_M, block_size_N)
     lens = _common.host_ints(seqlens)
-    if len(set(lens)) != 1:
-        raise NotImplementedError("per-batch KV lengths differ")
-    return _ops.masked_attention(q, k, v, block_mask, lens[0], sm_scale)
+    if len(lens) not in (1, q.shape[0]):
+        raise ValueError("seqlens must hold one valid KV length per batch element")
+    if len(set(lens)) == 1:
+        return _ops.masked_attention(q, k, v, block_mask, lens[0], sm_scale)
+    # the reference kernel loads seqlens[off_hz // H] per batch element (:36-37, :86): one launch per element, each
+    # writing its slice of the result
+    out = torch.empty_like(q)
+    for b, n in enumerate(lens):
+        _ops.masked_attention(q[b:b + 1], k[b:b + 1], v[b:b + 1], block_mask[b:b + 1], n, sm_scale, out=out[b:b + 1])
+    return out
 
 
 def _build_block_index_with_importance_optimized(query, key, top_k, block_size_M=128, block_size_N=128,

@@ -65,12 +65,13 @@ EXPORTS = [
     "rsa_peer_free", "rsa_peer_export", "rsa_peer_open", "rsa_peer_close", "rsa_qkv_prep_gather",
     "rsa_rectified_attention_pooled_scatter", "rsa_rectified_attention_reuse",
     "rsa_debug_attention_grid_slot", "rsa_debug_front_text_heads", "rsa_gilbert_xyz2d_r",
+    "rsa_attn_desc_size", "rsa_prep_desc_size", "rsa_peer_route_size",
 ]
 
 _lib = None
 
 
-ABI_VERSION = 102
+ABI_VERSION = 103
 
 
 def lib():
@@ -89,6 +90,11 @@ def lib():
         raise RsaError(f"{LIB_PATH} has ABI version {L.rsa_version()}, this package expects {ABI_VERSION}: rebuild it "
                        "with `python rectified-spaattn_b200/build_native.py`")
     L.rsa_device_ok.restype = i32
+    for n in ("rsa_attn_desc_size", "rsa_prep_desc_size", "rsa_peer_route_size"):
+        getattr(L, n).restype = sz
+    if (L.rsa_attn_desc_size(), L.rsa_prep_desc_size(), L.rsa_peer_route_size()) != (
+            C.sizeof(AttnDesc), C.sizeof(PrepDesc), C.sizeof(PeerRoute)):
+        raise RsaError("ctypes structures of rsa_b200/native.py do not match the library's include/rsa.h")
     L.rsa_gilbert_map.argtypes = [i32, i32, i32, C.c_char_p, p, p]
     L.rsa_gilbert_block_neighbors.argtypes = [i32, i32, i32, i32, C.c_char_p, p]
     L.rsa_gilbert_xyz2d_r.argtypes = [i64] * 16

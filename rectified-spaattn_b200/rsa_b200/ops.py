@@ -483,9 +483,10 @@ def rectified_attention(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfuse=Fal
     return out if shape_xfuse else out.view(b, s, h * d)
 
 
-def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None):
+def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None, out=None):
     """Kernel 4 alone on a dense block mask: the surface of _triton_block_sparse_attention_onehot
-    (rectified_wan21_attn.py:108-117).  q,k,v [B,H,S,D] bf16, block_mask bool [B,H,NQ,NB] -> [B,H,S,D]."""
+    (rectified_wan21_attn.py:108-117).  q,k,v [B,H,S,D] bf16 (any batch / head / token strides with D contiguous -- the
+    ABI takes strides, nothing is copied), block_mask bool [B,H,NQ,NB] -> [B,H,S,D]."""
     _need_cuda(q, "q")
     if q.dtype not in (torch.bfloat16, torch.float16) or k.dtype != q.dtype or v.dtype != q.dtype:
         raise RuntimeError("q, k, v must all be bfloat16 or all float16")
@@ -494,24 +495,41 @@ def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None):
     b, h, s, d = q.shape
     if d not in (64, 128):
         raise AssertionError("head_dim must be 128 or 64")
-    q3, k3, v3 = (t.reshape(b * h, t.shape[2], d).contiguous() for t in (q, k, v))
-    skv = k3.shape[1]
+    skv = k.shape[2]
     nqb, nkb = (s + 127) // 128, (skv + 127) // 128
     if tuple(block_mask.shape[-2:]) != (nqb, nkb):
         raise ValueError("block_mask shape does not match the sequence lengths")
     m = block_mask.reshape(b * h, nqb, nkb).to(device=q.device, dtype=torch.bool).contiguous().view(torch.uint8)
-    o = torch.zeros_like(q3)
+    if out is None:
+        out = torch.zeros_like(q, memory_format=torch.contiguous_format)
+    elif out.shape != q.shape or out.dtype != q.dtype or out.stride(3) != 1:
+        raise RuntimeError("out must have the shape and dtype of q with a contiguous head_dim")
     L = N.lib()
+
+    def flat(t):
+        """[B,H,S,D] view -> (tensor, (bh stride, token stride)) for a [B*H, S, D] addressing; copies only when batch and
+        head do not collapse into one stride and the strides are not multiples of 8."""
+        if t.stride(3) != 1 or any(x % 8 for x in t.stride()[:3]):
+            t = t.contiguous()
+        if t.shape[0] == 1 or t.stride(0) == t.shape[1] * t.stride(1):
+            return t, (t.stride(1), t.stride(2))
+        t = t.contiguous()
+        return t, (t.stride(1), t.stride(2))
+
+    (q3, qs), (k3, ks), (v3, vs) = flat(q), flat(k), flat(v)
+    o3, os_ = flat(out)
+    if o3.data_ptr() != out.data_ptr():
+        raise RuntimeError("out must be addressable as [B*H, S, D] with strides that are multiples of 8")
     nbytes = L.rsa_masked_attention_workspace_bytes(b * h, nqb, nkb)
     ws = torch.empty(nbytes, dtype=torch.uint8, device=q.device)
-    mk = lambda t: (C.c_int64 * 2)(t.stride(0), t.stride(1))
+    mk = lambda st: (C.c_int64 * 2)(*st)
     with torch.cuda.device(q.device):
-        N.check(L.rsa_masked_attention(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o.data_ptr(), b * h, s, skv,
-                                       int(kv_len), mk(q3), mk(k3), mk(v3), mk(o), m.data_ptr(), nqb, nkb,
+        N.check(L.rsa_masked_attention(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o3.data_ptr(), b * h, s, skv,
+                                       int(kv_len), mk(qs), mk(ks), mk(vs), mk(os_), m.data_ptr(), nqb, nkb,
                                        ws.data_ptr(), nbytes, _stream(q.device),
                                        N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16, d),
                 "rsa_masked_attention")
-    return o.view(b, h, s, d)
+    return out
 
 
 def set_attention_flags(flags):

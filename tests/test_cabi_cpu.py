@@ -26,7 +26,7 @@ def test_library_exports_every_declared_symbol():
     for name in sorted(declared):
         assert hasattr(lib, name), f"{name} declared in rsa.h but not exported"
     assert declared == set(N.EXPORTS)
-    assert lib.rsa_version() == 102
+    assert lib.rsa_version() == N.ABI_VERSION == int(re.search(r"#define RSA_VERSION (\d+)", hdr).group(1))
 
 
 def test_struct_layout_matches_header():
@@ -41,6 +41,41 @@ def test_struct_layout_matches_header():
         subprocess.check_call(["gcc", "-I", os.path.join(REPO, "include"), p, "-o", exe])
         a, b = map(int, subprocess.check_output([exe]).split())
     assert a == C.sizeof(N.AttnDesc) and b == C.sizeof(N.WsView)
+
+
+def test_integration_md_stub_matches_the_library():
+    """INTEGRATION.md section 2 shows the ctypes struct a maintainer of the reference would write.  A stale copy (a
+    field missing at the end) makes the library read past the caller's buffer: the documented class is extracted from
+    the document, executed, and held to the library's own sizeof and to every field offset of rsa_b200/native.py."""
+    import re
+    doc = open(os.path.join(REPO, "INTEGRATION.md"), encoding="utf-8").read()
+    m = re.search(r"^class _Desc\(C\.Structure\):.*?\n(?=\n)", doc, re.S | re.M)
+    assert m, "INTEGRATION.md no longer shows class _Desc"
+    ns = {"C": C}
+    exec(m.group(0), ns)
+    doc_desc = ns["_Desc"]
+    L = N.lib()
+    assert C.sizeof(doc_desc) == L.rsa_attn_desc_size() == C.sizeof(N.AttnDesc)
+    assert [(n, getattr(doc_desc, n).offset, getattr(doc_desc, n).size) for n, _ in doc_desc._fields_] == \
+           [(n, getattr(N.AttnDesc, n).offset, getattr(N.AttnDesc, n).size) for n, _ in N.AttnDesc._fields_]
+    assert "rsa_attn_desc_size() == C.sizeof(_Desc)" in doc          # and the stub checks itself at import
+    assert L.rsa_prep_desc_size() == C.sizeof(N.PrepDesc) and L.rsa_peer_route_size() == C.sizeof(N.PeerRoute)
+
+
+def test_too_many_kv_blocks_is_refused():
+    """Kernel 3b keeps a row's kept-block bitmask in RSA_MAX_ENTRIES/32 + 1 shared-memory words: a JOINT descriptor whose
+    visual blocks pass the entry bound but whose text blocks push n_blocks beyond it must fail validation."""
+    from rsa_b200 import geometry as G
+    d = N.AttnDesc()
+    nq, text = 2000, 200 * 128
+    s = nq * 128 + text
+    geo = G.BlockGeometry(1, s, nq + 200, nq, 128, s, s, nq + 200, text)
+    ops._fill_desc(d, (1, 1, s, 128), [(s * 128, s * 128, 128)] * 4, geo, 10, 0.3, None)
+    assert N.lib().rsa_attn_workspace_bytes(C.byref(d)) == 0
+    assert b"KV blocks" in N.lib().rsa_last_error_string()
+    geo_ok = G.BlockGeometry(1, nq * 128 + 1024, nq + 8, nq, 128, nq * 128 + 1024, nq * 128 + 1024, nq + 8, 1024)
+    ops._fill_desc(d, (1, 1, geo_ok.seq, 128), [(geo_ok.seq * 128, geo_ok.seq * 128, 128)] * 4, geo_ok, 10, 0.3, None)
+    assert N.lib().rsa_attn_workspace_bytes(C.byref(d)) > 0
 
 
 @pytest.fixture(scope="module")

@@ -824,3 +824,25 @@ def test_head_dim_64(dev):
     assert torch.equal(hout.view(torch.int16), out.cpu().view(torch.int16))
     with pytest.raises(RuntimeError):                     # kernel 0 is built for 128 columns
         plan.qkv_prep(*(torch.zeros(1, s, heads * 64, dtype=torch.bfloat16, device=dev) for _ in range(3)))
+
+
+def test_triton_mirror_per_batch_kv_len_and_head_dim_64(dev):
+    """_triton_block_sparse_attention_onehot(q, k, v, seqlens, block_mask, sm_scale): the reference kernel loads
+    seqlens[off_hz // H] per batch element (rectified_wan21_attn.py:36-37, :86) and takes head_dim 64 (:121) -- the
+    mirror does both, on strided [B, H, S, D] views without copies."""
+    from rectified_spaattn.rectified_cogvideo_attn import _triton_block_sparse_attention_onehot as cog_kernel
+    from rectified_spaattn.rectified_wan21_attn import _triton_block_sparse_attention_onehot as kernel
+    g = torch.Generator().manual_seed(17)
+    for d, fn in ((128, kernel), (64, cog_kernel)):
+        b, h, s = 2, 2, 512
+        # [B, S, H, D] storage viewed as [B, H, S, D]: token stride H*D, head stride D (what a processor holds)
+        q, k, v = (torch.randn(b, s, h, d, generator=g).to(torch.bfloat16).to(dev).transpose(1, 2) for _ in range(3))
+        mask = torch.rand(b, h, 4, 4, generator=g) < 0.5
+        mask |= torch.eye(4, dtype=torch.bool)
+        lens = torch.tensor([512, 300], dtype=torch.int32, device=dev)
+        out = fn(q, k, v, lens, mask.to(dev), d ** -0.5, 128, 128).float().cpu().numpy()
+        for bi in range(b):
+            for hi in range(h):
+                ref = O.masked_attention(q[bi, hi].float().cpu().numpy(), k[bi, hi].float().cpu().numpy(),
+                                         v[bi, hi].float().cpu().numpy(), mask[bi, hi].numpy(), int(lens[bi]), s)
+                assert np.abs(out[bi, hi] - ref).max() <= ATOL_OUT and cos_sim(out[bi, hi], ref) >= COS_OUT

@@ -306,3 +306,22 @@ def test_cogvideox_processor_with_64_dim_heads():
     _close(e, ed)
     _close(h, o[:, :nv])
     _close(e, o[:, nv:])
+
+
+def test_wan_rope_cache_is_keyed_by_tensor_identity():
+    """diffusers rebuilds rotary_emb on every forward and the allocator re-uses addresses, so (pointer, shape,
+    version) alone can name two different tables.  A hit needs the SAME tensor object; anything else is recomputed."""
+    import torch
+    from rectified_spaattn import _processors as P
+    n = 16
+    ang = torch.rand(1, 1, n, 64)
+    emb = torch.polar(torch.ones_like(ang), ang)
+    cos1, sin1 = P.wan_rope_tables(emb, n)
+    assert P.wan_rope_tables(emb, n)[0] is cos1                      # same object: cached
+    other = torch.polar(torch.ones_like(ang), ang + 0.5)
+    emb.data.copy_(other)                                            # same pointer, shape AND version, new contents
+    alias = emb.view(emb.shape)                                      # ... seen through another tensor object
+    assert alias.data_ptr() == emb.data_ptr() and alias._version == emb._version
+    cos2, _ = P.wan_rope_tables(alias, n)
+    assert cos2 is not cos1
+    assert torch.allclose(cos2[:, 0::2], other.real.reshape(n, 64).float())

@@ -297,11 +297,12 @@ def load_reference_from_baseline(names):
             stub(n)
         stub("diffusers.models.attention_processor", Attention=object, AttentionProcessor=object)
         stub("diffusers.models.transformers.transformer_wan", _get_qkv_projections=None, _get_added_kv_projections=None)
-    if "ref_rectified_spaattn" not in sys.modules:
-        pkg = types.ModuleType("ref_rectified_spaattn")
+    # its own alias: the CPU arm (oracle/ref_cpu.py) patches the two CUDA-only functions of ITS copy of these modules
+    if "refgpu_rectified_spaattn" not in sys.modules:
+        pkg = types.ModuleType("refgpu_rectified_spaattn")
         pkg.__path__ = [os.path.join(root, "rectified_spaattn")]
-        sys.modules["ref_rectified_spaattn"] = pkg
-    return {n: importlib.import_module("ref_rectified_spaattn." + n) for n in names}
+        sys.modules["refgpu_rectified_spaattn"] = pkg
+    return {n: importlib.import_module("refgpu_rectified_spaattn." + n) for n in names}
 
 
 def reference_on_gpu(name, regime, dev, ours_ms_fn):

@@ -310,6 +310,13 @@ int rsa_rectified_attention_pooled_scatter(const rsa_attn_desc* d, const void* q
                                            const rsa_peer_route* route, void* workspace, size_t workspace_bytes,
                                            void* stream);
 
+/* The reference's Triton kernel rounds the pre-scaled query to the input dtype before Q.K^T (q = (q * sm_scale *
+ * 1.44269504).to(dtype), rectified_wan21_attn.py:61-62); flash-attn, which the reference calls for text rows and for its
+ * dense "flash" mode (attn.py:107-120), scales the fp32 scores instead.  Kernel 4 does the former on visual query tiles
+ * and the latter on text tiles.  OR-ed into the `dtype` argument of rsa_masked_attention, this flag selects flash-attn's
+ * arithmetic for the whole call (the dense mode of the mirror's fullattn). */
+#define RSA_ATTN_FP32_SCALE 256
+
 /* Kernel 4 alone on a caller-supplied dense block mask (bytes, [BH, n_q_blocks, n_kv_blocks]) -- the literal
  * surface of _triton_block_sparse_attention_onehot(q, k, v, seqlens, block_mask, sm_scale) (wan21 :108-117).
  * q/k/v/out are [BH, seq, head_dim] with the given token strides; R = 1, C = 0.  workspace must hold

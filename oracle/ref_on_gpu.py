@@ -100,14 +100,29 @@ def golden_c3a():
         return r
 
     ref._build_block_index_with_importance_optimized = spy
-    out = call_ref(ref, "hunyuan", q, k.clone(), v.clone(), nbr, wp["top_k"], bench.P_REMAIN, wp["s"], wp["num_true"],
-                   wp["text"], None)
+    run = lambda: call_ref(ref, "hunyuan", q, k.clone(), v.clone(), nbr, wp["top_k"], bench.P_REMAIN, wp["s"],
+                           wp["num_true"], wp["text"], None)
+    out = run()
     ref._build_block_index_with_importance_optimized = orig
+    # the reference's own R and C (bf16 arithmetic, hunyuan :348-357): with its kernel replaced by a constant the visual
+    # rows of the result are C (kernel = 0) and R + C (kernel = 1), both constant per 128-row block
+    kernel = ref._triton_block_sparse_attention_onehot
+    ref._triton_block_sparse_attention_onehot = lambda q_, *a, **kw: torch.zeros_like(q_)
+    out_c = run()
+    ref._triton_block_sparse_attention_onehot = lambda q_, *a, **kw: torch.ones_like(q_)
+    out_rc = run()
+    ref._triton_block_sparse_attention_onehot = kernel
     torch.cuda.synchronize()
+    nq = wp["nv"] // 128
+    first = torch.arange(0, nq * 128, 128, device=dev)
+    c_ref = out_c[0].view(wp["s"], len(C3A_HEADS), 128)[first]                       # [NQ, H, 128] bf16
+    r_ref = (out_rc[0].view(wp["s"], len(C3A_HEADS), 128)[first].float() - c_ref.float()).mean(dim=-1)   # [NQ, H]
     o = out[0].view(wp["s"], len(C3A_HEADS), 128)
     rows = (torch.arange(0, wp["s"], 128, device=dev)[:, None] + torch.tensor(C3A_ROWS, device=dev)[None]).flatten()
     np.savez_compressed(os.path.join(OUT, "golden_gpu_c3a.npz"), rows=rows.cpu().numpy(),
                         out=o[rows].float().cpu().numpy().astype(np.float16),
+                        R=r_ref.cpu().numpy().astype(np.float32),
+                        C_bf16=c_ref.contiguous().view(torch.int16).cpu().numpy(),
                         mask=np.packbits(cap["mask"][0].cpu().numpy().astype(np.uint8)),
                         mask_shape=np.array(cap["mask"][0].shape), heads=np.array(C3A_HEADS))
     print("golden c3a", tuple(out.shape), tuple(cap["mask"].shape), float(cap["mask"].float().mean()), flush=True)

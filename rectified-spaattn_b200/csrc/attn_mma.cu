@@ -81,6 +81,8 @@ __global__ void __launch_bounds__(kThreads, 1) attn_mma_kernel(const AttnArgs a)
   const int cnt = min(max(a.kept_cnt[lrow], 0), a.nb);
   const uint16_t* list = a.kept_idx + lrow * a.nb;
   const int row0 = tile * 128;
+  const bool prescale = a.q_round != 0 && tile < a.nq_vis;  // as attn_tc5.cu: q~ rounding on visual tiles only
+  const float sc = prescale ? 1.f : a.scale_log2;
 
   const uint32_t sQ = smem_u32(smem);
   const uint32_t sK0 = sQ + kTileBytes, sV0 = sQ + 2 * kTileBytes;
@@ -117,6 +119,13 @@ __global__ void __launch_bounds__(kThreads, 1) attn_mma_kernel(const AttnArgs a)
       for (int ks = 0; ks < 8; ++ks) {
         const int r = warp * 16 + (lane & 15);
         ldsm4(sQ + tile_off(r, 2 * ks + (lane >> 4)), qf[ks][0], qf[ks][1], qf[ks][2], qf[ks][3]);
+        // q~ = bf16(q * sm_scale * log2 e): the reference kernel's rounding of the pre-scaled query (wan21 :61-62)
+        if (prescale) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            qf[ks][j] = pack_bf16(__uint_as_float(qf[ks][j] << 16) * a.scale_log2,
+                                  __uint_as_float(qf[ks][j] & 0xffff0000u) * a.scale_log2);
+        }
       }
     }
     const uint32_t sK = sK0 + st * 2 * kTileBytes, sV = sV0 + st * 2 * kTileBytes;
@@ -143,10 +152,10 @@ __global__ void __launch_bounds__(kThreads, 1) attn_mma_kernel(const AttnArgs a)
 #pragma unroll
     for (int n = 0; n < 16; ++n) {
       const int c = n * 8 + 2 * t4;
-      s[n][0] = (c < lim) ? s[n][0] * a.scale_log2 : -INFINITY;
-      s[n][1] = (c + 1 < lim) ? s[n][1] * a.scale_log2 : -INFINITY;
-      s[n][2] = (c < lim) ? s[n][2] * a.scale_log2 : -INFINITY;
-      s[n][3] = (c + 1 < lim) ? s[n][3] * a.scale_log2 : -INFINITY;
+      s[n][0] = (c < lim) ? s[n][0] * sc : -INFINITY;
+      s[n][1] = (c + 1 < lim) ? s[n][1] * sc : -INFINITY;
+      s[n][2] = (c < lim) ? s[n][2] * sc : -INFINITY;
+      s[n][3] = (c + 1 < lim) ? s[n][3] * sc : -INFINITY;
     }
     float mx0 = m0, mx1 = m1;
 #pragma unroll

@@ -15,7 +15,10 @@
 //     warp 0 (TMA)      K_j, V_j tiles -> 16 KB shared-memory granules (128 rows x 64 bf16, 128-byte swizzle),
 //                       (two per tile = one ring stage; 5 stages shared by both slots, filled in the order the
 //                       MMA warp consumes them)
-//     warp 1 (MMA)      S = Q K_j^T            8 x tcgen05.mma 128x128x16, A and B from shared memory
+//     warps 4-7 / 8-11  once per tile: q~ = dtype(q * head_dim^-1/2 * log2 e) in place in shared memory -- the
+//                       reference kernel rounds the pre-scaled query to the input dtype (wan21 :61-62), and at
+//                       HunyuanVideo sizes that rounding is most of what separates two correct kernels
+//     warp 1 (MMA)      S = q~ K_j^T           8 x tcgen05.mma 128x128x16, A and B from shared memory
 //     warps 4-7 / 8-11  S (TMEM) -> registers, running max with lazy rescale of O, p = exp2(s*c - m), row sums,
 //                       P (bf16) -> TMEM over the S columns, handed over in two halves of 64 keys
 //     warp 1 (MMA)      O += P V_j             8 x tcgen05.mma 128x128x16, A = P from TMEM, B = V_j (MN-major)
@@ -51,9 +54,10 @@ enum {
   B_SFULL = 2,   // [2]  MMA -> softmax: S = Q K^T complete
   B_PHALF = 4,   // [2][2]  softmax -> MMA: P columns of key half 0 / 1 written (and O rescaled)
   B_OFULL = 8,   // [2]  MMA -> softmax: last P V complete
-  B_KVFULL = 10,
-  B_KVEMPTY = 10 + kStages,
-  B_COUNT = 10 + 2 * kStages
+  B_QSCALED = 10,  // [2]  softmax -> MMA: Q tile of the slot pre-scaled and rounded in place (q~)
+  B_KVFULL = 12,
+  B_KVEMPTY = 12 + kStages,
+  B_COUNT = 12 + 2 * kStages
 };
 static_assert(B_COUNT * 8 + 4 <= 256, "barrier region");
 static_assert(kSmemBytes <= 232448, "shared memory per CTA");
@@ -150,6 +154,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       mbar_init(bar(B_PHALF + 2 * s), 128);
       mbar_init(bar(B_PHALF + 2 * s + 1), 128);
       mbar_init(bar(B_OFULL + s), 1);
+      mbar_init(bar(B_QSCALED + s), 128);
     }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar(B_KVFULL + i), 1);
@@ -280,7 +285,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool release = !(s == 0 && r < nsh);
             const uint64_t kd = smem_desc_sw128(sbase + kOffRing + st * 2 * kGranule);
             const uint64_t qd = smem_desc_sw128(sbase + kOffQ + 2 * s * kGranule);
-            if (r == 0) mbar_wait(bar(B_QFULL + s), 0);
+            if (r == 0) mbar_wait(bar(B_QSCALED + s), 0);
             RSA_TRACE(dbg && s == 0 && leader, r, 14);
             mbar_wait(bar(B_KVFULL + st), par);
             tc_fence_after();
@@ -312,12 +317,34 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     const int64_t lrow = lrow0 + s;
     const uint32_t tS = tmem + 128 * s + ((uint32_t)(quarter * 32) << 16);
     const uint32_t tO = tS + 256;
-    const float scale = a.scale_log2;
-    const float2 scale2 = make_float2(scale, scale);
     float m_ref = -INFINITY, l = 0.f;
     const bool tr = dbg && s == 0 && row == 0;
+    // Visual tiles follow the reference's Triton kernel, which rounds the pre-scaled query to the input dtype
+    // (q~ = dtype(q * sm_scale * log2 e), wan21 :61-62) so that S leaves the tensor core in the log2 domain; text tiles
+    // follow its flash-attn call (hunyuan :371-380), which scales S in fp32 instead.
+    const bool prescale = a.q_round != 0 && tile < a.nq_vis;
+    const float scale = prescale ? 1.f : a.scale_log2;
+    const float2 scale2 = make_float2(scale, scale);
 
     if (tile < a.nqt) {
+      if (cnt > 0) {
+        mbar_wait(bar(B_QFULL + s), 0);
+        if (prescale) {
+          // in place in shared memory; element-wise, so the swizzle does not matter: 128 threads x 16 bytes per step
+          uint4* qt = reinterpret_cast<uint4*>(smem + kOffQ + 2 * s * kGranule) + (threadIdx.x - 128 - 128 * s);
+#pragma unroll 4
+          for (int i = 0; i < (int)(kTileBytes / 2048); ++i) {
+            uint4 x = qt[i * 128];
+            x.x = scale_x2<kF16>(x.x, a.scale_log2);
+            x.y = scale_x2<kF16>(x.y, a.scale_log2);
+            x.z = scale_x2<kF16>(x.z, a.scale_log2);
+            x.w = scale_x2<kF16>(x.w, a.scale_log2);
+            qt[i * 128] = x;
+          }
+          fence_proxy_async_smem();
+        }
+        mbar_arrive(bar(B_QSCALED + s));
+      }
       for (int i = 0; i < cnt; ++i) {
         RSA_TRACE(tr, i, 0);
         // valid keys in this block (the schedule is not ascending): the end of the valid keys, and the end of the

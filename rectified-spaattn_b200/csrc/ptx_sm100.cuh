@@ -39,6 +39,9 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
       : "memory");
 }
 
+// Generic-proxy writes to shared memory (st.shared) made visible to the async proxy (TMA, tcgen05.mma operand reads).
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 // True in exactly one lane of a converged warp; lets ptxas keep the surrounding values in uniform registers.
 __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
@@ -195,6 +198,18 @@ template <bool kF16>
 __device__ __forceinline__ uint32_t pack_x2(float lo, float hi) {
   if constexpr (kF16) return pack_f16x2(lo, hi);
   else return pack_bf16x2(lo, hi);
+}
+// two packed 16-bit floats times c in fp32, rounded back to the 16-bit type (round to nearest even)
+template <bool kF16>
+__device__ __forceinline__ uint32_t scale_x2(uint32_t w, float c) {
+  float lo, hi;
+  if constexpr (kF16) {
+    asm("{.reg .f16 l, h; mov.b32 {l, h}, %2; cvt.f32.f16 %0, l; cvt.f32.f16 %1, h;}" : "=f"(lo), "=f"(hi) : "r"(w));
+  } else {
+    lo = __uint_as_float(w << 16);
+    hi = __uint_as_float(w & 0xffff0000u);
+  }
+  return pack_x2<kF16>(lo * c, hi * c);
 }
 
 }  // namespace ptx

@@ -198,11 +198,12 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->o_table = nullptr;
   a->peer_rows = a->peer_head0 = 0;
   a->peer_os[0] = a->peer_os[1] = 0;
-  a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.4426950408889634);
+  a->scale_log2 = (float)((1.0 / sqrt((double)d->head_dim)) * 1.44269504);  // the reference's qk_scale (wan21 :145)
   a->head_dim = d->head_dim;
   a->rescale_thr = attention_rescale_threshold(d->dtype == RSA_DTYPE_F16);
   a->front_text_heads = front_text_heads(L, d->top_k);
   a->f16 = d->dtype == RSA_DTYPE_F16;
+  a->q_round = 1;
   a->dbg = g_attention_dbg;
   a->dbg_flags = g_attention_dbg_flags;
   return RSA_OK;
@@ -600,6 +601,8 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
                                     int n_q_blocks, int n_kv_blocks, void* workspace, size_t bytes, void* stream,
                                     int dtype, int head_dim) {
   if (!q || !k || !v || !out || !block_mask) RSA_FAIL(RSA_ERR_ARG, "rsa_masked_attention: null pointer");
+  const int q_round = (dtype & RSA_ATTN_FP32_SCALE) ? 0 : 1;
+  dtype &= ~RSA_ATTN_FP32_SCALE;
   if (dtype != RSA_DTYPE_BF16 && dtype != RSA_DTYPE_F16) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_masked_attention: dtype %d", dtype);
   if (head_dim != RSA_HEAD_DIM && head_dim != 64) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_masked_attention: head_dim must be 128 or 64 (got %d)", head_dim);
   if (bh <= 0 || bh > 65535 || seq_q <= 0 || seq_kv <= 0 || kv_len < 1 || kv_len > seq_kv)
@@ -651,11 +654,12 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   a.o_table = nullptr;
   a.peer_rows = a.peer_head0 = 0;
   a.peer_os[0] = a.peer_os[1] = 0;
-  a.scale_log2 = (float)((1.0 / sqrt((double)head_dim)) * 1.4426950408889634);
+  a.scale_log2 = (float)((1.0 / sqrt((double)head_dim)) * 1.44269504);  // the reference's qk_scale (wan21 :145)
   a.head_dim = head_dim;
   a.rescale_thr = attention_rescale_threshold(dtype == RSA_DTYPE_F16);
   a.front_text_heads = 0;
   a.f16 = dtype == RSA_DTYPE_F16;
+  a.q_round = q_round;
   a.dbg = g_attention_dbg;
   a.dbg_flags = g_attention_dbg_flags;
   return launch_attention(a, s);

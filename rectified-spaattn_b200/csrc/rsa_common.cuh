@@ -153,6 +153,8 @@ struct AttnArgs {
   int front_text_heads;     // kernel 4's grid: the text pairs of this many last heads are scheduled before everything else
   float rescale_thr;        // kernel 4: O and l are rescaled only when a row maximum grows by more than 2^rescale_thr
   int head_dim;             // 128 or 64: columns that exist in q/k/v/o (the rest of the 128-column tiles reads as zeros)
+  int q_round;              // 1: visual query tiles use q~ = dtype(q * sm_scale * log2 e) like the reference's Triton kernel
+                            // (wan21 :61-62); 0: S is scaled in fp32 everywhere (flash-attn's arithmetic, attn.py:107-120)
   int f16;                  // q/k/v/o hold fp16 instead of bf16 (the pointer types above are nominal: 2-byte elements)
   int dbg_flags;            // bring-up ablations (rsa_debug_set_attention_flags), only read by the debug kernel
   float* dbg;               // bring-up dump of tile 0 / bh 0 (rsa_debug_set_attention_dump), normally null

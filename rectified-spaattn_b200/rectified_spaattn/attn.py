@@ -44,7 +44,7 @@ def _flash_like(q, k, v, cu_seqlens_q, cu_seqlens_kv, batch_size):
         kv_len = min(skv, int(ck[1]))
     nqb, nkb = (sq + 127) // 128, (skv + 127) // 128
     mask = torch.ones(b, h, nqb, nkb, dtype=torch.bool, device=q.device)
-    out = _ops.masked_attention(q, k, v, mask, kv_len)
+    out = _ops.masked_attention(q, k, v, mask, kv_len, fp32_scale=True)   # flash-attn's arithmetic: no q~ rounding
     if q_valid < sq:
         out[:, :, q_valid:] = 0
     return out

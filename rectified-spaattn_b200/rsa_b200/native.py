@@ -14,6 +14,7 @@ RSA_OK = 0
 FAMILY_WAN, FAMILY_JOINT = 0, 1
 MASK_BUILD, MASK_KEEP_LISTS, MASK_KEEP_ALL = 0, 1, 2   # enum rsa_mask_mode
 DTYPE_BF16, DTYPE_F16 = 0, 1                           # enum rsa_dtype
+ATTN_FP32_SCALE = 256                                  # RSA_ATTN_FP32_SCALE, OR-ed into rsa_masked_attention's dtype
 BLOCK = 128
 
 

@@ -483,10 +483,12 @@ def rectified_attention(q, k, v, geo, top_k, p_remain, nbr=None, shape_xfuse=Fal
     return out if shape_xfuse else out.view(b, s, h * d)
 
 
-def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None, out=None):
+def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None, out=None, fp32_scale=False):
     """Kernel 4 alone on a dense block mask: the surface of _triton_block_sparse_attention_onehot
     (rectified_wan21_attn.py:108-117).  q,k,v [B,H,S,D] bf16 (any batch / head / token strides with D contiguous -- the
-    ABI takes strides, nothing is copied), block_mask bool [B,H,NQ,NB] -> [B,H,S,D]."""
+    ABI takes strides, nothing is copied), block_mask bool [B,H,NQ,NB] -> [B,H,S,D].  Like that kernel, the query is
+    pre-scaled by sm_scale * log2(e) and ROUNDED to the input dtype (:61-62); fp32_scale=True scales the fp32 scores
+    instead, which is what flash-attn does (the mirror's dense `fullattn`)."""
     _need_cuda(q, "q")
     if q.dtype not in (torch.bfloat16, torch.float16) or k.dtype != q.dtype or v.dtype != q.dtype:
         raise RuntimeError("q, k, v must all be bfloat16 or all float16")
@@ -527,7 +529,8 @@ def masked_attention(q, k, v, block_mask, kv_len, sm_scale=None, out=None):
         N.check(L.rsa_masked_attention(q3.data_ptr(), k3.data_ptr(), v3.data_ptr(), o3.data_ptr(), b * h, s, skv,
                                        int(kv_len), mk(qs), mk(ks), mk(vs), mk(os_), m.data_ptr(), nqb, nkb,
                                        ws.data_ptr(), nbytes, _stream(q.device),
-                                       N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16, d),
+                                       (N.DTYPE_F16 if q.dtype == torch.float16 else N.DTYPE_BF16)
+                                       | (N.ATTN_FP32_SCALE if fp32_scale else 0), d),
                 "rsa_masked_attention")
     return out
 

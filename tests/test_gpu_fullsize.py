@@ -5,7 +5,8 @@ these shapes, so the checks are the size-independent ones --
     neighbours / the first-frame square / the text blocks, 0 < R <= 1, text query tiles dense with R = 1 and C = 0,
     kept lists strictly ascending);
   * sampled query tiles (first, last visual -- the ragged one at 129 frames --, random ones, a text tile) recomputed in
-    fp32 PyTorch from the kernel's kept list, R and C: output max-abs-err <= 2e-2 and cosine >= 0.999;
+    fp32 PyTorch from the kernel's kept list, R and C, with the reference kernel's rounding of the pre-scaled query on
+    visual tiles: output max-abs-err <= 2e-2 and cosine >= 0.999;
   * where the visual segment is block-aligned, the whole output against the independent mma.sync kernel.
 """
 import os
@@ -108,7 +109,12 @@ def test_full_size_invariants_and_sampled_tiles(dev, name):
                 a1 = min(a1, a0 + max(0, geo.kv_len - v0))    # keys >= kv_len are never attended
                 keys.append(torch.arange(a0, a1, device=dev))
             keys = torch.cat(keys)
-            p = torch.softmax((qi @ k[0, hi, keys].float().T) * scale, dim=-1)
+            if i < nq:      # visual tile: the reference kernel's q~ = bf16(q * sm_scale * log2 e) and exp2 (wan21 :61-62)
+                sc = (qi * (scale * 1.44269504)).to(torch.bfloat16).float() @ k[0, hi, keys].float().T
+                p = torch.exp2(sc - sc.max(dim=-1, keepdim=True).values)
+                p = p / p.sum(dim=-1, keepdim=True)
+            else:           # text tile: flash-attn's arithmetic (fp32 scores scaled)
+                p = torch.softmax((qi @ k[0, hi, keys].float().T) * scale, dim=-1)
             ref = p @ v[0, hi, keys].float()
             ref = ref * float(R[hi, i]) + C[hi, i][None, :]
             got = out[0, r0:r1, hi].float()

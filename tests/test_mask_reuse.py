@@ -103,7 +103,7 @@ def test_reuse_on_unchanged_inputs_is_bit_identical(dev, name, keep):
     b = p1.run()
     torch.cuda.synchronize()
     assert torch.equal(a.view(torch.int16), b.view(torch.int16))
-    ref = O.forward(*first, case["ogeo"], case["nbr"]).reshape(a.shape)
+    ref = O.forward(*first, case["ogeo"], case["nbr"], q_dtype="bf16").reshape(a.shape)
     assert np.abs(b.float().cpu().numpy() - ref).max() <= ATOL_OUT
 
 
@@ -133,7 +133,8 @@ def test_reuse_on_new_inputs_matches_oracle_with_carried_selection(dev, name, ke
     for hi in range(case["heads"]):
         q, k, v = (x[0, hi] for x in second)
         keep_rc = None if keep == "lists" else (r0[hi, :nq], c0[hi, :nq])
-        ref, st = O.head_forward(q, k, v, geo, nbr, return_stages=True, keep_mask=mask0[hi, :nq], keep_rc=keep_rc)
+        ref, st = O.head_forward(q, k, v, geo, nbr, return_stages=True, keep_mask=mask0[hi, :nq], keep_rc=keep_rc,
+                                 q_dtype="bf16")
         if keep == "lists":     # R, C recomputed from the second call's P, GAPR bytes and pooled V
             np.testing.assert_allclose(vw["R"][hi, :nq].cpu().numpy(), st["R"], rtol=0, atol=3e-6)
             np.testing.assert_allclose(vw["C"][hi, :nq].cpu().numpy(), st["C"], rtol=1e-4, atol=3e-6)

@@ -22,7 +22,9 @@
 // x * rsqrt(mean(x^2) + eps) in fp32 -> bf16 -> * weight -> bf16) and diffusers apply_rotary_emb(use_real=True,
 // use_real_unbind_dim=-1): out = x * cos + rotate_pairs(x) * sin in fp32 (two products and a sum, each rounded) -> bf16.
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
+#include "ptx_sm100.cuh"
 #include "rsa_common.cuh"
 
 namespace rsa {
@@ -387,6 +389,211 @@ __global__ void __launch_bounds__(kThreads, kMinBlocks) pool_stats_kernel(const 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 2, streaming form (the one rsa_pool_stats launches).  The per-block kernel above is latency-exposed: a CTA
+// requests its 32 KB, waits for them, reduces twice across three barriers and leaves -- nothing is in flight for the
+// SM while it reduces, and at C3b there are 67 000 such CTAs (0.77 of the measured copy bandwidth).  Here a persistent
+// grid (2 CTAs per SM) walks contiguous ranges of (tensor, head, block) items; an otherwise idle warp keeps
+// kPoolStages blocks in flight with bulk copies (cp.async.bulk, no tensor map: each row is head_dim * 2 contiguous
+// bytes; rows of a [B, H, S, D] tensor with token stride D are one 32 KB copy) into a shared-memory ring, and the 256
+// threads reduce block i from shared memory exactly as above -- same thread <-> row mapping, same summation order, so
+// the statistics are bit-identical -- while blocks i + 1, i + 2 land.
+constexpr int kPoolStages = 3;
+constexpr int kPoolStageBytes = 128 * 256;
+constexpr int kPoolSmem = kPoolStages * kPoolStageBytes + 64;
+
+struct StreamCursor {  // (tensor, head, block) walked in order without divisions
+  int which, bh, blk;
+  __device__ __forceinline__ void advance(const int (&per_head)[3], int n_bh) {
+    const int ph = which == 0 ? per_head[0] : (which == 1 ? per_head[1] : per_head[2]);
+    if (++blk == ph) {
+      blk = 0;
+      if (++bh == n_bh) {
+        bh = 0;
+        ++which;
+      }
+    }
+  }
+};
+
+template <bool kF16>
+__global__ void __launch_bounds__(kThreads, 2) pool_stats_stream_kernel(const PoolArgs a, const int n_items) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(16) float s_part[2][8][128];  // [sweep]: two buffers save the barrier between blocks
+  __shared__ __align__(16) float s_mean[128];
+  using namespace ptx;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kPoolStages * kPoolStageBytes;
+  // contiguous, balanced range of items for this CTA
+  const int lo = (int)((int64_t)n_items * blockIdx.x / gridDim.x), hi = (int)((int64_t)n_items * (blockIdx.x + 1) / gridDim.x);
+  const int per_head[3] = {a.n_blk[0], a.n_blk[1], a.n_blk[2]};
+  const int n_bh = n_items / (per_head[0] + per_head[1] + per_head[2]);
+  StreamCursor cur;
+  {
+    const int t0 = n_bh * per_head[0], t1 = t0 + n_bh * per_head[1];
+    cur.which = lo < t0 ? 0 : (lo < t1 ? 1 : 2);
+    const int r = lo - (cur.which == 0 ? 0 : (cur.which == 1 ? t0 : t1));
+    const int ph = cur.which == 0 ? per_head[0] : (cur.which == 1 ? per_head[1] : per_head[2]);
+    cur.bh = r / ph;
+    cur.blk = r - cur.bh * ph;
+  }
+  StreamCursor nxt = cur;  // warp 0: the next item to request
+  if (tid == 0) {
+    for (int s = 0; s < kPoolStages; ++s) mbar_init(bar0 + 8 * s, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  const int row_bytes = a.head_dim * 2;
+  // rows of a block that hold data (the others pool as zeros): visual blocks end at vis_len, K / V at kv_zero_from
+  auto rows_of = [&](const StreamCursor& it) {
+    const int valid = it.blk < a.nq_vis ? min(a.valid_rows[it.which], a.vis_len) : a.valid_rows[it.which];
+    return max(0, min(128, valid - it.blk * 128));
+  };
+  // warp 0 requests item `nxt` into stage n % kPoolStages
+  auto issue = [&](int n) {
+    const StreamCursor it = nxt;
+    nxt.advance(per_head, n_bh);
+    const int st = n % kPoolStages;
+    const int rows = rows_of(it);
+    const int shift = it.blk < a.nq_vis ? 0 : a.gap;
+    const int b = it.bh / a.heads, h = it.bh - b * a.heads;
+    const int64_t ts = a.stride[it.which][2];
+    const __nv_bfloat16* src = a.x[it.which] + b * a.stride[it.which][0] + h * a.stride[it.which][1] +
+                               (int64_t)(it.blk * 128 - shift) * ts;
+    const uint32_t dst = sbase + st * kPoolStageBytes, bar = bar0 + 8 * st;
+    if (lane == 0) {
+      if (rows > 0) mbar_arrive_expect_tx(bar, (uint32_t)(rows * row_bytes));
+      else mbar_arrive(bar);
+    }
+    __syncwarp();
+    if (ts == 128 && a.head_dim == 128) {
+      if (lane == 0 && rows > 0) bulk_load_1d(dst, src, (uint32_t)(rows * 256), bar);
+    } else {
+      for (int r = lane; r < rows; r += 32) bulk_load_1d(dst + r * 256, src + (int64_t)r * ts, (uint32_t)row_bytes, bar);
+    }
+  };
+  const int n_mine = hi - lo;
+  // The requests are issued by warp 7, which has nothing to do while warps 0-3 finish a block's means: after the first
+  // barrier of block n every thread holds that block in registers, so its stage is free for block n + kPoolStages.
+  constexpr int kIssuer = 7;
+  if (warp == kIssuer)
+    for (int n = 0; n < kPoolStages && n < n_mine; ++n) issue(n);
+
+  const int col = 8 * (lane & 15);
+  const int rloc = 16 * warp + (lane >> 4);  // this thread's first row inside a block; then every second row
+  for (int n = 0; n < n_mine; ++n) {
+    const int which = cur.which, bh = cur.bh, blk = cur.blk;
+    const int nrows = rows_of(cur);
+    cur.advance(per_head, n_bh);
+    const int st = n % kPoolStages;
+    mbar_wait(bar0 + 8 * st, (n / kPoolStages) & 1);
+    const uint4* tp = reinterpret_cast<const uint4*>(smem + st * kPoolStageBytes + rloc * 256 + col * 2);
+    // The block's values stay unpacked in registers for both sweeps, and the sweeps use packed fp32 instructions
+    // (add.rn.f32x2: two independent IEEE additions per instruction, so the summation order per column -- the contract
+    // with the oracle -- is untouched): at the SM clock the part sustains under its power cap this kernel is bound by
+    // issue slots, not by HBM (ncu: 57 % of the issue slots at 5.8 TB/s and 1.9 GHz before this diet).
+    float2 f[8][4];
+    auto unpack = [&](const uint4& u, int i) {
+      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if constexpr (kF16) f[i][c] = __half22float2(*reinterpret_cast<const __half2*>(&w[c]));
+        else f[i][c] = make_float2(__uint_as_float(w[c] << 16), __uint_as_float(w[c] & 0xffff0000u));
+      }
+    };
+    if (nrows == 128 && a.head_dim == 128) {  // the common case: a whole block, nothing to predicate
+#pragma unroll
+      for (int i = 0; i < 8; ++i) unpack(tp[i * 32], i);
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        uint4 u = make_uint4(0, 0, 0, 0);
+        if (rloc + 2 * i < nrows && col < a.head_dim) u = tp[i * 32];
+        unpack(u, i);
+      }
+    }
+    float2 acc[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[c] = __fadd2_rn(acc[c], f[i][c]);
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      acc[c].x = __fadd_rn(acc[c].x, __shfl_xor_sync(0xffffffffu, acc[c].x, 16));
+      acc[c].y = __fadd_rn(acc[c].y, __shfl_xor_sync(0xffffffffu, acc[c].y, 16));
+    }
+    if (lane < 16) {
+      reinterpret_cast<float4*>(&s_part[0][warp][col])[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+      reinterpret_cast<float4*>(&s_part[0][warp][col])[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+    }
+    __syncthreads();
+    if (warp == kIssuer && n + kPoolStages < n_mine) issue(n + kPoolStages);
+    if (tid < 128) {
+      float t = s_part[0][0][tid];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) t = __fadd_rn(t, s_part[0][w][tid]);
+      const float m = __fmul_rn(t, 1.0f / 128.0f);
+      s_mean[tid] = m;
+      a.mean[which][((int64_t)bh * a.out_rows[which] + blk) * 128 + tid] = m;
+    }
+    if (a.mad[which] == nullptr) {  // V: means only (uniform over the CTA)
+      __syncthreads();              // s_part[0] and the stage may be written again
+      continue;
+    }
+    __syncthreads();
+    const float4 m0 = reinterpret_cast<const float4*>(&s_mean[col])[0], m1 = reinterpret_cast<const float4*>(&s_mean[col])[1];
+    const float2 negm[4] = {make_float2(-m0.x, -m0.y), make_float2(-m0.z, -m0.w), make_float2(-m1.x, -m1.y),
+                            make_float2(-m1.z, -m1.w)};
+    float dev[8];
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dev[c] = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float2 d2 = __fadd2_rn(f[i][c], negm[c]);  // x - mean == x + (-mean) exactly
+        dev[2 * c] = __fadd_rn(dev[2 * c], fabsf(d2.x));
+        dev[2 * c + 1] = __fadd_rn(dev[2 * c + 1], fabsf(d2.y));
+      }
+#pragma unroll
+    for (int c = 0; c < 8; ++c) dev[c] = __fadd_rn(dev[c], __shfl_xor_sync(0xffffffffu, dev[c], 16));
+    if (lane < 16) {
+      reinterpret_cast<float4*>(&s_part[1][warp][col])[0] = make_float4(dev[0], dev[1], dev[2], dev[3]);
+      reinterpret_cast<float4*>(&s_part[1][warp][col])[1] = make_float4(dev[4], dev[5], dev[6], dev[7]);
+    }
+    __syncthreads();
+    if (tid < 128) {
+      float t = s_part[1][0][tid];
+#pragma unroll
+      for (int w = 1; w < 8; ++w) t = __fadd_rn(t, s_part[1][w][tid]);
+      a.mad[which][((int64_t)bh * a.n_blk[which] + blk) * 128 + tid] = __fmul_rn(t, 1.0f / 128.0f);
+    }
+    // no barrier here: the next block writes s_part[0] (last read two barriers ago) and s_mean / s_part[1] only after
+    // its own first / second barrier, which every reader above reaches first
+  }
+  __syncthreads();
+
+  // text keys scored as single tokens -> fp32 rows [NQ, NQ + a) of k_cat (hunyuan :193-194): one 16-lane group per row
+  const int64_t text_rows = (int64_t)n_bh * a.text_keys;
+  for (int64_t t = (int64_t)blockIdx.x * (kThreads / 16) + (tid >> 4); t < text_rows; t += (int64_t)gridDim.x * (kThreads / 16)) {
+    const int bh = (int)(t / a.text_keys), tk = (int)(t - (int64_t)bh * a.text_keys);
+    const int b = bh / a.heads, h = bh % a.heads;
+    const int tok = a.text_from + tk;
+    const __nv_bfloat16* src = a.x[1] + b * a.stride[1][0] + h * a.stride[1][1] + (int64_t)tok * a.stride[1][2];
+    float f[8];
+    uint4 u = make_uint4(0, 0, 0, 0);
+    if (tok + a.gap < a.valid_rows[1] && 8 * (tid & 15) < a.head_dim) u = *reinterpret_cast<const uint4*>(src + 8 * (tid & 15));
+    unpack8<kF16>(u, f);
+    float* dst = a.mean[1] + ((int64_t)bh * a.out_rows[1] + a.n_blk[1] + tk) * 128 + 8 * (tid & 15);
+    reinterpret_cast<float4*>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
+    reinterpret_cast<float4*>(dst)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+
 }  // namespace
 
 static PoolArgs pool_args(const rsa_attn_desc* d, const void* q, const void* k, const void* v, char* ws,
@@ -432,10 +639,38 @@ static PoolArgs pool_args(const rsa_attn_desc* d, const void* q, const void* k, 
 int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, const void* v, char* ws,
                       const WsLayout& L, cudaStream_t s) {
   const PoolArgs a = pool_args(d, q, k, v, ws, L);
-  const int text_ctas = (L.a + 15) / 16;
-  dim3 grid(L.nb + text_ctas, L.bh, 3);  // (a fourth z plane for the text keys launched nb - text_ctas empty CTAs per head)
-  if (d->dtype == RSA_DTYPE_F16) pool_stats_kernel<false, 3, 0, false, false, true><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
-  else pool_stats_kernel<false, 3><<<grid, kThreads, 0, s>>>(a, PrepArgs{});  // 4 CTAs per SM (64 registers, 68 B of spills): 0.49 against 0.465 ms at C3b
+  static int form = -1;  // RSA_POOL_FORM=0: the per-block kernel (A/B timing); default: the streaming kernel
+  if (form < 0) {
+    const char* e = getenv("RSA_POOL_FORM");
+    form = (e && e[0] == '0') ? 0 : 1;
+  }
+  if (form == 0) {
+    const int text_ctas = (L.a + 15) / 16;
+    dim3 grid(L.nb + text_ctas, L.bh, 3);
+    if (d->dtype == RSA_DTYPE_F16) pool_stats_kernel<false, 3, 0, false, false, true><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
+    else pool_stats_kernel<false, 3><<<grid, kThreads, 0, s>>>(a, PrepArgs{});
+    RSA_CUDA_CHECK(cudaGetLastError());
+    return RSA_OK;
+  }
+  static int sms = 0;
+  static bool configured = false;
+  if (!configured) {
+    int dev = 0;
+    RSA_CUDA_CHECK(cudaGetDevice(&dev));
+    RSA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    RSA_CUDA_CHECK(cudaFuncSetAttribute(pool_stats_stream_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmem));
+    RSA_CUDA_CHECK(cudaFuncSetAttribute(pool_stats_stream_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmem));
+    // two CTAs of 100 KB each per SM: without the hint the driver may pick a smaller shared-memory carve-out that holds one
+    RSA_CUDA_CHECK(cudaFuncSetAttribute(pool_stats_stream_kernel<false>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    RSA_CUDA_CHECK(cudaFuncSetAttribute(pool_stats_stream_kernel<true>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    configured = true;
+  }
+  const int64_t items = (int64_t)L.bh * (2 * (int64_t)L.nq + L.nb);
+  if (items == 0) return RSA_OK;
+  if (items > 0x7fffffffLL) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_pool_stats: too many blocks");
+  const int grid = (int)(items < 2 * sms ? items : 2 * sms);
+  if (d->dtype == RSA_DTYPE_F16) pool_stats_stream_kernel<true><<<grid, kThreads, kPoolSmem, s>>>(a, (int)items);
+  else pool_stats_stream_kernel<false><<<grid, kThreads, kPoolSmem, s>>>(a, (int)items);
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;
 }

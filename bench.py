@@ -403,6 +403,95 @@ def reference_on_gpu(name, regime, dev, ours_ms_fn):
                     "in cosine, not element-wise"}
 
 
+# ------------------------------------------------------------------- sequence-parallel host models (world > 1)
+def ulysses_leg(wp, dev, rank, world, steps=10):
+    """SURVEY 8e / 8f rank 3, measured beside the headline (not part of it): the same attention layer for a host model
+    that keeps the SEQUENCE sharded over the ranks (Ulysses).  Every rank holds tokens [r S/P, (r+1) S/P) of the Q/K/V
+    projection outputs and must end up with the same tokens of the result.
+      fused: rsa_b200.parallel.FusedUlysses -- kernel 0 gathers each token's rows from the owning rank's peer-mapped
+             buffer over NVLink while it normalises / rotates / pools, kernel 4's epilogue scatters every output row into
+             the owning rank's buffer; two one-element all-reduces as barriers, no data collective;
+      nccl:  all_to_all_single x3 in, kernel 0 + kernels 3a-4 locally, all_to_all_single out (+ staging copies).
+    Both must produce the same bits on every rank."""
+    import torch
+    import torch.distributed as dist
+    from rsa_b200 import ops, parallel
+    heads, s, nv = wp["heads"], wp["s"], wp["nv"]
+    if heads % world or s % world:
+        return {"unavailable": f"{heads} heads / {s} tokens do not divide by {world} ranks"}
+    geo = product_geometry(wp)
+    t, h, w = wp["grid"]
+    nbr = ops.gilbert_block_neighbors(t, h, w)
+    rows, hl = s // world, heads // world
+    g = torch.Generator(device=dev).manual_seed(1234)            # the same stream on every rank: the full tensors
+    full = [torch.randn(1, s, heads * 128, generator=g, device=dev).to(torch.bfloat16) for _ in range(3)]
+    mu = torch.cumsum(torch.randn(1, (s + 127) // 128, heads * 128, generator=g, device=dev) * 0.35, dim=1)
+    for x in full[:2]:                                           # block structure, as in the headline's inputs
+        x.add_(mu.repeat_interleave(128, dim=1)[:, :s].to(torch.bfloat16))
+    del mu
+    wq = (1 + 0.1 * torch.randn(128, generator=g, device=dev)).to(torch.bfloat16)
+    wk = (1 + 0.1 * torch.randn(128, generator=g, device=dev)).to(torch.bfloat16)
+    ang = torch.outer(torch.arange(nv, dtype=torch.float32, device=dev),
+                      1.0 / (256.0 ** (torch.arange(0, 128, 2, device=dev) / 128)))
+    rope = (ang.cos().repeat_interleave(2, 1).contiguous(), ang.sin().repeat_interleave(2, 1).contiguous())
+    del ang
+    mine = slice(rank * rows, (rank + 1) * rows)
+    norm = {} if wp["fam"] == "wan" else dict(q_weight=wq, k_weight=wk, eps=1e-6)   # the fused gather has the per-head norm
+    fu = parallel.FusedUlysses(1, heads, geo, wp["top_k"], P_REMAIN, nbr)
+    for dst, src in zip((fu.q_src, fu.k_src, fu.v_src), full):
+        dst.copy_(src[:, mine])
+    run_fused = lambda: fu.run(norm.get("q_weight"), norm.get("k_weight"), 1e-6, rope, nv)
+    out = run_fused().clone()
+    q, k, v = (torch.empty(1, hl, s, 128, dtype=torch.bfloat16, device=dev) for _ in range(3))
+    plan = ops.Plan(q, k, v, geo, wp["top_k"], P_REMAIN, nbr)
+
+    def run_nccl():
+        srcs = []
+        for x in full:
+            loc = x[:, mine].reshape(1, rows, world, hl * 128).permute(2, 0, 1, 3).contiguous()   # [P(dst), 1, rows, hl*128]
+            rcv = torch.empty_like(loc)
+            dist.all_to_all_single(rcv, loc)
+            srcs.append(rcv.permute(1, 0, 2, 3).reshape(1, s, hl * 128))                         # all tokens, my heads
+        if geo.gap:
+            plan.qkv_prep(*(x[:, :nv] for x in srcs), dst_row=0, rope=rope, **norm)
+            plan.qkv_prep(*(x[:, nv:] for x in srcs), dst_row=nv, **norm)
+        else:
+            plan.qkv_prep(*srcs, dst_row=0, rope=rope, rope_rows=nv, **norm)
+        o = plan.run_pooled()                                                                     # [1, S, hl, 128]
+        return parallel.head_to_seq_shard(o).reshape(1, rows, heads * 128)
+
+    ref = run_nccl().clone()
+    torch.cuda.synchronize()
+    same = bool(torch.equal(out.view(torch.int16), ref.view(torch.int16)))
+
+    def timed_max(fn):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        tt = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item())
+
+    ms_fused, ms_nccl = timed_max(run_fused), timed_max(run_nccl)
+    oks = [None] * world
+    dist.all_gather_object(oks, same)
+    fu.close()
+    return {"fused_ms": ms_fused, "nccl_all_to_all_form_ms": ms_nccl, "fused_over_nccl": ms_fused / ms_nccl,
+            "bitwise_equal": all(oks), "tokens_per_rank": rows, "heads_per_rank": hl,
+            "note": "one attention layer of a sequence-parallel (Ulysses) host model: kernel 0 (head split, QK norm, rotary "
+                    "embedding, pooling) + kernels 3a-4; fused = gather inside kernel 0 and scatter inside kernel 4's "
+                    "epilogue over peer memory; nccl = all_to_all_single x4 + staging copies around the same kernels; "
+                    "max over ranks, CUDA events"}
+
+
 # ------------------------------------------------------------------------------------------------------ main
 def main():
     ap = argparse.ArgumentParser()
@@ -421,6 +510,7 @@ def main():
     ap.add_argument("--no-reference-gpu", action="store_true",
                     help="skip the reference_gpu key (the unmodified reference from baseline/_ref on this GPU)")
     ap.add_argument("--no-permute", action="store_true")
+    ap.add_argument("--no-ulysses", action="store_true", help="world > 1: skip the sequence-parallel (Ulysses) leg")
     ap.add_argument("--host-chunk", type=int, default=0,
                     help="heads per chunk of the pipelined host-buffer call (0 = library default: 2, or 1 below 8 heads)")
     args = ap.parse_args()
@@ -611,6 +701,20 @@ def main():
             dv_.copy_(hv, non_blocking=True)
 
         ms_h2d = timed(h2d_only, 3)
+        # the copy ceiling of this step on this box: the step's bytes in BOTH directions at once (H2D of Q, K, V on one
+        # stream, D2H of the result on another), all ranks together, no kernels -- PCIe is not full duplex at full rate
+        # here (one GPU: 55 GB/s in alone, 71 GB/s in + out together), and 8 GPUs share the host's root ports
+        do_ = torch.empty((1, wp["s"], h_loc * 128), dtype=torch.bfloat16, device=dev)
+        side = torch.cuda.Stream()
+
+        def copies_only():
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                ho.copy_(do_, non_blocking=True)
+            h2d_only()
+            torch.cuda.current_stream().wait_stream(side)
+
+        ms_copies = timed(copies_only, 3)
         assert torch.equal(res["o"].view(torch.int16), ho.view(torch.int16)), "pipelined and serial results differ"
         bi = 3 * q.numel() * 2 * world
         bo = ho.numel() * 2 * world
@@ -619,8 +723,20 @@ def main():
                "path": f"public per-family entry point on pinned host tensors -> rsa_rectified_attention_host, "
                        f"{host_chunk} head(s) per chunk (the last {host_chunk} heads one per chunk), H2D | kernels | D2H on three streams",
                "ms_per_step_unpipelined": ms_serial,
-               "h2d_only_ms": ms_h2d, "host_numa_node_rank0": numa_node}
+               "h2d_only_ms": ms_h2d, "copies_only_ms": ms_copies, "frac_of_copy_ceiling": ms_copies / ms_e2e,
+               "copy_ceiling_note": "copies_only_ms = this step's H2D and D2H bytes moved concurrently by all ranks with no "
+                                    "kernel in between: the floor of any end-to-end schedule on this box",
+               "host_numa_node_rank0": numa_node}
 
+    ulysses = None
+    if world > 1 and not args.no_ulysses:
+        try:
+            del plan
+            torch.cuda.empty_cache()
+            ulysses = ulysses_leg(wp, dev, rank, world)
+        except Exception as e:  # noqa: BLE001
+            ulysses = {"unavailable": repr(e)[:300]}
+        plan = None
     if rank == 0:
         peaks = measured_peaks()
         t_attn = stages["sparse_attention"]
@@ -649,6 +765,8 @@ def main():
             line["hbm_kernels"] = hbm_kernels
         if e2e:
             line["e2e"] = e2e
+        if ulysses:
+            line["ulysses"] = ulysses
         if world == 1 and not args.no_cpu_baseline:
             arm = CpuArm(wp, args.regime)
             line["cpu_baseline"] = arm.describe(arm.head(), 1)

@@ -291,7 +291,9 @@ int rsa_peer_close(void* ptr);
  *                            rank's result buffer.
  * The caller provides the barriers: every rank's sources written before the gather, every rank's scatter finished
  * before the results are read (a zero-byte collective on the stream; rsa_b200/parallel.py uses an all_reduce of one
- * element).  Restrictions: seq == n_ranks * rows_per_rank, block-aligned visual segment, prep norm 0 or 1. */
+ * element).  Restrictions: seq == n_ranks * rows_per_rank, prep norm 0 or 1.  A ragged visual segment (HunyuanVideo 129
+ * frames) takes two gather calls like rsa_qkv_prep: the visual tokens (dst_row 0) and the text tokens (dst_row = visual
+ * token count); the source token of row r is dst_row + r in both. */
 typedef struct rsa_peer_route {
   int32_t n_ranks, rank;
   int32_t rows_per_rank;

@@ -118,12 +118,15 @@ __device__ __forceinline__ RopeRow load_rope(const PrepArgs& p, int r, int col, 
 // kNorm: 0 none, 1 RMSNorm over head_dim, 2 RMSNorm across heads (row statistic precomputed), 3 LayerNorm over head_dim.
 // kGather: rows come from peer-mapped buffers.  kCompact: one (cos, sin)-pair table.  Compile-time so that each form
 // carries only its own code and registers (with all of them behind run-time flags the HunyuanVideo form lost 40 %).
+template <int kNorm, bool kCompact>
+__device__ __forceinline__ void process_rows(const PrepArgs& p, int which, int b, int h, int jblk, int warp, int lane,
+                                             uint4 (&raw)[8]);
+
 template <int kNorm, bool kGather, bool kCompact>
 __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, int h, int jblk, int warp, int lane,
                                           uint4 (&raw)[8]) {
   const int col = 8 * (lane & 15);
   const __nv_bfloat16* src = p.src[which] + b * p.src_stride[which][0] + (int64_t)h * 128 + col;
-  __nv_bfloat16* dst = p.dst[which] + b * p.dst_stride[which][0] + h * p.dst_stride[which][1] + col;
   const int r0 = jblk * 128 + 16 * warp + (lane >> 4);  // source row of step 0; the 16 lanes of a half-warp share it
   if constexpr (!kGather) {
 #pragma unroll
@@ -140,12 +143,24 @@ __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, i
       const int r = r0 + 2 * it;
       raw[it] = make_uint4(0, 0, 0, 0);
       if (r < p.rows) {
-        const int owner = r / p.src_rows;
+        const int tok = p.dst_row0 + r;  // the peer buffers hold the tokens in memory order, like the destination
+        const int owner = tok / p.src_rows;
         const __nv_bfloat16* base = p.src_table[which * p.n_src + owner];
-        raw[it] = ld_global_v4(base + off + (int64_t)(r - owner * p.src_rows) * p.src_stride[which][1]);
+        raw[it] = ld_global_v4(base + off + (int64_t)(tok - owner * p.src_rows) * p.src_stride[which][1]);
       }
     }
   }
+  process_rows<kNorm, kCompact>(p, which, b, h, jblk, warp, lane, raw);
+}
+
+// raw[it] = source row jblk * 128 + 16 warp + 2 it + (lane >> 4), columns 8 (lane & 15) .. +7 of head h (zeros beyond the
+// source): normalise / rotate / round, store to the destination, and leave the rounded values in raw.
+template <int kNorm, bool kCompact>
+__device__ __forceinline__ void process_rows(const PrepArgs& p, int which, int b, int h, int jblk, int warp, int lane,
+                                             uint4 (&raw)[8]) {
+  const int col = 8 * (lane & 15);
+  __nv_bfloat16* dst = p.dst[which] + b * p.dst_stride[which][0] + h * p.dst_stride[which][1] + col;
+  const int r0 = jblk * 128 + 16 * warp + (lane >> 4);
   if (which == 2) {  // V: re-layout only
 #pragma unroll
     for (int it = 0; it < 8; ++it) {
@@ -402,6 +417,87 @@ constexpr int kPoolStages = 3;
 constexpr int kPoolStageBytes = 128 * 256;
 constexpr int kPoolSmem = kPoolStages * kPoolStageBytes + 64;
 
+// One block's statistics from its values held in registers (thread (warp, lane): rows 16 warp + 2 i + (lane >> 4),
+// columns 8 (lane & 15) .. +7 as four pairs), in the summation order documented at the top of this file.  Packed fp32
+// instructions (add.rn.f32x2: two independent IEEE additions per instruction, so the order per column -- the contract
+// with the oracle -- is untouched): at the SM clock the part sustains under its power cap these kernels are bound by
+// issue slots, not by HBM (ncu: 57 % of the issue slots at 5.8 TB/s and 1.9 GHz before this diet).
+// `after_first_barrier` runs once every thread of the CTA holds its part of the block in registers.  Three barriers per
+// block (two without deviations); s_part has one buffer per sweep, which saves the barrier between blocks: the next
+// block writes s_part[0] (last read two barriers ago) and s_mean / s_part[1] only after its own first / second
+// barrier, which every reader reaches first.
+template <class F>
+__device__ __forceinline__ void pool_block(const PoolArgs& a, const float2 (&f)[8][4], int which, int bh, int blk,
+                                           float (*s_part)[8][128], float* s_mean, int tid, int warp, int lane,
+                                           F&& after_first_barrier) {
+  const int col = 8 * (lane & 15);
+  float2 acc[4];
+#pragma unroll
+  for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) acc[c] = __fadd2_rn(acc[c], f[i][c]);
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    acc[c].x = __fadd_rn(acc[c].x, __shfl_xor_sync(0xffffffffu, acc[c].x, 16));
+    acc[c].y = __fadd_rn(acc[c].y, __shfl_xor_sync(0xffffffffu, acc[c].y, 16));
+  }
+  if (lane < 16) {
+    reinterpret_cast<float4*>(&s_part[0][warp][col])[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
+    reinterpret_cast<float4*>(&s_part[0][warp][col])[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
+  }
+  __syncthreads();
+  after_first_barrier();
+  if (tid < 128) {
+    float t = s_part[0][0][tid];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t = __fadd_rn(t, s_part[0][w][tid]);
+    const float m = __fmul_rn(t, 1.0f / 128.0f);
+    s_mean[tid] = m;
+    a.mean[which][((int64_t)bh * a.out_rows[which] + blk) * 128 + tid] = m;
+  }
+  __syncthreads();
+  if (a.mad[which] == nullptr) return;  // V: means only (uniform over the CTA)
+  const float4 m0 = reinterpret_cast<const float4*>(&s_mean[col])[0], m1 = reinterpret_cast<const float4*>(&s_mean[col])[1];
+  const float2 negm[4] = {make_float2(-m0.x, -m0.y), make_float2(-m0.z, -m0.w), make_float2(-m1.x, -m1.y),
+                          make_float2(-m1.z, -m1.w)};
+  float dev[8];
+#pragma unroll
+  for (int c = 0; c < 8; ++c) dev[c] = 0.f;
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      const float2 d2 = __fadd2_rn(f[i][c], negm[c]);  // x - mean == x + (-mean) exactly
+      dev[2 * c] = __fadd_rn(dev[2 * c], fabsf(d2.x));
+      dev[2 * c + 1] = __fadd_rn(dev[2 * c + 1], fabsf(d2.y));
+    }
+#pragma unroll
+  for (int c = 0; c < 8; ++c) dev[c] = __fadd_rn(dev[c], __shfl_xor_sync(0xffffffffu, dev[c], 16));
+  if (lane < 16) {
+    reinterpret_cast<float4*>(&s_part[1][warp][col])[0] = make_float4(dev[0], dev[1], dev[2], dev[3]);
+    reinterpret_cast<float4*>(&s_part[1][warp][col])[1] = make_float4(dev[4], dev[5], dev[6], dev[7]);
+  }
+  __syncthreads();
+  if (tid < 128) {
+    float t = s_part[1][0][tid];
+#pragma unroll
+    for (int w = 1; w < 8; ++w) t = __fadd_rn(t, s_part[1][w][tid]);
+    a.mad[which][((int64_t)bh * a.n_blk[which] + blk) * 128 + tid] = __fmul_rn(t, 1.0f / 128.0f);
+  }
+}
+
+template <bool kF16>
+__device__ __forceinline__ void unpack_row(const uint4& u, float2 (&f)[4]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int c = 0; c < 4; ++c) {
+    if constexpr (kF16) f[c] = __half22float2(*reinterpret_cast<const __half2*>(&w[c]));
+    else f[c] = make_float2(__uint_as_float(w[c] << 16), __uint_as_float(w[c] & 0xffff0000u));
+  }
+}
+
 struct StreamCursor {  // (tensor, head, block) walked in order without divisions
   int which, bh, blk;
   __device__ __forceinline__ void advance(const int (&per_head)[3], int n_bh) {
@@ -490,90 +586,21 @@ __global__ void __launch_bounds__(kThreads, 2) pool_stats_stream_kernel(const Po
     const int st = n % kPoolStages;
     mbar_wait(bar0 + 8 * st, (n / kPoolStages) & 1);
     const uint4* tp = reinterpret_cast<const uint4*>(smem + st * kPoolStageBytes + rloc * 256 + col * 2);
-    // The block's values stay unpacked in registers for both sweeps, and the sweeps use packed fp32 instructions
-    // (add.rn.f32x2: two independent IEEE additions per instruction, so the summation order per column -- the contract
-    // with the oracle -- is untouched): at the SM clock the part sustains under its power cap this kernel is bound by
-    // issue slots, not by HBM (ncu: 57 % of the issue slots at 5.8 TB/s and 1.9 GHz before this diet).
-    float2 f[8][4];
-    auto unpack = [&](const uint4& u, int i) {
-      const uint32_t w[4] = {u.x, u.y, u.z, u.w};
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if constexpr (kF16) f[i][c] = __half22float2(*reinterpret_cast<const __half2*>(&w[c]));
-        else f[i][c] = make_float2(__uint_as_float(w[c] << 16), __uint_as_float(w[c] & 0xffff0000u));
-      }
-    };
+    float2 f[8][4];  // the block's values stay unpacked in registers for both sweeps
     if (nrows == 128 && a.head_dim == 128) {  // the common case: a whole block, nothing to predicate
 #pragma unroll
-      for (int i = 0; i < 8; ++i) unpack(tp[i * 32], i);
+      for (int i = 0; i < 8; ++i) unpack_row<kF16>(tp[i * 32], f[i]);
     } else {
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         uint4 u = make_uint4(0, 0, 0, 0);
         if (rloc + 2 * i < nrows && col < a.head_dim) u = tp[i * 32];
-        unpack(u, i);
+        unpack_row<kF16>(u, f[i]);
       }
     }
-    float2 acc[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) acc[c] = make_float2(0.f, 0.f);
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) acc[c] = __fadd2_rn(acc[c], f[i][c]);
-#pragma unroll
-    for (int c = 0; c < 4; ++c) {
-      acc[c].x = __fadd_rn(acc[c].x, __shfl_xor_sync(0xffffffffu, acc[c].x, 16));
-      acc[c].y = __fadd_rn(acc[c].y, __shfl_xor_sync(0xffffffffu, acc[c].y, 16));
-    }
-    if (lane < 16) {
-      reinterpret_cast<float4*>(&s_part[0][warp][col])[0] = make_float4(acc[0].x, acc[0].y, acc[1].x, acc[1].y);
-      reinterpret_cast<float4*>(&s_part[0][warp][col])[1] = make_float4(acc[2].x, acc[2].y, acc[3].x, acc[3].y);
-    }
-    __syncthreads();
-    if (warp == kIssuer && n + kPoolStages < n_mine) issue(n + kPoolStages);
-    if (tid < 128) {
-      float t = s_part[0][0][tid];
-#pragma unroll
-      for (int w = 1; w < 8; ++w) t = __fadd_rn(t, s_part[0][w][tid]);
-      const float m = __fmul_rn(t, 1.0f / 128.0f);
-      s_mean[tid] = m;
-      a.mean[which][((int64_t)bh * a.out_rows[which] + blk) * 128 + tid] = m;
-    }
-    if (a.mad[which] == nullptr) {  // V: means only (uniform over the CTA)
-      __syncthreads();              // s_part[0] and the stage may be written again
-      continue;
-    }
-    __syncthreads();
-    const float4 m0 = reinterpret_cast<const float4*>(&s_mean[col])[0], m1 = reinterpret_cast<const float4*>(&s_mean[col])[1];
-    const float2 negm[4] = {make_float2(-m0.x, -m0.y), make_float2(-m0.z, -m0.w), make_float2(-m1.x, -m1.y),
-                            make_float2(-m1.z, -m1.w)};
-    float dev[8];
-#pragma unroll
-    for (int c = 0; c < 8; ++c) dev[c] = 0.f;
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float2 d2 = __fadd2_rn(f[i][c], negm[c]);  // x - mean == x + (-mean) exactly
-        dev[2 * c] = __fadd_rn(dev[2 * c], fabsf(d2.x));
-        dev[2 * c + 1] = __fadd_rn(dev[2 * c + 1], fabsf(d2.y));
-      }
-#pragma unroll
-    for (int c = 0; c < 8; ++c) dev[c] = __fadd_rn(dev[c], __shfl_xor_sync(0xffffffffu, dev[c], 16));
-    if (lane < 16) {
-      reinterpret_cast<float4*>(&s_part[1][warp][col])[0] = make_float4(dev[0], dev[1], dev[2], dev[3]);
-      reinterpret_cast<float4*>(&s_part[1][warp][col])[1] = make_float4(dev[4], dev[5], dev[6], dev[7]);
-    }
-    __syncthreads();
-    if (tid < 128) {
-      float t = s_part[1][0][tid];
-#pragma unroll
-      for (int w = 1; w < 8; ++w) t = __fadd_rn(t, s_part[1][w][tid]);
-      a.mad[which][((int64_t)bh * a.n_blk[which] + blk) * 128 + tid] = __fmul_rn(t, 1.0f / 128.0f);
-    }
-    // no barrier here: the next block writes s_part[0] (last read two barriers ago) and s_mean / s_part[1] only after
-    // its own first / second barrier, which every reader above reaches first
+    pool_block(a, f, which, bh, blk, s_part, s_mean, tid, warp, lane, [&]() {
+      if (warp == kIssuer && n + kPoolStages < n_mine) issue(n + kPoolStages);
+    });
   }
   __syncthreads();
 
@@ -591,6 +618,141 @@ __global__ void __launch_bounds__(kThreads, 2) pool_stats_stream_kernel(const Po
     float* dst = a.mean[1] + ((int64_t)bh * a.out_rows[1] + a.n_blk[1] + tk) * 128 + 8 * (tid & 15);
     reinterpret_cast<float4*>(dst)[0] = make_float4(f[0], f[1], f[2], f[3]);
     reinterpret_cast<float4*>(dst)[1] = make_float4(f[4], f[5], f[6], f[7]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Kernel 0, streaming form (what rsa_qkv_prep / rsa_qkv_prep_gather launch).  Same structure as the streaming kernel 2:
+// a persistent grid, the source rows of the next blocks in flight as 256-byte bulk copies (one per token row and head:
+// the projection output is [B, rows, H*128]) into a shared-memory ring, issued by the otherwise idle warp 7; the 256
+// threads take block n from shared memory into the register layout of process_rows (normalise / rotate / round /
+// store) and pool the rounded values with pool_block.  For the fused Ulysses gather the sources are the peer-mapped
+// buffers of the owning ranks: the copies cross NVLink with three blocks (96 KB) in flight per CTA, where the per-block
+// kernel exposed one NVLink round trip (~4 us) per block.
+// Items are ordered block-major, then tensor, then head: the 3 * B * H items of one token block read the same source
+// rows (all heads of a token are contiguous) and the same rotary-table rows, which therefore stay in L1 / L2 instead
+// of being streamed from HBM once per head (the table alone is as large as L2 at the HunyuanVideo size).
+template <int kNorm, bool kGather, bool kCompact>
+__global__ void __launch_bounds__(kThreads, 2) qkv_prep_stream_kernel(const PoolArgs a, const PrepArgs p, const int n_blocks,
+                                                                      const int n_bh) {
+  extern __shared__ __align__(128) uint8_t smem[];
+  __shared__ __align__(16) float s_part[2][8][128];
+  __shared__ __align__(16) float s_mean[128];
+  using namespace ptx;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + kPoolStages * kPoolStageBytes;
+  const int per_blk = 3 * n_bh;
+  const int n_items = n_blocks * per_blk;
+  const int lo = (int)((int64_t)n_items * blockIdx.x / gridDim.x), hi = (int)((int64_t)n_items * (blockIdx.x + 1) / gridDim.x);
+  struct Cursor {
+    int jblk, which, bh;
+  };
+  auto advance = [&](Cursor& c) {
+    if (++c.bh == n_bh) {
+      c.bh = 0;
+      if (++c.which == 3) {
+        c.which = 0;
+        ++c.jblk;
+      }
+    }
+  };
+  Cursor cur;
+  cur.jblk = lo / per_blk;
+  cur.which = (lo - cur.jblk * per_blk) / n_bh;
+  cur.bh = lo - cur.jblk * per_blk - cur.which * n_bh;
+  Cursor nxt = cur;
+  if (tid == 0) {
+    for (int s = 0; s < kPoolStages; ++s) mbar_init(bar0 + 8 * s, 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+
+  // Every warp requests its own 16 rows of item `nxt` (one 256-byte copy per lane 0..15) into stage n % kPoolStages;
+  // thread 0 arms the barrier with the byte count of the whole block.
+  auto issue = [&](int n) {
+    const Cursor it = nxt;
+    advance(nxt);
+    const int st = n % kPoolStages;
+    const int rows = max(0, min(128, p.rows - it.jblk * 128));
+    const int b = it.bh / a.heads, h = it.bh - b * a.heads;
+    const uint32_t dst = sbase + st * kPoolStageBytes, bar = bar0 + 8 * st;
+    if (tid == 0) {
+      if (rows > 0) mbar_arrive_expect_tx(bar, (uint32_t)(rows * 256));
+      else mbar_arrive(bar);
+    }
+    const int r = 16 * warp + lane;
+    if (lane < 16 && r < rows) {
+      const int64_t ts = p.src_stride[it.which][1];
+      const int row = it.jblk * 128 + r;
+      if constexpr (!kGather) {
+        bulk_load_1d(dst + r * 256, p.src[it.which] + b * p.src_stride[it.which][0] + (int64_t)h * 128 + (int64_t)row * ts, 256u, bar);
+      } else {
+        const int tok = p.dst_row0 + row;  // the peer buffers hold the tokens in memory order, like the destination
+        const int owner = tok / p.src_rows;
+        const __nv_bfloat16* base = p.src_table[it.which * p.n_src + owner];
+        bulk_load_1d(dst + r * 256, base + b * p.src_stride[it.which][0] + (int64_t)(p.src_head0 + h) * 128 +
+                                        (int64_t)(tok - owner * p.src_rows) * ts, 256u, bar);
+      }
+    }
+  };
+  const int n_mine = hi - lo;
+  for (int n = 0; n < kPoolStages && n < n_mine; ++n) issue(n);
+
+  const int col = 8 * (lane & 15);
+  const int rloc = 16 * warp + (lane >> 4);
+  for (int n = 0; n < n_mine; ++n) {
+    const int which = cur.which, bh = cur.bh, jblk = cur.jblk;
+    advance(cur);
+    const int blk = p.blk0 + jblk;
+    const int b = bh / a.heads, h = bh - b * a.heads;
+    const int st = n % kPoolStages;
+    mbar_wait(bar0 + 8 * st, (n / kPoolStages) & 1);
+    const uint4* tp = reinterpret_cast<const uint4*>(smem + st * kPoolStageBytes + rloc * 256 + col * 2);
+    const int rows = p.rows - jblk * 128;  // source rows of this block (>= 1)
+    uint4 raw[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      raw[i] = make_uint4(0, 0, 0, 0);
+      if (rloc + 2 * i < rows) raw[i] = tp[i * 32];
+    }
+    process_rows<kNorm, kCompact>(p, which, b, h, jblk, warp, lane, raw);
+    const bool visual = blk < a.nq_vis;
+    bool pooled = false;
+    if (p.pool) {
+      const int valid = visual ? min(a.valid_rows[which], a.vis_len) : a.valid_rows[which];
+      const int row0 = blk * 128 + rloc;
+      // rows the pooling counts as zeros (K, V rows >= kv_zero_from; hunyuan masked_fill_ :307-308) stay stored as they are
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (row0 + 2 * i >= valid) raw[i] = make_uint4(0, 0, 0, 0);
+      if (which == 1 && !visual) {
+        // text keys scored as single tokens: fp32 rows [NQ, NQ + a) of k_cat (hunyuan :193-194)
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int t = (blk - a.nq_vis) * 128 + rloc + 2 * i;  // text token index
+          if (t < a.text_keys) {
+            float f[8];
+            unpack8<false>(raw[i], f);
+            float* dstk = a.mean[1] + ((int64_t)bh * a.out_rows[1] + a.n_blk[1] + t) * 128 + col;
+            reinterpret_cast<float4*>(dstk)[0] = make_float4(f[0], f[1], f[2], f[3]);
+            reinterpret_cast<float4*>(dstk)[1] = make_float4(f[4], f[5], f[6], f[7]);
+          }
+        }
+      }
+      pooled = blk < a.n_blk[which];  // uniform over the CTA
+    }
+    if (pooled) {
+      float2 f[8][4];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) unpack_row<false>(raw[i], f[i]);
+      pool_block(a, f, which, bh, blk, s_part, s_mean, tid, warp, lane, [&]() {
+        if (n + kPoolStages < n_mine) issue(n + kPoolStages);
+      });
+    } else {
+      __syncthreads();  // every thread has taken its rows out of the stage
+      if (n + kPoolStages < n_mine) issue(n + kPoolStages);
+    }
   }
 }
 
@@ -743,12 +905,40 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
     a.gap = rm.gap;
   }
   const int blocks = (p->rows + 127) / 128;
-  dim3 grid(3 * d->batch * d->heads, blocks);
-  // 2 CTAs per SM (about 100 registers): capping at 3 or 4 CTAs spills and is no faster (1.24 / 1.25 / 2.17 ms at C3b)
   const bool compact = pa.rope_compact && pa.rope_rows > 0;
+  static int form = -1;  // RSA_PREP_FORM=0: the per-block kernel (A/B timing); default: the streaming kernel
+  static int sms = 0;
+  if (form < 0) {
+    const char* e = getenv("RSA_PREP_FORM");
+    form = (e && e[0] == '0') ? 0 : 1;
+    int dev = 0;
+    RSA_CUDA_CHECK(cudaGetDevice(&dev));
+    RSA_CUDA_CHECK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  }
+  const int n_bh = d->batch * d->heads;
+  const int64_t items = (int64_t)blocks * 3 * n_bh;
+  if (items > 0x7fffffffLL) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep: too many blocks");
+  const int sgrid = (int)(items < 2 * sms ? items : 2 * sms);
+  dim3 grid(3 * d->batch * d->heads, blocks);
+  // per-block form: 2 CTAs per SM (about 100 registers): capping at 3 or 4 CTAs spills and is no faster (1.24 / 1.25 / 2.17 ms at C3b)
+#define RSA_PREP_STREAM(NORM, GATHER, COMPACT)                                                                          \
+  do {                                                                                                                  \
+    static bool cfg = false;                                                                                            \
+    if (!cfg) {                                                                                                         \
+      RSA_CUDA_CHECK(cudaFuncSetAttribute(qkv_prep_stream_kernel<NORM, GATHER, COMPACT>,                                 \
+                                          cudaFuncAttributeMaxDynamicSharedMemorySize, kPoolSmem));                     \
+      RSA_CUDA_CHECK(cudaFuncSetAttribute(qkv_prep_stream_kernel<NORM, GATHER, COMPACT>,                                 \
+                                          cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared)); \
+      cfg = true;                                                                                                       \
+    }                                                                                                                   \
+    qkv_prep_stream_kernel<NORM, GATHER, COMPACT><<<sgrid, kThreads, kPoolSmem, s>>>(a, pa, blocks, n_bh);               \
+  } while (0)
 #define RSA_PREP_LAUNCH(NORM, GATHER)                                                               \
   do {                                                                                              \
-    if (compact) pool_stats_kernel<true, 2, NORM, GATHER, true><<<grid, kThreads, 0, s>>>(a, pa);   \
+    if (form == 1) {                                                                                \
+      if (compact) RSA_PREP_STREAM(NORM, GATHER, true);                                             \
+      else RSA_PREP_STREAM(NORM, GATHER, false);                                                    \
+    } else if (compact) pool_stats_kernel<true, 2, NORM, GATHER, true><<<grid, kThreads, 0, s>>>(a, pa);   \
     else pool_stats_kernel<true, 2, NORM, GATHER, false><<<grid, kThreads, 0, s>>>(a, pa);          \
   } while (0)
   if (route) {
@@ -762,6 +952,7 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
       default: RSA_PREP_LAUNCH(0, false); break;
     }
   }
+#undef RSA_PREP_STREAM
 #undef RSA_PREP_LAUNCH
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;

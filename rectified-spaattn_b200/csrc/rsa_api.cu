@@ -499,7 +499,6 @@ static int validate_route(const rsa_attn_desc* d, const rsa_peer_route* r, bool 
   if (r->rows_per_rank < 1 || (int64_t)r->rows_per_rank * r->n_ranks != d->seq)
     RSA_FAIL(RSA_ERR_ARG, "peer route: %d ranks x %d rows != seq %d", r->n_ranks, r->rows_per_rank, d->seq);
   if (r->heads_total != r->n_ranks * d->heads) RSA_FAIL(RSA_ERR_ARG, "peer route: heads_total != n_ranks * heads");
-  if (row_map(d).gap != 0) RSA_FAIL(RSA_ERR_UNSUPPORTED, "peer route: ragged visual segments are not supported");
   if (need_src && (!r->src_table || r->src_stride[0] < 0 || r->src_stride[1] < r->heads_total * 128 || r->src_stride[0] % 8 || r->src_stride[1] % 8))
     RSA_FAIL(RSA_ERR_ARG, "peer route: source table / strides");
   if (need_out && (!r->out_table || r->out_stride[0] < 0 || r->out_stride[1] < r->heads_total * 128 || r->out_stride[0] % 8 || r->out_stride[1] % 8))
@@ -514,7 +513,14 @@ extern "C" int rsa_qkv_prep_gather(const rsa_prep_desc* p, const rsa_attn_desc* 
   if ((rc = validate_route(d, route, true, false)) != RSA_OK) return rc;
   if (!p || !q || !k || !v) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: null pointer");
   if (d->dtype != RSA_DTYPE_BF16 || d->head_dim != RSA_HEAD_DIM) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep_gather: bf16 and head_dim 128 only");
-  if (p->rows != d->seq || p->dst_row != 0) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rows must be seq and dst_row 0");
+  // like rsa_qkv_prep: the whole sequence in one call, or -- ragged visual segment -- the visual tokens (dst_row 0) and
+  // the text tokens (dst_row = visual token count) in two; source token = dst_row + row either way
+  const RowMap rm = row_map(d);
+  const bool whole = p->dst_row == 0 && p->rows == d->seq && rm.gap == 0;
+  const bool vis = p->dst_row == 0 && p->rows == rm.vis_len && d->family == RSA_FAMILY_JOINT;
+  const bool txt = p->dst_row == rm.vis_len && p->rows == d->seq - rm.vis_len && d->family == RSA_FAMILY_JOINT;
+  if (!whole && !vis && !txt)
+    RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rows / dst_row must name the whole sequence, the visual tokens or the text tokens");
   if (p->norm != 0 && p->norm != 1) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep_gather: norm must be 0 or 1");
   if (p->norm && (!p->q_weight || !p->k_weight)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: norm weights are null");
   if (p->rope_rows < 0 || p->rope_rows > p->rows) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rope_rows out of range");

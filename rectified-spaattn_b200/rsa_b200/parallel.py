@@ -172,7 +172,16 @@ class FusedUlysses:
             p.cos, p.sin = cos.data_ptr(), sin.data_ptr()
         self._barrier()
         st = ops._stream(self.device)
+        gap = plan.desc.vis_len and plan.desc.nq_blocks * 128 - plan.desc.vis_len
         with torch.cuda.device(self.device):
+            if gap:     # ragged visual segment: the block structure restarts at the text tokens -> two gathers
+                nv = plan.desc.vis_len
+                p.rows, p.dst_row = nv, 0
+                p.rope_rows = min(p.rope_rows, nv)
+                N.check(self._lib.rsa_qkv_prep_gather(C.byref(p), C.byref(plan.desc), C.byref(self.route),
+                                                      plan.q.data_ptr(), plan.k.data_ptr(), plan.v.data_ptr(), 1,
+                                                      plan.ws.data_ptr(), plan.ws_bytes, st), "rsa_qkv_prep_gather")
+                p.rows, p.dst_row, p.rope_rows = self.seq - nv, nv, 0
             N.check(self._lib.rsa_qkv_prep_gather(C.byref(p), C.byref(plan.desc), C.byref(self.route), plan.q.data_ptr(),
                                                   plan.k.data_ptr(), plan.v.data_ptr(), 1, plan.ws.data_ptr(),
                                                   plan.ws_bytes, st), "rsa_qkv_prep_gather")

@@ -291,7 +291,8 @@ int rsa_peer_close(void* ptr);
  *                            rank's result buffer.
  * The caller provides the barriers: every rank's sources written before the gather, every rank's scatter finished
  * before the results are read (a zero-byte collective on the stream; rsa_b200/parallel.py uses an all_reduce of one
- * element).  Restrictions: seq == n_ranks * rows_per_rank, prep norm 0 or 1.  A ragged visual segment (HunyuanVideo 129
+ * element).  Restrictions: seq == n_ranks * rows_per_rank and heads_total == n_ranks * heads (even shards); prep norm
+ * 0, 1, or 2 (2 needs rinv_table).  A ragged visual segment (HunyuanVideo 129
  * frames) takes two gather calls like rsa_qkv_prep: the visual tokens (dst_row 0) and the text tokens (dst_row = visual
  * token count); the source token of row r is dst_row + r in both. */
 typedef struct rsa_peer_route {
@@ -304,7 +305,18 @@ typedef struct rsa_peer_route {
   void* const* out_table;       /* DEVICE array [n_ranks]: every rank's result buffer [batch, rows_per_rank,       */
                                 /* heads_total, 128] bf16, as mapped in this process                               */
   int64_t out_stride[2];        /* (batch, token) element strides of those buffers                                 */
+  const float* const* rinv_table; /* prep norm 2 (Wan: RMSNorm over all heads_total*128 channels of a token) only:  */
+                                /* DEVICE array [2][n_ranks] (q, k): every rank's per-token statistics              */
+                                /* rsqrt(mean(x^2) + eps), [batch, rows_per_rank] fp32, which the OWNING rank computes */
+                                /* from its full rows with rsa_row_rms before the barrier; NULL otherwise            */
 } rsa_peer_route;
+
+/* Per-token RMS statistic of the q and k projection rows over all `channels` (= heads_total * 128) channels:
+ * rinv[b * rows + r] = rsqrt(mean(x[b, r, :]^2) + eps), the fp32 value diffusers' RMSNorm multiplies by (Wan's norm_q /
+ * norm_k span all heads, rectified_wan21_attn.py:423-426).  rsa_qkv_prep (norm 2) runs this itself; under the fused
+ * Ulysses exchange every rank runs it on the tokens it owns so that the gathering ranks need not see whole rows. */
+int rsa_row_rms(const void* q_src, const void* k_src, int batch, int rows, int channels, const int64_t q_stride[2],
+                const int64_t k_stride[2], float eps, float* rinv_q, float* rinv_k, void* stream);
 
 int rsa_qkv_prep_gather(const rsa_prep_desc* p, const rsa_attn_desc* d, const rsa_peer_route* route, void* q, void* k,
                         void* v, int pool, void* workspace, size_t workspace_bytes, void* stream);

@@ -52,6 +52,7 @@ struct PrepArgs {
   int pool;                     // also pool the produced rows
   // fused Ulysses gather: source row r lives on rank r / src_rows (peer-mapped buffers), head h is head src_head0 + h there
   const __nv_bfloat16* const* src_table;  // device array [3][n_src] or nullptr
+  const float* const* rinv_table;         // gather with the norm across heads: device array [2][n_src] of [B, src_rows] fp32
   int n_src, src_rows, src_head0;
 };
 
@@ -118,7 +119,7 @@ __device__ __forceinline__ RopeRow load_rope(const PrepArgs& p, int r, int col, 
 // kNorm: 0 none, 1 RMSNorm over head_dim, 2 RMSNorm across heads (row statistic precomputed), 3 LayerNorm over head_dim.
 // kGather: rows come from peer-mapped buffers.  kCompact: one (cos, sin)-pair table.  Compile-time so that each form
 // carries only its own code and registers (with all of them behind run-time flags the HunyuanVideo form lost 40 %).
-template <int kNorm, bool kCompact>
+template <int kNorm, bool kCompact, bool kGather>
 __device__ __forceinline__ void process_rows(const PrepArgs& p, int which, int b, int h, int jblk, int warp, int lane,
                                              uint4 (&raw)[8]);
 
@@ -150,12 +151,12 @@ __device__ __forceinline__ void prep_rows(const PrepArgs& p, int which, int b, i
       }
     }
   }
-  process_rows<kNorm, kCompact>(p, which, b, h, jblk, warp, lane, raw);
+  process_rows<kNorm, kCompact, kGather>(p, which, b, h, jblk, warp, lane, raw);
 }
 
 // raw[it] = source row jblk * 128 + 16 warp + 2 it + (lane >> 4), columns 8 (lane & 15) .. +7 of head h (zeros beyond the
 // source): normalise / rotate / round, store to the destination, and leave the rounded values in raw.
-template <int kNorm, bool kCompact>
+template <int kNorm, bool kCompact, bool kGather>
 __device__ __forceinline__ void process_rows(const PrepArgs& p, int which, int b, int h, int jblk, int warp, int lane,
                                              uint4 (&raw)[8]) {
   const int col = 8 * (lane & 15);
@@ -170,8 +171,10 @@ __device__ __forceinline__ void process_rows(const PrepArgs& p, int which, int b
     return;
   }
   float wgt[8];
-  if constexpr (kNorm != 0) unpack8(__ldg(reinterpret_cast<const uint4*>(p.w[which] + h * p.w_head_stride + col)), wgt);
-  const float* rinv_rows = kNorm == 2 ? p.row_rinv[which] + (int64_t)b * p.rows : nullptr;
+  // (src_head0: under the fused Ulysses gather this rank's head h is head src_head0 + h of the token's row; else 0)
+  if constexpr (kNorm != 0)
+    unpack8(__ldg(reinterpret_cast<const uint4*>(p.w[which] + (p.src_head0 + h) * p.w_head_stride + col)), wgt);
+  const float* rinv_rows = (kNorm == 2 && !kGather) ? p.row_rinv[which] + (int64_t)b * p.rows : nullptr;
   float bia[8];
   if constexpr (kNorm == 3) unpack8(__ldg(reinterpret_cast<const uint4*>(p.bias[which] + col)), bia);
   RopeRow next = load_rope<kCompact>(p, r0, col, r0 < p.rows && r0 < p.rope_rows);
@@ -212,7 +215,12 @@ __device__ __forceinline__ void process_rows(const PrepArgs& p, int which, int b
     } else if constexpr (kNorm != 0) {
       float rinv;
       if constexpr (kNorm == 2) {  // norm across heads: the row statistic was computed over all H*128 channels beforehand
-        rinv = live ? __ldg(rinv_rows + r) : 0.f;
+        if constexpr (kGather) {  // the owning rank computed the statistic from its full rows (rsa_row_rms)
+          const int tok = p.dst_row0 + r, owner = live ? tok / p.src_rows : 0;
+          rinv = live ? __ldg(p.rinv_table[which * p.n_src + owner] + (int64_t)b * p.src_rows + (tok - owner * p.src_rows)) : 0.f;
+        } else {
+          rinv = live ? __ldg(rinv_rows + r) : 0.f;
+        }
       } else {
         // mean(x^2) over the 128 channels of this head: 8 per lane, then a fixed butterfly over the 16 lanes
         float ss = 0.f;
@@ -716,7 +724,7 @@ __global__ void __launch_bounds__(kThreads, 2) qkv_prep_stream_kernel(const Pool
       raw[i] = make_uint4(0, 0, 0, 0);
       if (rloc + 2 * i < rows) raw[i] = tp[i * 32];
     }
-    process_rows<kNorm, kCompact>(p, which, b, h, jblk, warp, lane, raw);
+    process_rows<kNorm, kCompact, kGather>(p, which, b, h, jblk, warp, lane, raw);
     const bool visual = blk < a.nq_vis;
     bool pooled = false;
     if (p.pool) {
@@ -837,6 +845,15 @@ int launch_pool_stats(const rsa_attn_desc* d, const void* q, const void* k, cons
   return RSA_OK;
 }
 
+int launch_row_rms(const void* q_src, const void* k_src, int batch, int rows, int channels, const int64_t* qs,
+                   const int64_t* ks, float eps, float* rq, float* rk, cudaStream_t s) {
+  dim3 g((rows + 7) / 8, batch, 2);
+  row_rms_kernel<<<g, 256, 0, s>>>((const __nv_bfloat16*)q_src, (const __nv_bfloat16*)k_src, qs[0], qs[1], ks[0], ks[1], rows,
+                                   channels, eps, rq, rk);
+  RSA_CUDA_CHECK(cudaGetLastError());
+  return RSA_OK;
+}
+
 int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* q_src, const void* k_src,
                     const void* v_src, const rsa_peer_route* route, void* q, void* k, void* v, char* ws,
                     const WsLayout* L, cudaStream_t s) {
@@ -860,7 +877,7 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
   pa.bias[0] = (const __nv_bfloat16*)p->q_bias;
   pa.bias[1] = (const __nv_bfloat16*)p->k_bias;
   pa.row_rinv[0] = pa.row_rinv[1] = nullptr;
-  if (p->norm == 2) {
+  if (p->norm == 2 && !route) {
     float* rq = p->row_scratch;
     float* rk = rq + (int64_t)d->batch * p->rows;
     dim3 g((p->rows + 7) / 8, d->batch, 2);
@@ -882,9 +899,11 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
   pa.blk0 = p->dst_row == 0 ? 0 : rm.nq_vis;
   pa.pool = L != nullptr;
   pa.src_table = nullptr;
+  pa.rinv_table = nullptr;
   pa.n_src = pa.src_rows = pa.src_head0 = 0;
   if (route) {
     pa.src_table = (const __nv_bfloat16* const*)route->src_table;
+    pa.rinv_table = route->rinv_table;
     pa.n_src = route->n_ranks;
     pa.src_rows = route->rows_per_rank;
     pa.src_head0 = route->rank * d->heads;
@@ -943,6 +962,7 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
   } while (0)
   if (route) {
     if (p->norm == 1) RSA_PREP_LAUNCH(1, true);
+    else if (p->norm == 2) RSA_PREP_LAUNCH(2, true);
     else RSA_PREP_LAUNCH(0, true);
   } else {
     switch (p->norm) {

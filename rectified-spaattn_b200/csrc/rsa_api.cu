@@ -521,7 +521,9 @@ extern "C" int rsa_qkv_prep_gather(const rsa_prep_desc* p, const rsa_attn_desc* 
   const bool txt = p->dst_row == rm.vis_len && p->rows == d->seq - rm.vis_len && d->family == RSA_FAMILY_JOINT;
   if (!whole && !vis && !txt)
     RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rows / dst_row must name the whole sequence, the visual tokens or the text tokens");
-  if (p->norm != 0 && p->norm != 1) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep_gather: norm must be 0 or 1");
+  if (p->norm < 0 || p->norm > 2) RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_qkv_prep_gather: norm must be 0, 1 or 2");
+  if (p->norm == 2 && !route->rinv_table)
+    RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: norm 2 needs route->rinv_table (rsa_row_rms on every owning rank)");
   if (p->norm && (!p->q_weight || !p->k_weight)) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: norm weights are null");
   if (p->rope_rows < 0 || p->rope_rows > p->rows) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rope_rows out of range");
   if (p->rope_rows > 0 && (!p->cos || (!p->sin && !p->rope_compact))) RSA_FAIL(RSA_ERR_ARG, "rsa_qkv_prep_gather: rotary tables are null");
@@ -529,6 +531,16 @@ extern "C" int rsa_qkv_prep_gather(const rsa_prep_desc* p, const rsa_attn_desc* 
   if (pool && (rc = check_ws(d, workspace, bytes, &L)) != RSA_OK) return rc;
   return launch_qkv_prep(p, d, nullptr, nullptr, nullptr, route, q, k, v, (char*)workspace, pool ? &L : nullptr,
                          (cudaStream_t)stream);
+}
+
+extern "C" int rsa_row_rms(const void* q_src, const void* k_src, int batch, int rows, int channels,
+                           const int64_t q_stride[2], const int64_t k_stride[2], float eps, float* rinv_q, float* rinv_k,
+                           void* stream) {
+  if (!q_src || !k_src || !rinv_q || !rinv_k || !q_stride || !k_stride) RSA_FAIL(RSA_ERR_ARG, "rsa_row_rms: null pointer");
+  if (batch < 1 || rows < 1 || channels < 8 || channels % 8) RSA_FAIL(RSA_ERR_ARG, "rsa_row_rms: bad sizes");
+  if (((uintptr_t)q_src | (uintptr_t)k_src) % 16 || q_stride[1] % 8 || k_stride[1] % 8 || q_stride[0] % 8 || k_stride[0] % 8)
+    RSA_FAIL(RSA_ERR_UNSUPPORTED, "rsa_row_rms: rows must be 16-byte aligned");
+  return launch_row_rms(q_src, k_src, batch, rows, channels, q_stride, k_stride, eps, rinv_q, rinv_k, (cudaStream_t)stream);
 }
 
 extern "C" int rsa_rectified_attention_pooled_scatter(const rsa_attn_desc* d, const void* q, const void* k,

@@ -53,7 +53,7 @@ class PrepDesc(C.Structure):
 class PeerRoute(C.Structure):
     _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("rows_per_rank", C.c_int32), ("heads_total", C.c_int32),
                 ("src_table", C.c_void_p), ("src_stride", C.c_int64 * 2), ("out_table", C.c_void_p),
-                ("out_stride", C.c_int64 * 2)]
+                ("out_stride", C.c_int64 * 2), ("rinv_table", C.c_void_p)]
 
 
 EXPORTS = [
@@ -66,7 +66,7 @@ EXPORTS = [
     "rsa_peer_free", "rsa_peer_export", "rsa_peer_open", "rsa_peer_close", "rsa_qkv_prep_gather",
     "rsa_rectified_attention_pooled_scatter", "rsa_rectified_attention_reuse",
     "rsa_debug_attention_grid_slot", "rsa_debug_front_text_heads", "rsa_gilbert_xyz2d_r",
-    "rsa_attn_desc_size", "rsa_prep_desc_size", "rsa_peer_route_size",
+    "rsa_attn_desc_size", "rsa_prep_desc_size", "rsa_peer_route_size", "rsa_row_rms",
 ]
 
 _lib = None
@@ -122,6 +122,7 @@ def lib():
     L.rsa_qkv_prep_gather.argtypes = [C.POINTER(PrepDesc), C.POINTER(AttnDesc), C.POINTER(PeerRoute), p, p, p, i32, p,
                                       sz, p]
     L.rsa_rectified_attention_pooled_scatter.argtypes = [C.POINTER(AttnDesc), p, p, p, C.POINTER(PeerRoute), p, sz, p]
+    L.rsa_row_rms.argtypes = [p, p, i32, i32, i32, C.POINTER(i64), C.POINTER(i64), C.c_float, p, p, p]
     L.rsa_peer_alloc.argtypes = [sz, C.POINTER(p)]
     L.rsa_peer_free.argtypes = [p]
     L.rsa_peer_export.argtypes = [p, p]

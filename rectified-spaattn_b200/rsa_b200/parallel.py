@@ -116,18 +116,21 @@ class FusedUlysses:
         self._lib, self._own, self._opened = L, [], []
         n_elems = batch * self.rows * heads_total * 128
         ptrs = []
-        for _ in range(4):                                   # q, k, v sources and the result
+        # q, k, v sources, the result, and the per-token RMS statistics of q and k (Wan's norm across heads: every rank
+        # computes them from the full rows of ITS tokens, the gathering ranks read them over NVLink)
+        sizes = [n_elems * 2] * 4 + [batch * self.rows * 4] * 2
+        for nbytes in sizes:
             ptr = C.c_void_p()
-            N.check(L.rsa_peer_alloc(n_elems * 2, C.byref(ptr)), "rsa_peer_alloc")
+            N.check(L.rsa_peer_alloc(nbytes, C.byref(ptr)), "rsa_peer_alloc")
             self._own.append(ptr.value)
             h = (C.c_char * 64)()
             N.check(L.rsa_peer_export(ptr, h), "rsa_peer_export")
             ptrs.append(bytes(h))
         everyone = [None] * self.world
         dist.all_gather_object(everyone, ptrs, group=group)
-        table = torch.empty(4, self.world, dtype=torch.int64)
+        table = torch.empty(6, self.world, dtype=torch.int64)
         for r in range(self.world):
-            for t in range(4):
+            for t in range(6):
                 if r == self.rank:
                     table[t, r] = self._own[t]
                 else:
@@ -137,7 +140,7 @@ class FusedUlysses:
                     table[t, r] = pp.value
         self._table = table.to(self.device)
         shape = (batch, self.rows, heads_total * 128)
-        self.q_src, self.k_src, self.v_src, self.out = (_peer_tensor(p, shape) for p in self._own)
+        self.q_src, self.k_src, self.v_src, self.out = (_peer_tensor(p, shape) for p in self._own[:4])
         self._flag = torch.zeros(1, device=self.device)
         q, k, v = (torch.empty(batch, self.heads, self.seq, 128, dtype=torch.bfloat16, device=self.device)
                    for _ in range(3))
@@ -148,6 +151,7 @@ class FusedUlysses:
         route.out_table = self._table[3].data_ptr()
         route.src_stride[0], route.src_stride[1] = self.rows * heads_total * 128, heads_total * 128
         route.out_stride[0], route.out_stride[1] = self.rows * heads_total * 128, heads_total * 128
+        route.rinv_table = self._table[4:6].data_ptr()
         self.route = route
 
     def _barrier(self):
@@ -165,6 +169,17 @@ class FusedUlysses:
             ws_ = [w.detach().to(device=self.device, dtype=torch.bfloat16).contiguous() for w in (q_weight, k_weight)]
             keep += ws_
             p.norm, p.eps, p.q_weight, p.k_weight = 1, float(eps), ws_[0].data_ptr(), ws_[1].data_ptr()
+            if all(w.numel() == self.heads_total * 128 for w in ws_):
+                # RMSNorm over all heads*128 channels of a token (Wan, rectified_wan21_attn.py:423-426): the statistic
+                # needs whole rows, which only the owning rank holds -> computed here, before the barrier
+                p.norm = 2
+                st2 = (C.c_int64 * 2)(self.rows * self.heads_total * 128, self.heads_total * 128)
+                with torch.cuda.device(self.device):
+                    N.check(self._lib.rsa_row_rms(self._own[0], self._own[1], self.batch, self.rows,
+                                                  self.heads_total * 128, st2, st2, float(eps), self._own[4],
+                                                  self._own[5], ops._stream(self.device)), "rsa_row_rms")
+            elif any(w.numel() != 128 for w in ws_):
+                raise RuntimeError("norm weights must have 128 (per head) or heads*128 (across heads) elements")
         if rope is not None:
             cos, sin = (t.detach().to(device=self.device, dtype=torch.float32).contiguous() for t in rope)
             keep += [cos, sin]

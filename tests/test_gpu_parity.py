@@ -612,6 +612,16 @@ def test_fused_ulysses_two_gpus(dev):
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    # c2 = Wan: RMSNorm across heads (each rank computes the statistic of its own tokens, the gathering ranks read it over
+    # NVLink); the bit reference is the single-GPU call (the NCCL form's norm is PyTorch's, other reduction order)
+    assert line["fused_equals_single_gpu_bitwise_rank0"] and line["fraction_of_elements_equal_to_nccl_form_rank0"] > 0.9
+    # HunyuanVideo form (per-head norm) on a small RAGGED visual segment: two gather calls, all three forms bit-identical
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                        "--master-addr", "127.0.0.1", "--master-port", "29578",
+                        os.path.join(repo, "tools", "check_fused_ulysses.py"), "c3b"],
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert line["fused_equals_nccl_form_bitwise_all_ranks"] and line["fused_equals_single_gpu_bitwise_rank0"]
 
 

@@ -501,7 +501,6 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c3b", choices=list(WORKLOADS))
     ap.add_argument("--regime", default="walk", choices=["walk", "iid", "cluster"])
-    ap.add_argument("--attn-impl", type=int, default=0, help="0 = tcgen05 kernel (product); 1 = mma.sync cross-check")
     ap.add_argument("--attn-flags", type=int, default=0,
                     help="kernel 4 A/B switches (rsa_debug_set_attention_flags): 4 = head_dim 64 through the 128-column "
                          "form, 16 = kernel 4 grid in the former order")
@@ -567,7 +566,6 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     assert native.lib().rsa_device_ok() == 1
-    ops.set_attention_impl(args.attn_impl)
     ops.set_attention_flags(args.attn_flags)
 
     heads = wp["heads"]
@@ -748,7 +746,7 @@ def main():
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": config, "ms_per_attn_call": ms_step, "kept_pair_density": density, "stages_ms": stages,
             "mask_reuse": reuse,
-            "attention_impl": "tcgen05" if args.attn_impl == 0 else "mma.sync cross-check",
+            "attention_impl": "tcgen05 (the library's only attention kernel)",
             "attention_flags": args.attn_flags,
             "gpu_launches": 7 * args.steps,
             "roofline": {"bound": "tensor", "kernel": "rect_attn (kernel 4)", "achieved": achieved,

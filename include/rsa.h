@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RSA_VERSION 103
+#define RSA_VERSION 104
 #define RSA_BLOCK 128
 #define RSA_HEAD_DIM 128
 #define RSA_MAX_ENTRIES 2048 /* max sortable entries per query block: NQ (+1 for the text aggregate) */
@@ -341,10 +341,6 @@ int rsa_masked_attention(const void* q, const void* k, const void* v, void* out,
                          const int64_t v_stride[2], const int64_t o_stride[2], const uint8_t* block_mask,
                          int n_q_blocks, int n_kv_blocks, void* workspace, size_t workspace_bytes, void* stream,
                          int dtype /* enum rsa_dtype */, int head_dim /* 128 or 64 */);
-
-/* Selects the attention kernel implementation for this process: 0 = tcgen05/TMEM/TMA (product path),
- * 1 = mma.sync cross-check kernel (tests only).  Returns the previous value. */
-int rsa_set_attention_impl(int impl);
 
 /* Bring-up hook (tests only): while non-null, the tcgen05 kernel's CTA for query tile 0 of batch*head 0 writes, as
  * fp32, S of its first kept block [128x128], the un-normalised O [128x128], the row sums l [128] and the row

@@ -10,7 +10,6 @@
 namespace rsa {
 
 static thread_local char g_err[512] = "";
-int g_attention_impl = 0;
 float* g_attention_dbg = nullptr;
 // RSA_ATTN_FLAGS: switches that stay set for the whole process (A/B runs of the test suite), OR-ed into whatever
 // rsa_debug_set_attention_flags sets
@@ -212,10 +211,6 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
 // reschedule = false: the kept lists have not changed since the last launch on this workspace, so neither has the
 // pair schedule kernel 4 walks (mask re-use)
 static int launch_attention(const AttnArgs& a, cudaStream_t s, bool reschedule = true) {
-  if (g_attention_impl == 1) {
-    if (a.f16 || a.head_dim != RSA_HEAD_DIM) RSA_FAIL(RSA_ERR_UNSUPPORTED, "the mma.sync cross-check kernel is bf16 / head_dim 128 only");
-    return launch_attention_mma(a, s);
-  }
   int rc = reschedule ? launch_pair_schedule(a, s) : RSA_OK;
   return rc != RSA_OK ? rc : launch_attention_tc5(a, s);
 }
@@ -338,12 +333,6 @@ extern "C" int rsa_device_ok(void) {
   cudaDeviceProp p;
   if (cudaGetDeviceProperties(&p, dev) != cudaSuccess) return 0;
   return p.major == 10 ? 1 : 0;
-}
-
-extern "C" int rsa_set_attention_impl(int impl) {
-  const int prev = g_attention_impl;
-  g_attention_impl = impl == 1 ? 1 : 0;
-  return prev;
 }
 
 extern "C" void rsa_debug_set_attention_dump(float* device_buffer) { g_attention_dbg = device_buffer; }
@@ -552,7 +541,6 @@ extern "C" int rsa_rectified_attention_pooled_scatter(const rsa_attn_desc* d, co
   if ((rc = validate_route(d, route, false, true)) != RSA_OK) return rc;
   if (d->head_dim != RSA_HEAD_DIM) RSA_FAIL(RSA_ERR_UNSUPPORTED, "the scatter epilogue is built for head_dim 128");
   if (!q || !k || !v) RSA_FAIL(RSA_ERR_ARG, "rsa_rectified_attention_pooled_scatter: null tensor");
-  if (g_attention_impl != 0) RSA_FAIL(RSA_ERR_UNSUPPORTED, "the scatter epilogue exists in the tcgen05 kernel only");
   char* ws = (char*)workspace;
   cudaStream_t s = (cudaStream_t)stream;
   if ((rc = launch_block_scores(d, ws, L, s)) != RSA_OK) return rc;

@@ -162,13 +162,12 @@ struct AttnArgs {
   float* dbg;               // bring-up dump of tile 0 / bh 0 (rsa_debug_set_attention_dump), normally null
 };
 
-int launch_attention_mma(const AttnArgs& a, cudaStream_t s);      // mma.sync cross-check kernel
+int launch_attention_mma(const AttnArgs& a, cudaStream_t s);      // mma.sync cross-check kernel: tests/xcheck only, not in the product library
 int launch_attention_tc5(const AttnArgs& a, cudaStream_t s);      // tcgen05 / TMEM / TMA kernel
 int launch_pair_schedule(const AttnArgs& a, cudaStream_t s);  // kept lists -> sched_idx / pair_shared
 int launch_mask_to_lists(const uint8_t* mask, int bh, int nq, int nkv, int kv_blocks_valid, uint16_t* kept_idx,
                          int32_t* kept_cnt, cudaStream_t s);
 
-extern int g_attention_impl;
 extern float* g_attention_dbg;
 extern int g_attention_dbg_flags;
 

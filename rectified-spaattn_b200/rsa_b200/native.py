@@ -60,7 +60,7 @@ EXPORTS = [
     "rsa_last_error_string", "rsa_version", "rsa_device_ok", "rsa_gilbert_map", "rsa_gilbert_block_neighbors",
     "rsa_permute_rows", "rsa_attn_workspace_bytes", "rsa_attn_workspace_view", "rsa_pool_stats",
     "rsa_block_scores", "rsa_block_select", "rsa_rect_c", "rsa_sparse_attention", "rsa_rectified_attention",
-    "rsa_masked_attention_workspace_bytes", "rsa_masked_attention", "rsa_set_attention_impl",
+    "rsa_masked_attention_workspace_bytes", "rsa_masked_attention",
     "rsa_debug_set_attention_dump", "rsa_debug_set_attention_flags", "rsa_host_call_scratch_bytes",
     "rsa_rectified_attention_host", "rsa_qkv_prep", "rsa_rectified_attention_pooled", "rsa_peer_alloc",
     "rsa_peer_free", "rsa_peer_export", "rsa_peer_open", "rsa_peer_close", "rsa_qkv_prep_gather",
@@ -72,7 +72,7 @@ EXPORTS = [
 _lib = None
 
 
-ABI_VERSION = 103
+ABI_VERSION = 104
 
 
 def lib():
@@ -128,7 +128,6 @@ def lib():
     L.rsa_peer_export.argtypes = [p, p]
     L.rsa_peer_open.argtypes = [p, C.POINTER(p)]
     L.rsa_peer_close.argtypes = [p]
-    L.rsa_set_attention_impl.argtypes = [i32]
     L.rsa_debug_set_attention_dump.argtypes = [p]
     L.rsa_debug_set_attention_dump.restype = None
     L.rsa_debug_set_attention_flags.argtypes = [i32]
@@ -138,9 +137,7 @@ def lib():
     L.rsa_debug_front_text_heads.argtypes = [C.POINTER(AttnDesc)]
     L.rsa_debug_front_text_heads.restype = i32
     for n in EXPORTS:
-        f = getattr(L, n)
-        if f.restype is C.c_int and n not in ("rsa_version", "rsa_device_ok", "rsa_set_attention_impl"):
-            pass
+        getattr(L, n)            # every symbol of include/rsa.h must be there
     _lib = L
     return L
 

@@ -539,8 +539,3 @@ def set_attention_flags(flags):
     """Bring-up / cross-check switches of kernel 4 (rsa_debug_set_attention_flags); bit 2 = head_dim 64 through the
     128-column instantiation."""
     N.lib().rsa_debug_set_attention_flags(int(flags))
-
-
-def set_attention_impl(impl):
-    """0 = tcgen05 kernel (product), 1 = mma.sync cross-check kernel (tests only)."""
-    return N.lib().rsa_set_attention_impl(int(impl))

@@ -441,3 +441,18 @@ def test_product_never_imports_the_oracle():
     imports = re.findall(r"^\s*from oracle import .*$", bench_src, re.M)
     assert imports and all(line.strip() in body for line in imports)
     assert not re.search(r"^\s*(from|import)\s+(rsa_b200|rectified_spaattn|utils)\b", body, re.M)
+
+
+def test_product_library_has_one_attention_kernel():
+    """north_star: "no multi-backend dispatch".  The mma.sync cross-check implementation of kernel 4 lives in the tests'
+    own library (tests/xcheck/librsa_xcheck.so); the product library exports no switch and contains no such kernel."""
+    import subprocess
+    syms = subprocess.run(["nm", "-D", "--defined-only", N.LIB_PATH], capture_output=True, text=True, check=True).stdout
+    assert "rsa_set_attention_impl" not in syms and "attn_mma" not in syms
+    everything = subprocess.run(["nm", N.LIB_PATH], capture_output=True, text=True).stdout
+    assert "attn_mma" not in everything
+    assert not hasattr(ops, "set_attention_impl")
+    xlib = os.path.join(REPO, "tests", "xcheck", "librsa_xcheck.so")
+    assert os.path.exists(xlib), "build() compiles the tests' cross-check library too"
+    xsyms = subprocess.run(["nm", "-D", "--defined-only", xlib], capture_output=True, text=True, check=True).stdout
+    assert "rsa_xcheck_attention" in xsyms

@@ -1,7 +1,7 @@
 // attn_mma.cu -- CROSS-CHECK implementation of kernel 4 on the legacy mma.sync (HMMA) path.
-// Not the product path: it exists so the tcgen05 kernel (attn_tc5.cu) can be compared against an independent
-// CUDA implementation at full BASELINE.json sizes, where the CPU oracle is too slow.  Selected only through
-// rsa_set_attention_impl(1) by the tests.
+// TEST INFRASTRUCTURE (tests/xcheck/librsa_xcheck.so), not part of the product library: it exists so the tcgen05 kernel
+// (csrc/attn_tc5.cu) can be compared against an independent CUDA implementation at full BASELINE.json sizes, where the
+// CPU oracle is too slow.  Entry point: rsa_xcheck_attention (xcheck_api.cu), driven by tests/xcheck/__init__.py.
 //
 // Same contract as attn_tc5.cu: per 128-row query tile walk the ascending kept-block list, online softmax in
 // fp32 with exp2 (reference rectified_wan21_attn.py:56-105), keys >= kv_len masked to -inf (:86-87), then the

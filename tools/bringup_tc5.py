@@ -16,13 +16,13 @@ dev = torch.device("cuda:0")
 L = native.lib()
 
 
+sys.path.insert(0, os.path.join(REPO, "tests"))
+import xcheck  # noqa: E402  (the tests' mma.sync kernel: its own library)
+
+
 def run(q, k, v, mask, kv_len, impl):
-    ops.set_attention_impl(impl)
-    try:
-        o = ops.masked_attention(q, k, v, mask, kv_len)
-        torch.cuda.synchronize()
-    finally:
-        ops.set_attention_impl(0)
+    o = (ops.masked_attention if impl == 0 else xcheck.masked_attention)(q, k, v, mask, kv_len)
+    torch.cuda.synchronize()
     return o
 
 
@@ -95,14 +95,13 @@ def perf(h, s, dens):
     for impl in (0, 1):
         for _ in range(2):
             run(q, k, v, mask, s, impl)
-        ops.set_attention_impl(impl)
+        fn = ops.masked_attention if impl == 0 else xcheck.masked_attention
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         for _ in range(5):
-            ops.masked_attention(q, k, v, mask, s)
+            fn(q, k, v, mask, s)
         e1.record()
         torch.cuda.synchronize()
-        ops.set_attention_impl(0)
         ms = e0.elapsed_time(e1) / 5
         print(f"  impl {impl}: {ms:.3f} ms (incl. mask->lists)  {pairs * 8388608 / ms / 1e9:.1f} TFLOP/s on kept pairs",
               flush=True)

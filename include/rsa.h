@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RSA_VERSION 104
+#define RSA_VERSION 105
 #define RSA_BLOCK 128
 #define RSA_HEAD_DIM 128
 #define RSA_MAX_ENTRIES 2048 /* max sortable entries per query block: NQ (+1 for the text aggregate) */
@@ -146,6 +146,8 @@ typedef struct rsa_ws_view {
   uint16_t* sched_idx;   /* [BH, NQT, NB] the order kernel 4 walks each list in: for the pair of query tiles (2p, 2p+1)  */
                          /* first the blocks both keep (ascending; K/V tiles loaded once for both), then the rest       */
   int32_t* pair_shared;  /* [BH, ceil(NQT/2)] length of that common prefix                                              */
+  int32_t* quad_shared;  /* [BH, ceil(NQT/2)] how many of those blocks the PARTNER pair of kernel 4's 2-CTA cluster keeps  */
+                         /* as well (they lead the prefix; one K/V tile per cluster, TMA multicast); 0 = no partner       */
 } rsa_ws_view;
 
 /* sizeof(rsa_attn_desc) / sizeof(rsa_prep_desc) / sizeof(rsa_peer_route) as THIS library was compiled: a binding written in

@@ -23,6 +23,13 @@
 //                       P (bf16) -> TMEM over the S columns, handed over in two halves of 64 keys
 //     warp 1 (MMA)      O += P V_j             8 x tcgen05.mma 128x128x16, A = P from TMEM, B = V_j (MN-major)
 // and at the end of a list the slot's warpgroup reads O from TMEM, applies 1/l, R and C and stores bf16 rows.
+//
+// Two CTAs with consecutive grid ids form a CLUSTER (two adjacent pairs of query tiles = four adjacent tiles of a head).
+// The blocks all four tiles keep lead every list (pair_schedule_kernel, rsa_api.cu); over that prefix each K / V tile is
+// fetched from L2 once per cluster: CTA rank r loads the 64-column granule r and MULTICASTS it into both CTAs' rings
+// (cp.async.bulk.tensor ... .multicast::cluster), both CTAs walk the prefix at the same ring positions, and a stage of
+// the prefix is refilled only after both CTAs' MMAs have released it (tcgen05.commit ... .multicast::cluster onto both
+// "empty" barriers).  Behind the prefix the two CTAs are independent again.
 #include <cuda.h>
 #include <math.h>
 #include <stdlib.h>
@@ -110,9 +117,11 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   extern __shared__ __align__(1024) uint8_t smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // which pair of query tiles this CTA works on: attention_grid_slot (rsa_common.cuh) explains the order
+  const int n_pairs = (a.nqt + 1) / 2;
+  const int total_ctas = n_pairs * a.batch * a.heads;
+  if ((int)blockIdx.x >= total_ctas) return;  // the grid is rounded up to whole clusters
   const GridSlot gs = attention_grid_slot((int)blockIdx.x, a.nqt, a.nq_vis, a.batch * a.heads, a.front_text_heads,
                                           (a.dbg_flags & 16) != 0);
-  const int n_pairs = (a.nqt + 1) / 2;
   const int pair = gs.pair, bh = gs.bh, tile0 = gs.tile0, tile1 = gs.tile1;
   const bool repair = gs.repaired;
   const int b = bh / a.heads, h = bh % a.heads;
@@ -128,6 +137,25 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   const int nsh = repair ? min(cnt0, cnt1)
                          : min(max(a.pair_shared[(int64_t)bh * n_pairs + pair], 0), min(cnt0, cnt1));
   const int rounds = max(cnt0, cnt1);
+  // The common prefix of the two partner pairs (pair, pair ^ 1; see the header) is walked by every pair, but only a
+  // cluster that actually holds both partners shares its K / V tiles.  Both CTAs evaluate the SAME expression on the same
+  // words of the workspace -- both pairs' quad counts, pair counts and list lengths -- so they agree on nq4 whatever
+  // those words hold.  (The 64-column and debug instantiations never share.)
+  int nq4 = 0;
+  const int vis_pairs = min(a.nq_vis, a.nqt) / 2;
+  if (kD == 128 && !kDebug && !repair && pair < vis_pairs && (pair ^ 1) < vis_pairs && ((int)blockIdx.x ^ 1) < total_ctas) {
+    const GridSlot gp = attention_grid_slot((int)blockIdx.x ^ 1, a.nqt, a.nq_vis, a.batch * a.heads, a.front_text_heads,
+                                            (a.dbg_flags & 16) != 0);
+    if (!gp.repaired && gp.bh == bh && gp.pair == (pair ^ 1)) {
+      const int64_t prow = (int64_t)bh * a.nqt + gp.tile0;
+      const int pc0 = min(max(a.kept_cnt[prow], 0), a.nb), pc1 = min(max(a.kept_cnt[prow + 1], 0), a.nb);
+      const int pnsh = min(max(a.pair_shared[(int64_t)bh * n_pairs + gp.pair], 0), min(pc0, pc1));
+      const int qa = a.quad_shared[(int64_t)bh * n_pairs + pair], qb = a.quad_shared[(int64_t)bh * n_pairs + gp.pair];
+      if (qa == qb && qa > 0 && qa <= min(nsh, pnsh)) nq4 = qa;
+    }
+  }
+  const int n_quad_tiles = 2 * nq4;  // ring positions [0, 2 nq4): K0, V0, K1, V1, ... of the common prefix
+  const uint32_t cta_rank = nq4 > 0 ? cluster_ctarank() : 0u;
 
   constexpr int kG = kD / 64;                       // granules per Q/K/V tile
   constexpr uint32_t kTileBytes = kG * kGranule;
@@ -158,7 +186,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
     }
     for (int i = 0; i < kStages; ++i) {
       mbar_init(bar(B_KVFULL + i), 1);
-      mbar_init(bar(B_KVEMPTY + i), 1);
+      mbar_init(bar(B_KVEMPTY + i), 2);  // two releases per use: this CTA's and the cluster partner's, or this CTA's twice
     }
     fence_barrier_init();
   }
@@ -170,6 +198,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
+  if (nq4 > 0) cluster_sync_all();  // the partner's barriers exist before anything of this CTA can signal them
 
   if (warp < 4) {
     setmaxnreg_dec<56>();
@@ -218,6 +247,11 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 mbar_wait(bar(B_KVEMPTY + st), ((n / kStages) & 1) ^ 1);
                 if (kDebug && (a.dbg_flags & 2) && n >= kStages) {  // ablation: no K/V traffic after the first fill
                   mbar_arrive(bar(B_KVFULL + st));
+                } else if (n < n_quad_tiles) {
+                  // common prefix of the cluster: this CTA fetches granule `cta_rank` for BOTH CTAs, the partner the other
+                  mbar_arrive_expect_tx(bar(B_KVFULL + st), kTileBytes);
+                  tma_load_4d_multicast(dst + cta_rank * kGranule, map, bar(B_KVFULL + st), 64 * (int)cta_rank, row, h, b,
+                                        (uint16_t)3);
                 } else {
                   mbar_arrive_expect_tx(bar(B_KVFULL + st), kTileBytes);
                   tma_load_4d(dst, map, bar(B_KVFULL + st), 0, row, h, b);
@@ -238,6 +272,18 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
       const bool leader = elect_one();
       int n = 0;
       int st_v0 = 0, par_v0 = 0, st_k0 = 0, par_k0 = 0;  // slot 0's stages of this round (slot 1 re-uses them when shared)
+      int pos_v0 = 0, pos_k0 = 0;                        // ... and their ring positions
+      // Frees the stage used at ring position `pos`: two arrivals complete a phase of its "empty" barrier.  If the stage's
+      // NEXT use (pos + kStages) is a tile of the cluster's common prefix, the partner writes into it too and needs this
+      // CTA's release: one arrival on each CTA's barrier; otherwise the next writer is this CTA alone: both arrivals here.
+      auto release_stage = [&](int st, int pos) {
+        if (pos + kStages < n_quad_tiles) {
+          umma_commit_multicast(bar(B_KVEMPTY + st), (uint16_t)3);
+        } else {
+          umma_commit(bar(B_KVEMPTY + st));
+          umma_commit(bar(B_KVEMPTY + st));
+        }
+      };
       for (int r = 0; r <= rounds; ++r) {
 #pragma unroll
         for (int s = 0; s < 2; ++s) {
@@ -250,8 +296,9 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool reuse = s == 1 && r - 1 < nsh;  // V tile shared with slot 0
             const int st = reuse ? st_v0 : n % kStages;
             const int par = reuse ? par_v0 : (n / kStages) & 1;
+            const int pos = reuse ? pos_v0 : n;
             if (!reuse) ++n;
-            if (s == 0) st_v0 = st, par_v0 = par;
+            if (s == 0) st_v0 = st, par_v0 = par, pos_v0 = pos;
             const bool release = !(s == 0 && r - 1 < nsh);  // the last user frees the stage
             const uint64_t vd = smem_desc_sw128(sbase + kOffRing + st * 2 * kGranule, kGranule);
             RSA_TRACE(dbg && s == 0 && leader, r - 1, 10);
@@ -270,7 +317,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             if (leader) {
 #pragma unroll
               for (int ks = 4; ks < 8; ++ks) umma_ts(tO, tS + ks * 8, vd + 128 * ks, kIdPV, 1u);
-              if (release) umma_commit(bar(B_KVEMPTY + st));
+              if (release) release_stage(st, pos);
               if (r == cnt) umma_commit(bar(B_OFULL + s));
             }
             RSA_TRACE(dbg && s == 0 && leader, r - 1, 11);
@@ -280,8 +327,9 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
             const bool reuse = s == 1 && r < nsh;  // K tile shared with slot 0
             const int st = reuse ? st_k0 : n % kStages;
             const int par = reuse ? par_k0 : (n / kStages) & 1;
+            const int pos = reuse ? pos_k0 : n;
             if (!reuse) ++n;
-            if (s == 0) st_k0 = st, par_k0 = par;
+            if (s == 0) st_k0 = st, par_k0 = par, pos_k0 = pos;
             const bool release = !(s == 0 && r < nsh);
             const uint64_t kd = smem_desc_sw128(sbase + kOffRing + st * 2 * kGranule);
             const uint64_t qd = smem_desc_sw128(sbase + kOffQ + 2 * s * kGranule);
@@ -296,7 +344,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
                 const uint32_t off = (ks >> 2) * (kGranule >> 4) + 2 * (ks & 3);
                 umma_ss(tS, qd + off, kd + off, kIdQK, ks != 0);
               }
-              if (release) umma_commit(bar(B_KVEMPTY + st));
+              if (release) release_stage(st, pos);
               umma_commit(bar(B_SFULL + s));
             }
             RSA_TRACE(dbg && s == 0 && leader, r, 8);
@@ -614,8 +662,20 @@ int launch(dim3 grid, cudaStream_t s, const Maps& m, const AttnArgs& a) {
                                         cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     configured = true;
   }
-  attn_tc5_kernel<kDebug, kPolyPairs, kF16, kD><<<grid, kThreads, kSmemBytes, s>>>(m.q, m.k, m.v, m.qt, m.kt, m.vt, a);
-  RSA_CUDA_CHECK(cudaGetLastError());
+  // clusters of two CTAs (consecutive ids): the grid is rounded up to a whole number of them
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((grid.x + 1) / 2 * 2);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = kSmemBytes;
+  cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  RSA_CUDA_CHECK(cudaLaunchKernelEx(&cfg, attn_tc5_kernel<kDebug, kPolyPairs, kF16, kD>, m.q, m.k, m.v, m.qt, m.kt, m.vt, a));
   return RSA_OK;
 }
 

@@ -123,6 +123,7 @@ WsLayout make_layout(const rsa_attn_desc* d) {
   L.off_C = take((size_t)L.bh * L.nqt * 128 * f);
   L.off_sched = take((size_t)L.bh * L.nqt * L.nb * 2);
   L.off_pshared = take((size_t)L.bh * ((L.nqt + 1) / 2) * 4);
+  L.off_qshared = take((size_t)L.bh * ((L.nqt + 1) / 2) * 4);
   L.ldq = (int)align_up(L.nq > 0 ? L.nq : 1, 4);
   L.ldk = (int)align_up(L.nkc > 0 ? L.nkc : 1, 4);
   L.off_q_pool_t = take((size_t)L.bh * 128 * L.ldq * f);
@@ -192,6 +193,7 @@ static int fill_attn_args(const rsa_attn_desc* d, const void* q, const void* k, 
   a->kept_cnt = (const int32_t*)(ws + L.off_kcnt);
   a->sched_idx = (uint16_t*)(ws + L.off_sched);
   a->pair_shared = (int32_t*)(ws + L.off_pshared);
+  a->quad_shared = (int32_t*)(ws + L.off_qshared);
   a->R = (const float*)(ws + L.off_R);
   a->C = (const float*)(ws + L.off_C);
   a->o_table = nullptr;
@@ -215,67 +217,96 @@ static int launch_attention(const AttnArgs& a, cudaStream_t s, bool reschedule =
   return rc != RSA_OK ? rc : launch_attention_tc5(a, s);
 }
 
-// Pair schedule for kernel 4: query tiles (2p, 2p+1) of a head are processed by one CTA.  Attention over a set of
-// kept blocks does not depend on the order they are visited in, so each list is re-ordered as [blocks both tiles keep,
-// ascending] + [the rest, ascending]; over the common prefix one K tile and one V tile serve both tiles.
+// Schedule for kernel 4.  One CTA of kernel 4 works on a pair of query tiles (2p, 2p+1) of a head; pairs p and p ^ 1 --
+// four adjacent tiles -- are PARTNERS when both consist of whole visual tiles.  Attention over a set of kept blocks does
+// not depend on the order they are visited in, so each tile's list is re-ordered as
+//   [blocks all FOUR tiles of the two partner pairs keep, ascending]   quad_shared counts them: where kernel 4's grid puts
+//                                                 the partners into one 2-CTA cluster, one K / V tile is fetched per
+//                                                 cluster (each CTA loads one 64-column granule and multicasts it)
+//   [other blocks both tiles of the pair keep, ascending]    one K / V tile per CTA serves both of its tiles (pair_shared
+//                                                 counts these and the quad blocks)
+//   [the rest, ascending].
+// The order depends on the head's own lists only -- not on how many heads a call holds or where kernel 4's grid puts the
+// pair -- so a head's result is bit-identical however the heads are split over calls, chunks or GPUs.
 __global__ void __launch_bounds__(128) pair_schedule_kernel(const uint16_t* __restrict__ kept_idx,
                                                             const int32_t* __restrict__ kept_cnt, int nqt, int nb,
-                                                            uint16_t* __restrict__ sched_idx,
-                                                            int32_t* __restrict__ pair_shared) {
-  __shared__ uint32_t bm[2][2048];  // one bit per KV block (nb <= 65535)
-  __shared__ int warp_tot[2][4];
-  __shared__ int n_common;
+                                                            int vis_pairs, int quads_off, uint16_t* __restrict__ sched_idx,
+                                                            int32_t* __restrict__ pair_shared,
+                                                            int32_t* __restrict__ quad_shared) {
+  __shared__ uint32_t bm[4][2048];  // one bit per KV block (nb <= 65535): own tiles 0, 1; partner tiles 2, 3
+  __shared__ int warp_tot[3][4];
+  __shared__ int n_common[2];
   const int pair = blockIdx.x, bh = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int npairs = (nqt + 1) / 2;
+  const bool partner = !quads_off && pair < vis_pairs && (pair ^ 1) < vis_pairs;
   const int64_t row0 = (int64_t)bh * nqt + 2 * pair;
   const bool has1 = 2 * pair + 1 < nqt;
-  const int cnt[2] = {kept_cnt[row0], has1 ? kept_cnt[row0 + 1] : 0};
+  const int64_t prow0 = (int64_t)bh * nqt + 2 * (pair ^ 1);
+  const int cnt[4] = {kept_cnt[row0], has1 ? kept_cnt[row0 + 1] : 0, partner ? kept_cnt[prow0] : 0,
+                      partner ? kept_cnt[prow0 + 1] : 0};
   const int words = (nb + 31) / 32;
-  for (int w = tid; w < words; w += 128) bm[0][w] = bm[1][w] = 0u;
-  if (tid == 0) n_common = 0;
+  for (int w = tid; w < words; w += 128) bm[0][w] = bm[1][w] = bm[2][w] = bm[3][w] = 0u;
+  if (tid < 2) n_common[tid] = 0;
   __syncthreads();
-  for (int t = 0; t < 2; ++t)
+  for (int t = 0; t < 4; ++t) {
+    const uint16_t* src = kept_idx + ((t < 2 ? row0 : prow0) + (t & 1)) * nb;
     for (int i = tid; i < cnt[t]; i += 128) {
-      const int x = kept_idx[(row0 + t) * nb + i];
+      const int x = src[i];
       atomicOr(&bm[t][x >> 5], 1u << (x & 31));
     }
+  }
   __syncthreads();
-  int c = 0;
-  for (int w = tid; w < words; w += 128) c += __popc(bm[0][w] & bm[1][w]);
-  for (int o = 16; o > 0; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
-  if (lane == 0 && c) atomicAdd(&n_common, c);
+  int c2 = 0, c4 = 0;
+  for (int w = tid; w < words; w += 128) {
+    const uint32_t m2 = bm[0][w] & bm[1][w];
+    c2 += __popc(m2);
+    c4 += __popc(m2 & bm[2][w] & bm[3][w]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    c2 += __shfl_xor_sync(0xffffffffu, c2, o);
+    c4 += __shfl_xor_sync(0xffffffffu, c4, o);
+  }
+  if (lane == 0) {
+    if (c2) atomicAdd(&n_common[0], c2);
+    if (c4) atomicAdd(&n_common[1], c4);
+  }
   __syncthreads();
-  const int ncom = n_common;
-  if (tid == 0) pair_shared[(int64_t)bh * npairs + pair] = ncom;
+  const int ncom = n_common[0], nquad = partner ? n_common[1] : 0;
+  if (tid == 0) {
+    pair_shared[(int64_t)bh * npairs + pair] = ncom;
+    quad_shared[(int64_t)bh * npairs + pair] = nquad;
+  }
   for (int t = 0; t < 2; ++t) {
     const uint16_t* src = kept_idx + (row0 + t) * nb;
     uint16_t* dst = sched_idx + (row0 + t) * nb;
-    int base_c = 0, base_r = ncom;  // next output slot among the common / the remaining blocks
+    int base[3] = {0, nquad, ncom};  // next output slot of: quad blocks, other pair-common blocks, the rest
     for (int i0 = 0; i0 < cnt[t]; i0 += 128) {
       const int i = i0 + tid;
       const bool ok = i < cnt[t];
       const int x = ok ? (int)src[i] : 0;
-      const bool com = ok && ((bm[t ^ 1][x >> 5] >> (x & 31)) & 1u);
-      const uint32_t bc = __ballot_sync(0xffffffffu, com), br = __ballot_sync(0xffffffffu, ok && !com);
+      const uint32_t bit = 1u << (x & 31);
+      const bool com = ok && (bm[t ^ 1][x >> 5] & bit);
+      const bool quad = com && partner && (bm[2][x >> 5] & bm[3][x >> 5] & bit);
+      const int cls = !ok ? -1 : (quad ? 0 : (com ? 1 : 2));
+      uint32_t bal[3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) bal[c] = __ballot_sync(0xffffffffu, cls == c);
       if (lane == 0) {
-        warp_tot[0][warp] = __popc(bc);
-        warp_tot[1][warp] = __popc(br);
+#pragma unroll
+        for (int c = 0; c < 3; ++c) warp_tot[c][warp] = __popc(bal[c]);
       }
       __syncthreads();
-      int pc = 0, pr = 0, tc = 0, trm = 0;
-      for (int w = 0; w < 4; ++w) {
-        if (w < warp) {
-          pc += warp_tot[0][w];
-          pr += warp_tot[1][w];
-        }
-        tc += warp_tot[0][w];
-        trm += warp_tot[1][w];
-      }
       const uint32_t below = (1u << lane) - 1u;
-      if (com) dst[base_c + pc + __popc(bc & below)] = (uint16_t)x;
-      else if (ok) dst[base_r + pr + __popc(br & below)] = (uint16_t)x;
-      base_c += tc;
-      base_r += trm;
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        int before = 0, tot = 0;
+        for (int w = 0; w < 4; ++w) {
+          if (w < warp) before += warp_tot[c][w];
+          tot += warp_tot[c][w];
+        }
+        if (cls == c) dst[base[c] + before + __popc(bal[c] & below)] = (uint16_t)x;
+        base[c] += tot;
+      }
       __syncthreads();
     }
   }
@@ -283,8 +314,12 @@ __global__ void __launch_bounds__(128) pair_schedule_kernel(const uint16_t* __re
 
 int launch_pair_schedule(const AttnArgs& a, cudaStream_t s) {
   if (a.nqt == 0) return RSA_OK;
+  const int nqv = a.nq_vis < a.nqt ? a.nq_vis : a.nqt;
+  // attention flag 32 (A/B): no quad prefix at all, i.e. the schedule and the kernel of round 1
+  const int quads_off = (a.dbg_flags & 32) ? 1 : 0;
   dim3 grid((a.nqt + 1) / 2, a.batch * a.heads);
-  pair_schedule_kernel<<<grid, 128, 0, s>>>(a.kept_idx, a.kept_cnt, a.nqt, a.nb, a.sched_idx, a.pair_shared);
+  pair_schedule_kernel<<<grid, 128, 0, s>>>(a.kept_idx, a.kept_cnt, a.nqt, a.nb, nqv / 2, quads_off, a.sched_idx,
+                                            a.pair_shared, a.quad_shared);
   RSA_CUDA_CHECK(cudaGetLastError());
   return RSA_OK;
 }
@@ -383,6 +418,7 @@ extern "C" int rsa_attn_workspace_view(const rsa_attn_desc* d, void* workspace, 
   out->reserved = 0;
   out->sched_idx = (uint16_t*)(ws + L.off_sched);
   out->pair_shared = (int32_t*)(ws + L.off_pshared);
+  out->quad_shared = (int32_t*)(ws + L.off_qshared);
   return RSA_OK;
 }
 
@@ -598,7 +634,7 @@ extern "C" size_t rsa_masked_attention_workspace_bytes(int bh, int nq, int nkv) 
   if (bh <= 0 || nq <= 0 || nkv <= 0) return 0;
   // kept lists + counts + pair schedule + common-prefix lengths
   return 2 * align_up((size_t)bh * nq * nkv * 2, 256) + align_up((size_t)bh * nq * 4, 256) +
-         align_up((size_t)bh * ((nq + 1) / 2) * 4, 256);
+         2 * align_up((size_t)bh * ((nq + 1) / 2) * 4, 256);
 }
 
 extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v, void* out, int bh, int seq_q,
@@ -627,6 +663,7 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   uint16_t* sched = (uint16_t*)(ws + list_bytes);
   int32_t* kcnt = (int32_t*)(ws + 2 * list_bytes);
   int32_t* pshared = (int32_t*)(ws + 2 * list_bytes + align_up((size_t)bh * n_q_blocks * 4, 256));
+  int32_t* qshared = (int32_t*)((char*)pshared + align_up((size_t)bh * ((n_q_blocks + 1) / 2) * 4, 256));
   cudaStream_t s = (cudaStream_t)stream;
   int rc = launch_mask_to_lists(block_mask, bh, n_q_blocks, n_kv_blocks, (kv_len + 127) / 128, kidx, kcnt, s);
   if (rc != RSA_OK) return rc;
@@ -655,6 +692,7 @@ extern "C" int rsa_masked_attention(const void* q, const void* k, const void* v,
   a.kept_cnt = kcnt;
   a.sched_idx = sched;
   a.pair_shared = pshared;
+  a.quad_shared = qshared;
   a.R = nullptr;
   a.C = nullptr;
   a.o_table = nullptr;

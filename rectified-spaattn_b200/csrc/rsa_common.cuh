@@ -33,7 +33,7 @@ struct WsLayout {
   size_t off_q_pool_t, off_q_mad_t, off_k_cat_t, off_k_mad_t;
   int ldq, ldk;
   size_t off_q_pool, off_q_mad, off_k_cat, off_k_mad, off_v_pool, off_scores, off_nogapr, off_probs, off_w,
-      off_mask, off_kidx, off_kcnt, off_nneed, off_R, off_C, off_sched, off_pshared, total;
+      off_mask, off_kidx, off_kcnt, off_nneed, off_R, off_C, off_sched, off_pshared, off_qshared, total;
 };
 
 // Padded ("virtual") layout <-> memory rows.  Visual token t sits at row t in both; the last visual block is completed
@@ -146,6 +146,7 @@ struct AttnArgs {
   const int32_t* kept_cnt;  // [bh, nqt]
   uint16_t* sched_idx;      // [bh, nqt, nb]  pair schedule written by launch_pair_schedule, walked by kernel 4
   int32_t* pair_shared;     // [bh, ceil(nqt/2)]
+  int32_t* quad_shared;     // [bh, ceil(nqt/2)]  blocks the partner pair of the 2-CTA cluster keeps too (lead the prefix)
   const float* R;           // [bh, nqt]  or nullptr (=1)
   const float* C;           // [bh, nqt, 128] or nullptr (=0)
   __nv_bfloat16* const* o_table;  // fused Ulysses scatter: result buffer of every rank (device array) or nullptr

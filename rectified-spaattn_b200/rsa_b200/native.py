@@ -40,7 +40,7 @@ class WsView(C.Structure):
         "q_pool", "q_mad", "k_cat", "k_mad", "v_pool", "scores", "nogapr", "probs", "w_skip", "mask_bits",
         "kept_idx", "kept_cnt", "n_needed", "R", "C")] + [(n, C.c_int32) for n in (
             "nkc", "score_ld", "n_entries", "ent_ld", "mask_words", "nqt", "nogapr_ld", "reserved")] + [
-                ("sched_idx", C.c_void_p), ("pair_shared", C.c_void_p)]
+                ("sched_idx", C.c_void_p), ("pair_shared", C.c_void_p), ("quad_shared", C.c_void_p)]
 
 
 class PrepDesc(C.Structure):
@@ -72,7 +72,7 @@ EXPORTS = [
 _lib = None
 
 
-ABI_VERSION = 104
+ABI_VERSION = 105
 
 
 def lib():

@@ -342,7 +342,8 @@ class Plan:
             n_needed=t(v.n_needed, (bh, max(nq, 1)), torch.int32),
             R=t(v.R, (bh, v.nqt), torch.float32), C=t(v.C, (bh, v.nqt, 128), torch.float32),
             sched_idx=t(v.sched_idx, (bh, v.nqt, nb), torch.int16),
-            pair_shared=t(v.pair_shared, (bh, (v.nqt + 1) // 2), torch.int32))
+            pair_shared=t(v.pair_shared, (bh, (v.nqt + 1) // 2), torch.int32),
+            quad_shared=t(v.quad_shared, (bh, (v.nqt + 1) // 2), torch.int32))
 
     def dense_mask(self):
         """bool [BH, NQT, NB] reconstructed from the kept-block bitmask (the reference's one_hot layout)."""

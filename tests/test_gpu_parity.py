@@ -212,11 +212,17 @@ def test_against_unmodified_reference_on_b200(dev, name, gold_dir):
         assert np.abs(out[t0: t0 + nt] - ref[t0: t0 + nt]).max() <= ATOL_OUT
 
 
-@pytest.mark.parametrize("name", ["wan_c1", "hunyuan_mid", "cog_small", "hunyuan_ragged"])
+@pytest.mark.parametrize("name", ["wan_c1", "hunyuan_mid", "cog_small", "hunyuan_ragged", "wan_300"])
 def test_pair_schedule_is_a_permutation_with_common_prefix(dev, name):
-    """Kernel 4 walks each kept list as [blocks the tile pair (2p, 2p+1) has in common] + [the rest]; the order of
-    blocks does not change the attention result, the common prefix lets one K/V tile serve both tiles."""
-    case = load_case(name)
+    """Kernel 4 walks each kept list as [blocks all four tiles of its 2-CTA cluster keep] + [other blocks the tile pair
+    keeps] + [the rest], each part ascending; the order of blocks does not change the attention result, the common
+    prefixes let one K/V tile serve two tiles (shared-memory stage) or four (TMA multicast across the cluster)."""
+    if name in C.MID_CASES:
+        fam, (t, h, w), nv, s, text_len, ntrue_d, heads, top_k, p, q, k, v = C.mid_case_inputs(name)
+        case = dict(fam=fam, grid=(t, h, w), nv=nv, s=s, text_len=text_len, ntrue_d=ntrue_d, heads=heads, top_k=top_k, p=p,
+                    q=q, k=k, v=v, nbr=GO.gilbert_block_neighbors(t, h, w))
+    else:
+        case = load_case(name)
     plan = _plan(case, dev, dump=False)
     plan.run()
     torch.cuda.synchronize()
@@ -225,20 +231,33 @@ def test_pair_schedule_is_a_permutation_with_common_prefix(dev, name):
     kept = vw["kept_idx"].cpu().numpy().astype(np.int64) & 0xFFFF
     sched = vw["sched_idx"].cpu().numpy().astype(np.int64) & 0xFFFF
     nsh = vw["pair_shared"].cpu().numpy()
+    nquad = vw["quad_shared"].cpu().numpy()
     bh, nqt = cnt.shape
+    npairs = (nqt + 1) // 2
+    nq_vis = plan.desc.nq_blocks if plan.desc.family == 1 else nqt
+    vis_pairs = min(nq_vis, nqt) // 2                      # pairs of whole visual tiles: p and p ^ 1 are partners
+    seen_quads = 0
     for h in range(bh):
-        for t in range(nqt):
-            assert sorted(sched[h, t, : cnt[h, t]]) == list(kept[h, t, : cnt[h, t]])
-        for p in range((nqt + 1) // 2):
-            a = set(kept[h, 2 * p, : cnt[h, 2 * p]])
-            b = set(kept[h, 2 * p + 1, : cnt[h, 2 * p + 1]]) if 2 * p + 1 < nqt else set()
-            n = nsh[h, p]
-            assert n == len(a & b)
-            assert list(sched[h, 2 * p, :n]) == sorted(a & b)
-            if 2 * p + 1 < nqt:
-                assert list(sched[h, 2 * p + 1, :n]) == sorted(a & b)
-                assert list(sched[h, 2 * p + 1, n: cnt[h, 2 * p + 1]]) == sorted(b - a)
-            assert list(sched[h, 2 * p, n: cnt[h, 2 * p]]) == sorted(a - b)
+        for p in range(npairs):
+            t0, t1 = 2 * p, 2 * p + 1
+            sets = [set(kept[h, t, : cnt[h, t]]) if t < nqt else set() for t in (t0, t1)]
+            com = sets[0] & sets[1]
+            quad = set()
+            if p < vis_pairs and (p ^ 1) < vis_pairs:
+                pt0 = 2 * (p ^ 1)
+                quad = com & set(kept[h, pt0, : cnt[h, pt0]]) & set(kept[h, pt0 + 1, : cnt[h, pt0 + 1]])
+                seen_quads += 1
+            assert nsh[h, p] == len(com) and nquad[h, p] == len(quad)
+            for t, mine in zip((t0, t1), sets):
+                if t >= nqt:
+                    continue
+                row = list(sched[h, t, : cnt[h, t]])
+                nq4, n2 = len(quad), len(com)
+                assert row[:nq4] == sorted(quad)
+                assert row[nq4:n2] == sorted(com - quad)
+                assert row[n2:] == sorted(mine - com)
+    if vis_pairs >= 2:
+        assert seen_quads > 0
 
 
 @pytest.mark.parametrize("impl", _impls())

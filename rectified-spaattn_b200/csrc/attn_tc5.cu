@@ -143,7 +143,7 @@ attn_tc5_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__
   // those words hold.  (The 64-column and debug instantiations never share.)
   int nq4 = 0;
   const int vis_pairs = min(a.nq_vis, a.nqt) / 2;
-  if (kD == 128 && !kDebug && !repair && pair < vis_pairs && (pair ^ 1) < vis_pairs && ((int)blockIdx.x ^ 1) < total_ctas) {
+  if (kD == 128 && !kDebug && !(a.dbg_flags & 32) && !repair && pair < vis_pairs && (pair ^ 1) < vis_pairs && ((int)blockIdx.x ^ 1) < total_ctas) {
     const GridSlot gp = attention_grid_slot((int)blockIdx.x ^ 1, a.nqt, a.nq_vis, a.batch * a.heads, a.front_text_heads,
                                             (a.dbg_flags & 16) != 0);
     if (!gp.repaired && gp.bh == bh && gp.pair == (pair ^ 1)) {
@@ -670,7 +670,7 @@ int launch(dim3 grid, cudaStream_t s, const Maps& m, const AttnArgs& a) {
   cfg.stream = s;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = 2;
+  attr[0].val.clusterDim.x = (a.dbg_flags & 32) ? 1 : 2;  // flag 32 (A/B): no clusters, no quad prefix = the round-1 kernel
   attr[0].val.clusterDim.y = 1;
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;

@@ -237,25 +237,34 @@ class ProcessorBase:
     # sparse call of this layer and re-use it in between (`mask_keep` = "lists": R and C are still recomputed from the
     # current tensors; "all": only kernel 4 runs).  1 = the reference's behaviour (a new mask per call).  The cache is
     # dropped whenever `current_step` wraps, i.e. at the start of every generation.
+    # A pipeline that runs classifier-free guidance as two forwards per denoising step calls the processor
+    # `calls_per_step` = 2 times per step (the Wan pipelines: that is why their counter wraps at 100 for 50 steps): every
+    # branch then has its own cache, so the interval counts denoising steps and the unconditional pass is never handed a
+    # selection built from the conditional pass's Q / K.
     mask_refresh_interval = 1
     mask_keep = "lists"
-    _cache = None
+    calls_per_step = 1
+    _caches = None
 
     def _mask_cache(self):
         if self.mask_refresh_interval <= 1:
             return None
-        c = self._cache
+        if self._caches is None or len(self._caches) != self.calls_per_step:
+            self._caches = [None] * self.calls_per_step
+        branch = self.current_step % self.calls_per_step
+        c = self._caches[branch]
         if c is None or c.refresh_every != self.mask_refresh_interval or c.keep != self.mask_keep:
             from rsa_b200 import ops
-            c = self._cache = ops.MaskCache(self.mask_refresh_interval, self.mask_keep)
+            c = self._caches[branch] = ops.MaskCache(self.mask_refresh_interval, self.mask_keep)
         return c
 
     def _tick(self):
         self.current_step += 1
         if self.current_step == self.steps_per_cycle:
             self.current_step = 0
-            if self._cache is not None:
-                self._cache.reset()
+            for c in self._caches or ():
+                if c is not None:
+                    c.reset()
 
 
 class WanProcessorBase(ProcessorBase):
@@ -263,6 +272,7 @@ class WanProcessorBase(ProcessorBase):
     the RoPE convention and the step wrap."""
 
     steps_per_cycle = 100
+    calls_per_step = 2  # conditional + unconditional forward per denoising step
     rope = "complex"  # "complex" (Wan2.1) | "cos_sin" (Wan2.2)
 
     def __init__(self, mode, select_block_num, block_neighbor_list, p_remain_rates, processor_id=0,

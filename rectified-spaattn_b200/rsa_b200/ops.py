@@ -99,9 +99,16 @@ def _device_neighbors(nbr, device):
 
 
 def _workspace(device, nbytes):
-    key = str(device)
+    """Scratch shared by the short-lived Plans of one (device, CUDA stream): calls enqueued on one stream run one after
+    the other and may re-use it; calls on different streams of a device (cond / uncond on parallel streams, threads) each
+    get their own, so kernels of one call never overwrite scores, lists, R or C of another.  A buffer that is outgrown is
+    kept alive until its stream has drained (record_stream) instead of being freed under kernels still using it."""
+    stream = torch.cuda.current_stream(device)
+    key = (str(device), stream.cuda_stream)
     ws = _ws_cache.get(key)
     if ws is None or ws.numel() < nbytes:
+        if ws is not None:
+            ws.record_stream(stream)
         ws = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=device)
         _ws_cache[key] = ws
     return ws

@@ -61,6 +61,27 @@ def test_processor_cache_follows_its_attributes():
     assert p.current_step == 0 and c2.calls == 0 and c2._key is None and not c2.valid
 
 
+def test_processor_cache_is_per_guidance_branch():
+    """The Wan pipelines call a processor twice per denoising step (conditional, unconditional: the reference's counter
+    wraps at 50 * 2, rectified_wan21_attn.py:501): each branch has its own cache, so a refresh interval counts denoising
+    steps and the unconditional pass never runs on a selection built from the conditional pass.  HunyuanVideo (one call
+    per step, wrap at 50, rectified_hunyuan_attn.py:542) has one."""
+    from rectified_spaattn.rectified_hunyuan_attn import RectifiedHunyuanVideoSpaAttnProcessor2_0 as H
+    from rectified_spaattn.rectified_wan21_attn import RectifiedWanT2VSpaAttnProcessor2_0 as W
+    w = W("sparse", 4, None, 0.3)
+    w.mask_refresh_interval = 2
+    seen = []
+    for _ in range(6):
+        seen.append(w._mask_cache())
+        w._tick()
+    assert seen[0] is seen[2] is seen[4] and seen[1] is seen[3] is seen[5] and seen[0] is not seen[1]
+    h = H("sparse", 4, None, 0.3)
+    h.mask_refresh_interval = 2
+    a = h._mask_cache()
+    h._tick()
+    assert h._mask_cache() is a
+
+
 # ----------------------------------------------------------------------------------------------------- GPU parity
 @pytest.fixture(scope="module")
 def dev():

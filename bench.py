@@ -129,8 +129,13 @@ def bind_to_gpu_numa_node(local_rank):
 
 def ncu_traffic(workload):
     """DRAM bytes per launch of kernel 4 from the committed ncu --set full capture of this workload (or None)."""
-    p = os.path.join(REPO, "profiles", f"r01_ncu_summary_{workload}.json")
-    if not os.path.exists(p):
+    # the capture of the shipped kernel (2-CTA clusters, round 2) where there is one, else the round-1 capture of the
+    # workload (same kernel without the multicast prefix: 3 % more DRAM bytes at C3b)
+    cands = [os.path.join(REPO, "profiles", f"r02_ncu_summary_{workload}_kernel4_cluster.json"),
+             os.path.join(REPO, "profiles", f"r02_ncu_summary_{workload}.json"),
+             os.path.join(REPO, "profiles", f"r01_ncu_summary_{workload}.json")]
+    p = next((c for c in cands if os.path.exists(c)), None)
+    if p is None:
         return None
     k = json.load(open(p))["kernels"].get("attn_tc5_kernel", {})
     rd = next((v * (1e9 if "Gbyte" in m else 1e6) for m, v in k.items() if m.startswith("dram__bytes_read.sum")), None)
@@ -756,7 +761,7 @@ def main():
                          "frac_of_sustained_peak": achieved / peaks["bf16_sustained"] if peaks["bf16_sustained"] else None,
                          "flop_per_kept_pair": FLOP_PER_PAIR, "kept_pairs_per_launch": pairs_all // world,
                          "ms_per_launch": t_attn, "traffic": ncu_traffic(args.workload) if world == 1 else None,
-                         "traffic_note": "DRAM read+write bytes of one launch, ncu --set full, profiles/r01_ncu_summary_*.json"},
+                         "traffic_note": "DRAM read+write bytes of one launch, ncu --set full, profiles/r02_ncu_summary_<workload>_kernel4_cluster.json (else the r01 capture)"},
             "clocks": clocks,
         }
         if hbm_kernels:

@@ -353,8 +353,10 @@ void rsa_debug_set_attention_dump(float* device_buffer);
  * garbage; measures the TMA + tensor pipeline alone), bit 1 = no K/V loads after the first ring fill.  Bit 2 is
  * honoured without a dump buffer: head_dim 64 runs through the 128-column instantiation (second granule = TMA zero
  * fill) instead of the 64-column one -- the cross-check and the A/B timing of the two forms; bit 4 likewise: kernel 4's
- * grid in its former order (head by head, no re-pairing of the tail) for A/B timing.  The environment variable
- * RSA_ATTN_FLAGS holds bits for the whole process (OR-ed into whatever this call sets). */
+ * grid in its former order (head by head, no re-pairing of the tail) for A/B timing; bit 5 (32) likewise: kernel 4
+ * launched without thread-block clusters and without the multicast prefix (the round-1 skeleton), the same results
+ * bit for bit, for A/B timing of the clusters.  The environment variable RSA_ATTN_FLAGS holds bits for the whole
+ * process (OR-ed into whatever this call sets). */
 void rsa_debug_set_attention_flags(int flags);
 /* Host-side views of kernel 4's grid order (tests): the (batch*head, pair, tile0, tile1, repaired) CTA `id` of a launch
  * over n_bh heads works on, given the number of last heads whose text pairs go first -- the same inline function the

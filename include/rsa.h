@@ -293,8 +293,9 @@ int rsa_peer_close(void* ptr);
  *                            rank's result buffer.
  * The caller provides the barriers: every rank's sources written before the gather, every rank's scatter finished
  * before the results are read (a zero-byte collective on the stream; rsa_b200/parallel.py uses an all_reduce of one
- * element).  Restrictions: seq == n_ranks * rows_per_rank and heads_total == n_ranks * heads (even shards); prep norm
- * 0, 1, or 2 (2 needs rinv_table).  A ragged visual segment (HunyuanVideo 129
+ * element).  Rank i owns tokens [i * rows_per_rank, min((i + 1) * rows_per_rank, seq)): rows_per_rank = ceil(seq / n_ranks)
+ * when the tokens do not divide (every rank must own at least one; all buffers are laid out for rows_per_rank rows).
+ * Restrictions: heads_total == n_ranks * heads (even head shards); prep norm 0, 1, or 2 (2 needs rinv_table).  A ragged visual segment (HunyuanVideo 129
  * frames) takes two gather calls like rsa_qkv_prep: the visual tokens (dst_row 0) and the text tokens (dst_row = visual
  * token count); the source token of row r is dst_row + r in both. */
 typedef struct rsa_peer_route {

@@ -521,8 +521,11 @@ static int validate_route(const rsa_attn_desc* d, const rsa_peer_route* r, bool 
   if (!r) RSA_FAIL(RSA_ERR_ARG, "peer route is null");
   if (r->n_ranks < 1 || r->n_ranks > RSA_MAX_PEERS || r->rank < 0 || r->rank >= r->n_ranks)
     RSA_FAIL(RSA_ERR_ARG, "peer route: rank %d of %d", r->rank, r->n_ranks);
-  if (r->rows_per_rank < 1 || (int64_t)r->rows_per_rank * r->n_ranks != d->seq)
-    RSA_FAIL(RSA_ERR_ARG, "peer route: %d ranks x %d rows != seq %d", r->n_ranks, r->rows_per_rank, d->seq);
+  // rank i owns tokens [i * rows_per_rank, min((i + 1) * rows_per_rank, seq)): every rank at least one, the last one possibly fewer
+  if (r->rows_per_rank < 1 || (int64_t)r->rows_per_rank * r->n_ranks < d->seq ||
+      (int64_t)r->rows_per_rank * (r->n_ranks - 1) >= d->seq)
+    RSA_FAIL(RSA_ERR_ARG, "peer route: %d ranks x %d rows do not tile seq %d (every rank must own a token)", r->n_ranks,
+             r->rows_per_rank, d->seq);
   if (r->heads_total != r->n_ranks * d->heads) RSA_FAIL(RSA_ERR_ARG, "peer route: heads_total != n_ranks * heads");
   if (need_src && (!r->src_table || r->src_stride[0] < 0 || r->src_stride[1] < r->heads_total * 128 || r->src_stride[0] % 8 || r->src_stride[1] % 8))
     RSA_FAIL(RSA_ERR_ARG, "peer route: source table / strides");

@@ -88,7 +88,8 @@ def _peer_tensor(ptr, shape):
 class FusedUlysses:
     """Ulysses sequence parallelism without data collectives (one process per GPU of one NVSwitch box).
 
-    Every rank owns `rows = S / P` consecutive tokens.  It writes its Q/K/V projection outputs [B, rows, H*128] into
+    Rank r owns the consecutive tokens [r * rows, min((r + 1) * rows, S)), rows = ceil(S / P) (`self.local_rows` of
+    them: the last rank may hold fewer).  It writes its Q/K/V projection outputs [B, local_rows, H*128] into
     peer-visible buffers (`self.q_src`, `self.k_src`, `self.v_src`); `run()` then
       1. barrier (one-element all_reduce: every rank's sources are written),
       2. kernel 0 in gather form: reads, for this rank's H/P heads, every token's rows straight from the owning rank's
@@ -107,10 +108,14 @@ class FusedUlysses:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > 8:
             raise ValueError("at most 8 ranks (one NVSwitch box)")
-        if heads_total % self.world or geo.seq % self.world:
-            raise ValueError("heads and tokens must divide by the number of ranks")
+        if heads_total % self.world:
+            raise ValueError("heads must divide by the number of ranks")
         self.batch, self.heads_total, self.heads = batch, heads_total, heads_total // self.world
-        self.rows, self.seq = geo.seq // self.world, geo.seq
+        self.seq = geo.seq
+        self.rows = -(-geo.seq // self.world)           # rows per rank the buffers are laid out for
+        if self.rows * (self.world - 1) >= geo.seq:
+            raise ValueError("every rank must own at least one token")
+        self.local_rows = min(self.rows, geo.seq - self.rank * self.rows)
         self.device = torch.device("cuda", torch.cuda.current_device())
         L = N.lib()
         self._lib, self._own, self._opened = L, [], []
@@ -140,7 +145,8 @@ class FusedUlysses:
                     table[t, r] = pp.value
         self._table = table.to(self.device)
         shape = (batch, self.rows, heads_total * 128)
-        self.q_src, self.k_src, self.v_src, self.out = (_peer_tensor(p, shape) for p in self._own[:4])
+        # views of this rank's own rows (the buffers themselves hold `rows` rows on every rank)
+        self.q_src, self.k_src, self.v_src, self.out = (_peer_tensor(p, shape)[:, :self.local_rows] for p in self._own[:4])
         self._flag = torch.zeros(1, device=self.device)
         q, k, v = (torch.empty(batch, self.heads, self.seq, 128, dtype=torch.bfloat16, device=self.device)
                    for _ in range(3))
@@ -175,9 +181,16 @@ class FusedUlysses:
                 p.norm = 2
                 st2 = (C.c_int64 * 2)(self.rows * self.heads_total * 128, self.heads_total * 128)
                 with torch.cuda.device(self.device):
-                    N.check(self._lib.rsa_row_rms(self._own[0], self._own[1], self.batch, self.rows,
-                                                  self.heads_total * 128, st2, st2, float(eps), self._own[4],
-                                                  self._own[5], ops._stream(self.device)), "rsa_row_rms")
+                    # the statistics buffers are [batch, rows] like every peer buffer; rsa_row_rms packs its output as
+                    # [batch, its row count], so a short last shard is done one batch element at a time
+                    even = self.local_rows == self.rows
+                    for b in range(1 if even else self.batch):
+                        off = b * self.rows
+                        N.check(self._lib.rsa_row_rms(self._own[0] + off * self.heads_total * 256,
+                                                      self._own[1] + off * self.heads_total * 256,
+                                                      self.batch if even else 1, self.local_rows, self.heads_total * 128,
+                                                      st2, st2, float(eps), self._own[4] + off * 4, self._own[5] + off * 4,
+                                                      ops._stream(self.device)), "rsa_row_rms")
             elif any(w.numel() != 128 for w in ws_):
                 raise RuntimeError("norm weights must have 128 (per head) or heads*128 (across heads) elements")
         if rope is not None:

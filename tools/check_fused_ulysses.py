@@ -23,15 +23,18 @@ rank, world, lrank = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int
 torch.cuda.set_device(lrank)
 dev = torch.device("cuda", lrank)
 dist.init_process_group("nccl", device_id=dev)
+if name == "odd":
+    # tokens that do NOT divide by the ranks (Wan form, 5 x 9 x 23 = 1035 tokens, 4 heads): the last rank owns fewer rows
+    bench.WORKLOADS["odd"] = dict(desc="uneven token shards", fam="wan", grid=(5, 9, 23), text=0, text_valid=0, heads=4,
+                                  drop=0.6, ffb=True)
 wp = bench.workload_params(name)
 heads, s, nv = wp["heads"], wp["s"], wp["nv"]
-if name == "small":
-    pass
 geo = bench.product_geometry(wp)
 t, h, w = wp["grid"]
 nbr = ops.gilbert_block_neighbors(t, h, w)
-rows, hl = s // world, heads // world
-assert rows * world == s and hl * world == heads, "tokens and heads must divide by the ranks"
+rows, hl = -(-s // world), heads // world          # rows per rank (the last rank may own fewer)
+even = rows * world == s
+assert hl * world == heads, "heads must divide by the ranks"
 g = torch.Generator(device=dev).manual_seed(1234)                       # same stream on every rank: the full tensors
 full = [torch.randn(1, s, heads * 128, generator=g, device=dev).to(torch.bfloat16) for _ in range(3)]
 if wp["fam"] != "wan":                                                   # give the pooled scores some structure
@@ -44,7 +47,7 @@ wq = (1 + 0.1 * torch.randn(nw, generator=g, device=dev)).to(torch.bfloat16)
 wk = (1 + 0.1 * torch.randn(nw, generator=g, device=dev)).to(torch.bfloat16)
 ang = torch.outer(torch.arange(nv, dtype=torch.float32, device=dev), 1.0 / (256.0 ** (torch.arange(0, 128, 2, device=dev) / 128)))
 rope = (ang.cos().repeat_interleave(2, 1).contiguous(), ang.sin().repeat_interleave(2, 1).contiguous())
-mine = slice(rank * rows, (rank + 1) * rows)
+mine = slice(rank * rows, min((rank + 1) * rows, s))
 
 fu = parallel.FusedUlysses(1, heads, geo, wp["top_k"], bench.P_REMAIN, nbr)
 for dst, src in zip((fu.q_src, fu.k_src, fu.v_src), full):
@@ -84,14 +87,15 @@ def nccl_form():
     return parallel.head_to_seq_shard(o).reshape(1, rows, heads * 128)
 
 
-ref = nccl_form().clone()
+# (the NCCL form below is written for even shards; with uneven ones the single-GPU call is the only reference)
+ref = nccl_form().clone() if even else out
 torch.cuda.synchronize()
 # Wan: the NCCL form's norm is PyTorch's (other reduction order: a bf16 rounding may flip, and with it a block selection),
 # so it is a timing reference there, not a bit reference -- the bit reference is the single-GPU call below
 same_as_nccl = bool(torch.equal(out.view(torch.int16), ref.view(torch.int16)))
 frac_equal_nccl = float((out.view(torch.int16) == ref.view(torch.int16)).float().mean())
 same_as_single = None
-if check and rank == 0:
+if check and (rank == 0 or not even):       # uneven shards: every rank checks its own rows (the shapes are small)
     # one GPU, all heads, no exchange at all
     qa, ka, va = (torch.empty(1, heads, s, 128, dtype=torch.bfloat16, device=dev) for _ in range(3))
     pa = ops.Plan(qa, ka, va, geo, wp["top_k"], bench.P_REMAIN, nbr)
@@ -124,9 +128,11 @@ def timed(fn, n=10):
 
 
 ms_fused = timed(lambda: fu.run(wq, wk, 1e-6, rope, nv))
-ms_nccl = timed(nccl_form)
+ms_nccl = timed(nccl_form) if even else None
 oks = [None] * world
 dist.all_gather_object(oks, same_as_nccl)
+singles = [None] * world
+dist.all_gather_object(singles, same_as_single)
 if rank == 0:
     print(json.dumps({"workload": name, "n_gpus": world, "tokens": s, "heads": heads,
                       "fused_ms_per_layer_attention": ms_fused, "nccl_all_to_all_form_ms": ms_nccl,
@@ -134,6 +140,8 @@ if rank == 0:
                       "fused_equals_nccl_form_bitwise_all_ranks": all(oks),
                       "fraction_of_elements_equal_to_nccl_form_rank0": frac_equal_nccl,
                       "fused_equals_single_gpu_bitwise_rank0": same_as_single,
+                      "fused_equals_single_gpu_bitwise_checked_ranks": [x for x in singles if x is not None],
+                      "rows_per_rank": rows, "rows_last_rank": s - (world - 1) * rows,
                       "note": "both forms run kernel 0 + kernels 3a-4; fused = gather inside kernel 0 and scatter inside "
                               "kernel 4's epilogue over peer memory, barriers only; nccl = all_to_all_single x4 + staging copies"}))
 fu.close()

@@ -355,8 +355,8 @@ void rsa_debug_set_attention_dump(float* device_buffer);
  * honoured without a dump buffer: head_dim 64 runs through the 128-column instantiation (second granule = TMA zero
  * fill) instead of the 64-column one -- the cross-check and the A/B timing of the two forms; bit 4 likewise: kernel 4's
  * grid in its former order (head by head, no re-pairing of the tail) for A/B timing; bit 5 (32) likewise: kernel 4
- * launched without thread-block clusters and without the multicast prefix (the round-1 skeleton), the same results
- * bit for bit, for A/B timing of the clusters.  The environment variable RSA_ATTN_FLAGS holds bits for the whole
+ * launched without thread-block clusters and without the multicast prefix (the round-1 skeleton; the kept lists are then
+ * walked in another order, so results agree within the output bar, not bit for bit), for A/B timing of the clusters.  The environment variable RSA_ATTN_FLAGS holds bits for the whole
  * process (OR-ed into whatever this call sets). */
 void rsa_debug_set_attention_flags(int flags);
 /* Host-side views of kernel 4's grid order (tests): the (batch*head, pair, tile0, tile1, repaired) CTA `id` of a launch

@@ -1,5 +1,5 @@
-"""Kernel 4's grid order with many heads (runs last: it is the newest GPU test, written when session 6's GPU budget was
-nearly spent -- its block-aligned case ran once on a B200, its ragged case has not run yet)."""
+"""Kernel 4 with many heads: the grid order (in-order branch of the decode, re-paired tail) and the 2-CTA clusters with
+their multicast prefix, each against the form it replaced and against the independent mma.sync kernel."""
 import os
 import sys
 
@@ -73,6 +73,44 @@ def test_grid_order_with_many_heads(dev, grid, text):
         assert bool((d <= ATOL_OUT + 2.0 ** -7 * ref_all.float().abs()).all()), f"tcgen05 vs mma.sync max-abs {float(d.max()):.4f}"
         cos = float(torch.nn.functional.cosine_similarity(out.float().flatten(), ref_all.float().flatten(), dim=0))
         assert cos >= 0.9999
+
+
+def test_clusters_against_the_kernel_without_them(dev):
+    """Two CTAs with consecutive grid ids form a cluster and fetch the blocks four adjacent query tiles share once (TMA
+    multicast, releases multicast onto both rings).  Attention flag 32 launches the same kernel without clusters and
+    schedules the lists without the quad prefix (the round-1 skeleton): the same kept sets walked in another order, so
+    the outputs agree within the output bar plus an ulp, and the cluster form must also agree with the mma.sync kernel.
+    24 heads x 64 visual blocks, top_k 32: long common prefixes, partner CTAs of different list lengths, the odd pair at
+    the end of a head whose partner belongs to the next head (no sharing there)."""
+    from rsa_b200 import geometry as G
+    from rsa_b200 import ops
+    import xcheck
+    bench = _bench()
+    t, h, w, text = 8, 32, 32, 256
+    nv, heads, top_k = t * h * w, 24, 32
+    s = nv + text
+    geo = G.hunyuan(s, nv + 200, text)
+    nbr = ops.gilbert_block_neighbors(t, h, w)
+    q, k, v = bench.synth_heads_device(heads, 0, s, "walk", dev, seed=5)
+    plan = ops.Plan(q, k, v, geo, top_k, 0.3, nbr, private_workspace=True)
+    out = plan.run().clone()
+    torch.cuda.synchronize()
+    vw = plan.view()
+    assert int(vw["quad_shared"].max().item()) >= 8, "the case must exercise the multicast prefix"
+    ops.set_attention_flags(32)
+    try:
+        plain = plan.run().clone()
+        torch.cuda.synchronize()
+    finally:
+        ops.set_attention_flags(0)
+    d = (out.float() - plain.float()).abs()
+    assert bool((d <= ATOL_OUT + 2.0 ** -6 * plain.float().abs()).all()), f"clusters vs none: max-abs {float(d.max()):.4f}"
+    assert float(torch.nn.functional.cosine_similarity(out.float().flatten(), plain.float().flatten(), dim=0)) >= 0.9999
+    plan.run()
+    ref_all = xcheck.sparse_attention(plan)
+    torch.cuda.synchronize()
+    d = (out.float() - ref_all.float()).abs()
+    assert bool((d <= ATOL_OUT + 2.0 ** -7 * ref_all.float().abs()).all()), f"tcgen05 vs mma.sync max-abs {float(d.max()):.4f}"
 
 
 def test_selection_with_power_of_two_visual_blocks(dev):

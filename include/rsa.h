@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define RSA_VERSION 105
+#define RSA_VERSION 106
 #define RSA_BLOCK 128
 #define RSA_HEAD_DIM 128
 #define RSA_MAX_ENTRIES 2048 /* max sortable entries per query block: NQ (+1 for the text aggregate) */
@@ -295,13 +295,17 @@ int rsa_peer_close(void* ptr);
  * before the results are read (a zero-byte collective on the stream; rsa_b200/parallel.py uses an all_reduce of one
  * element).  Rank i owns tokens [i * rows_per_rank, min((i + 1) * rows_per_rank, seq)): rows_per_rank = ceil(seq / n_ranks)
  * when the tokens do not divide (every rank must own at least one; all buffers are laid out for rows_per_rank rows).
- * Restrictions: heads_total == n_ranks * heads (even head shards); prep norm 0, 1, or 2 (2 needs rinv_table).  A ragged visual segment (HunyuanVideo 129
+ * This rank computes heads [head0, head0 + desc->heads) of the heads_total heads; the shards need not be even (12 heads
+ * on 8 ranks: 2,2,2,2,1,1,1,1), every rank states its own first head and its own count.  Prep norm 0, 1, or 2 (2 needs
+ * rinv_table).  A ragged visual segment (HunyuanVideo 129
  * frames) takes two gather calls like rsa_qkv_prep: the visual tokens (dst_row 0) and the text tokens (dst_row = visual
  * token count); the source token of row r is dst_row + r in both. */
 typedef struct rsa_peer_route {
   int32_t n_ranks, rank;
   int32_t rows_per_rank;
-  int32_t heads_total;          /* n_ranks * desc->heads                                                          */
+  int32_t heads_total;          /* heads of the host model = channels / 128 of the source and result rows          */
+  int32_t head0;                /* this rank's first head: it computes heads [head0, head0 + desc->heads)          */
+  int32_t reserved;             /* 0                                                                               */
   const void* const* src_table; /* DEVICE array [3][n_ranks] (q, k, v): every rank's projection output,           */
                                 /* [batch, rows_per_rank, heads_total*128] bf16, as mapped in THIS process          */
   int64_t src_stride[2];        /* (batch, token) element strides of those buffers                                 */

@@ -906,7 +906,7 @@ int launch_qkv_prep(const rsa_prep_desc* p, const rsa_attn_desc* d, const void* 
     pa.rinv_table = route->rinv_table;
     pa.n_src = route->n_ranks;
     pa.src_rows = route->rows_per_rank;
-    pa.src_head0 = route->rank * d->heads;
+    pa.src_head0 = route->head0;
     for (int t = 0; t < 3; ++t) {
       pa.src_stride[t][0] = route->src_stride[0];
       pa.src_stride[t][1] = route->src_stride[1];

@@ -526,7 +526,8 @@ static int validate_route(const rsa_attn_desc* d, const rsa_peer_route* r, bool 
       (int64_t)r->rows_per_rank * (r->n_ranks - 1) >= d->seq)
     RSA_FAIL(RSA_ERR_ARG, "peer route: %d ranks x %d rows do not tile seq %d (every rank must own a token)", r->n_ranks,
              r->rows_per_rank, d->seq);
-  if (r->heads_total != r->n_ranks * d->heads) RSA_FAIL(RSA_ERR_ARG, "peer route: heads_total != n_ranks * heads");
+  if (r->head0 < 0 || d->heads < 1 || r->head0 + d->heads > r->heads_total)
+    RSA_FAIL(RSA_ERR_ARG, "peer route: heads [%d, %d) outside the %d heads of a row", r->head0, r->head0 + d->heads, r->heads_total);
   if (need_src && (!r->src_table || r->src_stride[0] < 0 || r->src_stride[1] < r->heads_total * 128 || r->src_stride[0] % 8 || r->src_stride[1] % 8))
     RSA_FAIL(RSA_ERR_ARG, "peer route: source table / strides");
   if (need_out && (!r->out_table || r->out_stride[0] < 0 || r->out_stride[1] < r->heads_total * 128 || r->out_stride[0] % 8 || r->out_stride[1] % 8))
@@ -589,7 +590,7 @@ extern "C" int rsa_rectified_attention_pooled_scatter(const rsa_attn_desc* d, co
   fill_attn_args(d, q, k, v, nullptr, ws, L, &a);
   a.o_table = (__nv_bfloat16* const*)route->out_table;
   a.peer_rows = route->rows_per_rank;
-  a.peer_head0 = route->rank * d->heads;
+  a.peer_head0 = route->head0;
   a.peer_os[0] = route->out_stride[0];
   a.peer_os[1] = route->out_stride[1];
   return launch_attention(a, s);

@@ -52,7 +52,7 @@ class PrepDesc(C.Structure):
 
 class PeerRoute(C.Structure):
     _fields_ = [("n_ranks", C.c_int32), ("rank", C.c_int32), ("rows_per_rank", C.c_int32), ("heads_total", C.c_int32),
-                ("src_table", C.c_void_p), ("src_stride", C.c_int64 * 2), ("out_table", C.c_void_p),
+                ("head0", C.c_int32), ("reserved", C.c_int32), ("src_table", C.c_void_p), ("src_stride", C.c_int64 * 2), ("out_table", C.c_void_p),
                 ("out_stride", C.c_int64 * 2), ("rinv_table", C.c_void_p)]
 
 
@@ -72,7 +72,7 @@ EXPORTS = [
 _lib = None
 
 
-ABI_VERSION = 105
+ABI_VERSION = 106
 
 
 def lib():

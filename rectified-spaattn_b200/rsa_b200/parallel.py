@@ -108,9 +108,14 @@ class FusedUlysses:
         self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
         if self.world > 8:
             raise ValueError("at most 8 ranks (one NVSwitch box)")
-        if heads_total % self.world:
-            raise ValueError("heads must divide by the number of ranks")
-        self.batch, self.heads_total, self.heads = batch, heads_total, heads_total // self.world
+        if heads_total < self.world:
+            raise ValueError("every rank must compute at least one head")
+        # heads need not divide by the ranks: the first (H mod P) ranks take one head more (12 heads on 8 ranks:
+        # 2,2,2,2,1,1,1,1); this rank computes heads [head0, head0 + heads)
+        base, extra = divmod(heads_total, self.world)
+        self.batch, self.heads_total = batch, heads_total
+        self.heads = base + (1 if self.rank < extra else 0)
+        self.head0 = self.rank * base + min(self.rank, extra)
         self.seq = geo.seq
         self.rows = -(-geo.seq // self.world)           # rows per rank the buffers are laid out for
         if self.rows * (self.world - 1) >= geo.seq:
@@ -153,6 +158,7 @@ class FusedUlysses:
         self.plan = ops.Plan(q, k, v, geo, top_k, p_remain, nbr, private_workspace=True)
         route = N.PeerRoute()
         route.n_ranks, route.rank, route.rows_per_rank, route.heads_total = self.world, self.rank, self.rows, heads_total
+        route.head0 = self.head0
         route.src_table = self._table[:3].data_ptr()
         route.out_table = self._table[3].data_ptr()
         route.src_stride[0], route.src_stride[1] = self.rows * heads_total * 128, heads_total * 128

@@ -640,15 +640,15 @@ def test_fused_ulysses_two_gpus(dev):
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
     assert line["fused_equals_nccl_form_bitwise_all_ranks"] and line["fused_equals_single_gpu_bitwise_rank0"]
-    # tokens that do not divide by the ranks (1035 tokens on 2 ranks: 518 + 517), Wan form: every rank's rows bit-identical
-    # to the single-GPU call
+    # tokens and heads that do not divide by the ranks (1035 tokens on 2 ranks: 518 + 517; 3 heads: 2 + 1), Wan form:
+    # every rank's rows bit-identical to the single-GPU call
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                         "--master-addr", "127.0.0.1", "--master-port", "29579",
                         os.path.join(repo, "tools", "check_fused_ulysses.py"), "odd"],
                        capture_output=True, text=True, timeout=600)
     assert r.returncode == 0, r.stderr[-2000:]
     line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
-    assert line["rows_last_rank"] < line["rows_per_rank"]
+    assert line["rows_last_rank"] < line["rows_per_rank"] and line["heads_rank0"] == 2
     assert line["fused_equals_single_gpu_bitwise_checked_ranks"] == [True, True]
 
 
